@@ -1,0 +1,346 @@
+#!/usr/bin/env python
+"""bench.py — node-expansions/sec of the B200 expansion engine (and of the reference CPU path).
+
+A "step" is one pass of the hot path (batched env_map::get_succ) over one batch of
+synthetic frontier nodes.  Default workload: the north_star target — 512^3 voxel map @0.1 m,
+3-D ACC control, 27 primitives per node (BASELINE.json metric "on 512^3 voxel map").
+
+  python bench.py --gpus 1 --steps K --warmup W [--workload 512c_acc27|cfg2|cfg3|cfg4]
+  python bench.py --impl reference ...      # the reference's CPU path (oracle) on the host cores
+
+Prints ONE JSON line (rank 0).  See DESIGN.md §Measurement for the definition of every key.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+METRIC = "node-expansions/sec (frontier x |U| primitives validated+costed) on 512^3 voxel map"
+UNIT = "expansions/s"
+S_IN = 112  # bytes of one frontier node (3-D Waypoint payload)
+S_OUT = 132  # bytes of one successor record: 112 Waypoint + 8 cost + 4 action + 8 key
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="512c_acc27")
+    ap.add_argument("--nodes", type=int, default=1 << 18, help="frontier nodes per step per GPU")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline leg")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+def make_env(sc, device):
+    from motion_primitive_library_b200 import MapUtil, env_map
+
+    mu = MapUtil()
+    mu.setMap(sc.origin, sc.dim_cells, sc.grid(), sc.res)
+    e = env_map(mu, device=device)
+    e.set_control(sc.control)
+    e.set_u(sc.U)
+    e.set_dt(sc.T)
+    e.set_w(sc.w)
+    e.set_wyaw(sc.wyaw)
+    e.set_v_max(sc.v_max)
+    e.set_a_max(sc.a_max)
+    e.set_j_max(sc.j_max)
+    e.set_yaw_max(sc.yaw_max)
+    if sc.potential() is not None:
+        e.set_potential_weight(sc.potential_weight)
+        e.set_gradient_weight(sc.gradient_weight)
+        e.set_potential_map(sc.potential())
+    e._sync_params()
+    return e
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index=0):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+        self.idx = gpu_index
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                       "-lms", "100", "-i", str(self.idx)], stdout=self.f, stderr=subprocess.DEVNULL)
+        except OSError:
+            self.p = None
+
+    def stop(self):
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.p.kill()
+        self.f.flush()
+        rows = [r.split(",") for r in Path(self.f.name).read_text().strip().splitlines() if r.count(",") >= 8]
+        os.unlink(self.f.name)
+        if not rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        sm = sorted(float(r[1]) for r in rows)
+        reasons = set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in rows:
+            for k, nm in enumerate(names):
+                if r[5 + k].strip().lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(rows[0][2]), "samples": len(rows),
+                "power_w_max": max(float(r[3]) for r in rows), "reasons": sorted(reasons)}
+
+
+def algorithmic_bytes(nU, mean_samples_per_node, mean_succ_per_node, has_region):
+    """B = S_in + sum_samples*b_vox + N_succ*S_out per expansion."""
+    b_vox = 1.0 + (0.125 if has_region else 0.0)
+    return S_IN + mean_samples_per_node * b_vox + mean_succ_per_node * S_OUT
+
+
+def cpu_reference(sc, nodes, threads, budget_s):
+    """Time the reference's CPU path (the oracle restatement, or oracle/_ref when built) on a bounded sample."""
+    sys.path.insert(0, str(ROOT / "tests"))
+    import oracle_bindings as ob
+
+    env = ob.OracleEnv.from_scenario(sc)
+    probe = nodes[: min(len(nodes), 256 * threads)]
+    t = env.timed(probe, nthreads=threads)
+    rate = len(probe) / max(t["seconds"], 1e-9)
+    n = int(min(len(nodes), max(len(probe), rate * budget_s)))
+    t = env.timed(nodes[:n], nthreads=threads)
+    return dict(rate=n / t["seconds"], n=n, seconds=t["seconds"], samples=t["samples"], successors=t["successors"])
+
+
+def run_reference(args, sc, rank, world):
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    nodes = sc.frontier(max(4096, 512 * threads), seed=7)
+    sys.path.insert(0, str(ROOT / "tests"))
+    import oracle_bindings as ob
+
+    env = ob.OracleEnv.from_scenario(sc)
+    # size a step at ~1.5 s of all-core CPU work
+    t = env.timed(nodes[: 128 * threads], nthreads=threads)
+    per_step = int(max(64 * threads, min(1 << 20, 1.5 * 128 * threads / max(t["seconds"], 1e-9))))
+    if per_step > len(nodes):
+        nodes = sc.frontier(per_step, seed=7)
+    batch = nodes[:per_step]
+    for _ in range(args.warmup):
+        env.timed(batch, nthreads=threads)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        env.timed(batch, nthreads=threads)
+    dt = time.perf_counter() - t0
+    v = per_step * args.steps / dt
+    line = {
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": sc.name, "nodes_per_step": per_step, "primitives_per_node": sc.nU},
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
+                         "sample": f"{per_step} frontier nodes/step x {args.steps} steps, oracle restatement of "
+                                   f"env_map::get_succ, g++ -O2 no-FMA, {threads} std::threads"},
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    from motion_primitive_library_b200 import scenarios as S
+
+    sc = S.WORKLOADS[args.workload]()
+    if args.impl == "reference":
+        run_reference(args, sc, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+
+    from motion_primitive_library_b200 import abi
+    from motion_primitive_library_b200.abi import SuccOut, WAYPOINT_DTYPE
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the expansion engine has no CPU fallback "
+                         "(use --impl reference for the CPU path)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    lib = abi.load()
+
+    # ---- inputs: every rank holds the full map (replica) and its own slice of the frontier ----
+    env = make_env(sc, local)
+    n, nU = args.nodes, sc.nU
+    nodes_np = sc.frontier(n, seed=7 + rank)
+    slots = n * nU
+
+    # measured algorithmic bytes (untimed stats pass)
+    d_nodes = torch.from_numpy(nodes_np.view(np.uint8).reshape(n, 112)).cuda()
+    d_count = torch.empty(n, dtype=torch.int32, device="cuda")
+    d_succ = torch.empty((slots, 112), dtype=torch.uint8, device="cuda")
+    d_cost = torch.empty(slots, dtype=torch.float64, device="cuda")
+    d_action = torch.empty(slots, dtype=torch.int32, device="cuda")
+    d_key = torch.empty(slots, dtype=torch.int64, device="cuda")
+    out_d = SuccOut(d_count.data_ptr(), d_succ.data_ptr(), d_cost.data_ptr(), d_action.data_ptr(), d_key.data_ptr(), None)
+    stream = torch.cuda.current_stream()
+
+    def step_device():
+        abi.check(lib.mplx_expand_device(env.handle, d_nodes.data_ptr(), n, C.byref(out_d), stream.cuda_stream))
+
+    env.enable_stats(True)
+    step_device()
+    torch.cuda.synchronize()
+    samples, succ_total = env.last_stats()
+    env.enable_stats(False)
+    mean_samples, mean_succ = samples / n, succ_total / n
+    bytes_per_exp = algorithmic_bytes(nU, mean_samples, mean_succ, False)
+
+    launches0 = env.launch_count()
+    for _ in range(args.warmup):
+        step_device()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    torch.cuda.synchronize()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    ev[0].record(stream)
+    for k in range(args.steps):
+        step_device()
+        ev[k + 1].record(stream)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    elapsed_ms = ev[0].elapsed_time(ev[-1])
+    kernel_ms = [ev[k].elapsed_time(ev[k + 1]) for k in range(args.steps)]
+    gpu_launches = env.launch_count() - launches0 - args.warmup
+    t_el = torch.tensor([elapsed_ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t_el, op=dist.ReduceOp.MAX)
+    elapsed_ms = float(t_el.item())
+    value = world * n * args.steps / (elapsed_ms * 1e-3)
+
+    # ---- e2e: the reference-facing C-ABI call with HOST (pinned) buffers, copies inside the timed region
+    e2e = None
+    if not args.no_e2e:
+        h_nodes = env._pinned_empty(n, WAYPOINT_DTYPE)
+        h_nodes[:] = nodes_np
+        h_count = env._pinned_empty(n, np.int32)
+        h_succ = env._pinned_empty(slots, WAYPOINT_DTYPE)
+        h_cost = env._pinned_empty(slots, np.float64)
+        h_action = env._pinned_empty(slots, np.int32)
+        h_key = env._pinned_empty(slots, np.uint64)
+        out_h = SuccOut(h_count.ctypes.data, h_succ.ctypes.data, h_cost.ctypes.data, h_action.ctypes.data,
+                        h_key.ctypes.data, None)
+
+        def step_host():
+            abi.check(lib.mplx_expand(env.handle, h_nodes.ctypes.data, n, C.byref(out_h)))
+
+        e2e_steps = max(3, min(args.steps, 10))
+        for _ in range(2):
+            step_host()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        l0 = env.launch_count()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            step_host()
+        torch.cuda.synchronize()
+        t1 = time.perf_counter()
+        e2e_launches = env.launch_count() - l0
+        t_e = torch.tensor([t1 - t0], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t_e, op=dist.ReduceOp.MAX)
+        checksum = int(h_count.sum())  # the step's result is read on the host
+        assert checksum == succ_total, (checksum, succ_total)
+        e2e = {"value": world * n * e2e_steps / float(t_e.item()), "unit": UNIT,
+               "h2d_bytes_per_step": int(n * 112),
+               "d2h_bytes_per_step": int(n * 4 + slots * (112 + 8 + 4 + 8)),
+               "steps": e2e_steps, "ms_per_step": 1e3 * float(t_e.item()) / e2e_steps,
+               "launches": int(e2e_launches), "buffers": "pinned host (mplx_host_alloc), full 132 B successor records"}
+        gpu_launches += 0  # e2e launches reported separately above
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peaks = {}
+    pk = ROOT / "MEASURED_PEAKS.json"
+    if pk.exists():
+        peaks = json.loads(pk.read_text())
+    peak_gbs = float(peaks.get("hbm_gbs", 6650.0))
+    k_ms = float(np.mean(kernel_ms))
+    achieved = bytes_per_exp * n / (k_ms * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s", "frac": achieved / peak_gbs,
+                "traffic": None, "peak_source": "measured" if pk.exists() else "fallback",
+                "kernel": "mplx::expand_kernel", "kernel_ms": k_ms,
+                "algorithmic_bytes_per_expansion": bytes_per_exp,
+                "mean_samples_per_expansion": mean_samples, "mean_successors_per_expansion": mean_succ}
+    prof = ROOT / "profiles" / "traffic.json"
+    if prof.exists():
+        try:
+            tr = json.loads(prof.read_text()).get(sc.name)
+            if tr:
+                roofline["traffic"] = tr["dram_bytes_per_launch"] * n / tr["nodes_per_launch"]
+        except Exception:
+            pass
+
+    cpu_baseline = None
+    if world == 1 and not args.no_cpu_baseline:
+        threads = os.cpu_count() or 1
+        r = cpu_reference(sc, nodes_np, threads, args.cpu_seconds)
+        cpu_baseline = {"value": r["rate"], "unit": UNIT, "cores": threads, "kind": "port",
+                        "sample": f"first {r['n']} of the same frontier nodes, {r['seconds']:.1f} s, oracle "
+                                  f"restatement of env_map::get_succ (g++ -O2, no FMA), {threads} std::threads"}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": sc.name, "map": "x".join(str(d) for d in sc.dim_cells) + f" @{sc.res} m int8",
+                   "control": f"0x{sc.control:02x}", "primitives_per_node": nU, "nodes_per_step_per_gpu": n,
+                   "primitives_per_sec": value * nU, "parallelism": f"replicas x{world}, frontier sharded",
+                   "l2": f"per-step working set {(n * 112 + slots * 132 + int(np.prod(sc.dim_cells))) / 1e6:.0f} MB "
+                         f"(frontier + successor records + map) exceeds the 126 MB L2"},
+        "clocks": clocks, "e2e": e2e, "gpu_launches": int(gpu_launches), "roofline": roofline,
+        "cpu_baseline": cpu_baseline,
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,180 @@
+// mplx_device.cuh — device-side arithmetic of the node-expansion path (sm_100a).
+//
+// Everything here must reproduce the reference's IEEE-754 double results bit for bit where
+// they feed a lattice key, so this translation unit is compiled with -fmad=false (no FMA
+// contraction: the reference build has none, CMakeLists.txt:8) and uses true divisions,
+// round-half-away (round()), and the reference's operand association.  Citations are
+// path:line relative to the reference checkout.
+#pragma once
+#include <stdint.h>
+
+namespace mplx {
+
+// Kernel-visible copy of the env state (env_base.h:368-400, env_map.h:288-296,
+// map_util.h:300-313).  Passed by value as a kernel parameter.
+struct EnvParams {
+  int dim, control, nU, udim;
+  double T, w, wyaw;
+  double v_max, a_max, j_max, yaw_max;
+  double cos_yaw_max;  // cos(yaw_max) evaluated on the host (primitive.h:521 calls libm cos)
+  int mdim[3];
+  double origin[3];
+  double res;
+  double pot_w, grad_w;
+  const int8_t *map;           // x-fastest int8 grid in HBM
+  const int8_t *pot;           // potential grid or nullptr
+  const uint32_t *region_bits; // 1 bit / voxel (bit i of word i>>5) or nullptr
+  const double *U;             // nU*udim
+  unsigned long long *stats;   // [0]=samples visited, [1]=successors emitted; or nullptr
+};
+
+#define MPLX_PI 3.14159265358979323846 /* M_PI */
+
+// normalize_angle: include/mpl_basis/math.h:15-19
+__device__ __forceinline__ double normalize_angle(double a) {
+  while (a > MPLX_PI) a -= 2.0 * MPLX_PI;
+  while (a < -MPLX_PI) a += 2.0 * MPLX_PI;
+  return a;
+}
+
+// boost::hash_combine, 64-bit size_t, Boost 1.56-1.80 (hash_combine_impl(uint64&,uint64));
+// boost::hash<int> = sign-extending cast.  waypoint.h:98..121 call sites.
+__device__ __forceinline__ void hash_combine(uint64_t &h, int v) {
+  uint64_t k = (uint64_t)(int64_t)v;
+  const uint64_t m = 0xc6a4a7935bd1e995ULL;
+  k *= m;
+  k ^= k >> 47;
+  k *= m;
+  h ^= k;
+  h *= m;
+  h += 0xe6546b64ULL;
+}
+
+// `int id = std::round(x / res)` (waypoint.h:97,101,105,109,115)
+__device__ __forceinline__ int lattice_id(double x, double res) { return (int)round(x / res); }
+
+// One axis of a primitive built by the state+control constructor (primitive.h:220-256):
+// ORD = number of state derivatives carried (VEL 1, ACC 2, JRK 3, SNP 4); the leading
+// 6-1-ORD coefficients are the literal +0 of the comma initialisers (primitive.h:34-50).
+// We keep the four pre-divided quotients the evaluators use (c1/24, c2/6, c3/2, ...).
+template <int ORD>
+struct Axis {
+  double c1, c2, c3, c4, c5;  // c0 is always the literal 0
+
+  __device__ __forceinline__ void build(double u, double p, double v, double a, double j) {
+    c1 = c2 = c3 = 0.0;
+    if (ORD == 1) { c4 = u; c5 = p; }
+    if (ORD == 2) { c3 = u; c4 = v; c5 = p; }
+    if (ORD == 3) { c2 = u; c3 = a; c4 = v; c5 = p; }
+    if (ORD == 4) { c1 = u; c2 = j; c3 = a; c4 = v; c5 = p; }
+  }
+
+  // Primitive1D::p (primitive.h:128-131).  power(t,n) = ((1*t)*t).. = t*t*..*t (math.h:197-205)
+  // so pw3=(t*t)*t etc. are shared by the caller.  Terms whose coefficient is the literal 0
+  // contribute exactly +0 (t finite) and the running sum starts at +0.
+  template <bool EXACT_ZERO>
+  __device__ __forceinline__ double p(double t, double pw3, double pw4) const {
+    double s = 0.0;
+    if (ORD >= 4) s = s + c1 / 24 * pw4;
+    if (ORD >= 3) s = s + c2 / 6 * pw3;
+    if (ORD >= 2) s = s + c3 / 2 * t * t;
+    if (EXACT_ZERO || ORD >= 2)
+      s = s + c4 * t;
+    else
+      s = c4 * t;
+    return s + c5;
+  }
+  // Primitive1D::v (primitive.h:134-137)
+  __device__ __forceinline__ double v(double t, double pw3) const {
+    double s = 0.0;
+    if (ORD >= 4) s = s + c1 / 6 * pw3;
+    if (ORD >= 3) s = s + c2 / 2 * t * t;
+    if (ORD >= 2) s = s + c3 * t;
+    return s + c4;
+  }
+  // Primitive1D::a (primitive.h:140-142)
+  __device__ __forceinline__ double a(double t) const {
+    double s = 0.0;
+    if (ORD >= 4) s = s + c1 / 2 * t * t;
+    if (ORD >= 3) s = s + c2 * t;
+    return s + c3;
+  }
+  // Primitive1D::j (primitive.h:145): c0/2*t*t + c1*t + c2
+  __device__ __forceinline__ double j(double t) const {
+    double s = 0.0;
+    if (ORD >= 4) s = s + c1 * t;
+    return s + c2;
+  }
+
+  // max_vel (primitive.h:353-363) with extrema_v (:152-162) and solve (math.h:117-131).
+  // solve(0, c0/6, c1/2, c2, c3): with c0 = 0 the cubic branch is unreachable;
+  //   c1 != 0 -> quad(c1/2, c2, c3) (math.h:22-32);  else c2 != 0 -> linear root -c3/c2.
+  __device__ __forceinline__ double max_vel(double T) const {
+    // v(0) = 0+..+c4 ; |v(0)| = |c4|
+    double pw3T = (T * T) * T;
+    double m = fmax(fabs(v(0.0, 0.0)), fabs(v(T, pw3T)));
+    if (ORD >= 4 && c1 / 2 != 0) {
+      double b = c1 / 2, c = c2, d = c3;
+      double disc = c * c - 4 * b * d;
+      if (!(disc < 0)) {
+        double r0 = (-c - sqrt(disc)) / (2 * b);
+        double r1 = (-c + sqrt(disc)) / (2 * b);
+        // filter with the unsorted early break (primitive.h:155-160)
+        bool brk = false;
+        if (r0 > 0 && r0 < T) {
+          double vv = fabs(v(r0, (r0 * r0) * r0));
+          m = vv > m ? vv : m;
+        } else if (r0 >= T)
+          brk = true;
+        if (!brk && r1 > 0 && r1 < T) {
+          double vv = fabs(v(r1, (r1 * r1) * r1));
+          m = vv > m ? vv : m;
+        }
+      }
+    } else if (ORD >= 3 && c2 != 0) {
+      double r = -c3 / c2;
+      if (r > 0 && r < T) {
+        double vv = fabs(v(r, (r * r) * r));
+        m = vv > m ? vv : m;
+      }
+    }
+    return m;
+  }
+  // max_acc (primitive.h:369-379), extrema_a (:169-179): solve(0,0,c0/2,c1,c2):
+  //   c0/2 == 0 -> c1 != 0 -> linear root -c2/c1.
+  __device__ __forceinline__ double max_acc(double T) const {
+    double m = fmax(fabs(a(0.0)), fabs(a(T)));
+    if (ORD >= 4 && c1 != 0) {
+      double r = -c2 / c1;
+      if (r > 0 && r < T) {
+        double aa = fabs(a(r));
+        m = aa > m ? aa : m;
+      }
+    }
+    return m;
+  }
+  // max_jrk (primitive.h:384-394), extrema_j (:186-193): c0 == 0 -> no interior root.
+  __device__ __forceinline__ double max_jrk(double T) const { return fmax(fabs(j(0.0)), fabs(j(T))); }
+
+  // Primitive1D::J (primitive.h:92-122) for a ctor-built primitive: every term but the last
+  // has a literal-0 factor and sums to +0, leaving (u*u)*T with u the control coefficient.
+  __device__ __forceinline__ double J(double T) const {
+    double u = ORD == 1 ? c4 : ORD == 2 ? c3 : ORD == 3 ? c2 : c1;
+    return 0.0 + u * u * T;
+  }
+};
+
+// v.normalized().dot((cos yaw, sin yaw)) with Eigen's definitions (normalized(): divide by
+// sqrt(squaredNorm) when squaredNorm > 0).  primitive.h:520, env_map.h:124-125.
+__device__ __forceinline__ double dot2_normalized(double v0, double v1, double c, double s) {
+  double z = v0 * v0 + v1 * v1;
+  double n0 = v0, n1 = v1;
+  if (z > 0) {
+    double nn = sqrt(z);
+    n0 = v0 / nn;
+    n1 = v1 / nn;
+  }
+  return n0 * c + n1 * s;
+}
+
+}  // namespace mplx
