@@ -209,7 +209,12 @@ def main():
     d_action = torch.empty(slots, dtype=torch.int32, device="cuda")
     d_key = torch.empty(slots, dtype=torch.int64, device="cuda")
     out_d = SuccOut(d_count.data_ptr(), d_succ.data_ptr(), d_cost.data_ptr(), d_action.data_ptr(), d_key.data_ptr(), None)
-    stream = torch.cuda.current_stream()
+    # a dedicated non-default stream: the kernel, and the CUDA events that time it, are both
+    # issued on this stream (mplx_expand_device treats a NULL stream as "the ctx's own stream",
+    # so torch's legacy default stream, whose handle is 0, must not be used here)
+    stream = torch.cuda.Stream()
+    assert stream.cuda_stream != 0
+    stream.wait_stream(torch.cuda.current_stream())
 
     def step_device():
         abi.check(lib.mplx_expand_device(env.handle, d_nodes.data_ptr(), n, C.byref(out_d), stream.cuda_stream))

@@ -122,6 +122,11 @@ int mplx_expand(mplx_ctx *ctx, const mplx_waypoint *nodes, int n_nodes, const mp
 int mplx_expand_device(mplx_ctx *ctx, const void *d_nodes, int n_nodes, const mplx_succ_out *out,
                        void *stream);
 
+/* Kernel selection (diagnostics): 0 = auto (the flat sample-parallel kernel whenever
+ * |U| <= 256), 1 = the sequential kernel that keeps traverse_primitive's literal per-primitive
+ * loop (env_map.h:99-130).  Both produce identical results. */
+int mplx_set_kernel(mplx_ctx *ctx, int which);
+
 /* Synchronise the ctx stream. */
 int mplx_sync(mplx_ctx *ctx);
 

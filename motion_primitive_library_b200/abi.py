@@ -37,6 +37,7 @@ EXPORTED_SYMBOLS = (
     "mplx_set_params",
     "mplx_expand",
     "mplx_expand_device",
+    "mplx_set_kernel",
     "mplx_sync",
     "mplx_launch_count",
     "mplx_enable_stats",
@@ -102,6 +103,8 @@ def load() -> C.CDLL:
     lib.mplx_expand.restype = i32
     lib.mplx_expand_device.argtypes = [vp, vp, i32, C.POINTER(SuccOut), vp]
     lib.mplx_expand_device.restype = i32
+    lib.mplx_set_kernel.argtypes = [vp, i32]
+    lib.mplx_set_kernel.restype = i32
     lib.mplx_sync.argtypes = [vp]
     lib.mplx_sync.restype = i32
     lib.mplx_launch_count.argtypes = [vp]

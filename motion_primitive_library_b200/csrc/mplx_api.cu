@@ -95,8 +95,10 @@ struct mplx_ctx {
   cudaStream_t stream = nullptr;
   // static data in HBM
   DevBuf<int8_t> map, pot;
-  DevBuf<uint32_t> region;
-  DevBuf<double> U;
+  DevBuf<uint32_t> region, occ;
+  DevBuf<double> U, ttab;
+  DevBuf<int> tcount;
+  int force_seq = 0;
   DevBuf<unsigned long long> stats;
   bool has_map = false, has_pot = false, has_region = false, has_params = false, stats_on = false;
   size_t nvox = 0;
@@ -126,6 +128,18 @@ static void refresh_params(mplx_ctx *c) {
   c->P.region_bits = c->has_region ? c->region.p : nullptr;
   c->P.U = c->U.p;
   c->P.stats = c->stats_on ? c->stats.p : nullptr;
+  c->P.occ_bits = c->has_map ? c->occ.p : nullptr;
+  c->P.ttab = c->ttab.p;
+  c->P.tcount = c->tcount.p;
+  // largest sample count n the flat phase will meet: validated primitives have
+  // max_vel <= v_max (primitive.h:482-496), so n = max(5, ceil(max_v*T/res)) (env_map.h:95)
+  // is bounded; VEL control and v_max <= 0 are unbounded -> whole table.
+  int maxn = mplx::kNMax;
+  if (c->has_map && c->has_params && (c->P.control & 15) != MPLX_VEL && c->P.v_max > 0) {
+    const double nb = ceil(c->P.v_max * c->P.T / c->P.res);
+    if (nb < (double)mplx::kNMax) maxn = nb < 5 ? 5 : (int)nb;
+  }
+  c->P.maxn = maxn;
 }
 
 extern "C" {
@@ -176,6 +190,7 @@ int mplx_destroy(mplx_ctx *c) {
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
   c->map.release(); c->pot.release(); c->region.release(); c->U.release(); c->stats.release();
+  c->occ.release(); c->ttab.release(); c->tcount.release();
   c->d_nodes.release(); c->d_succ.release(); c->d_count.release(); c->d_action.release();
   c->d_lattice.release(); c->d_cost.release(); c->d_key.release();
   c->h_nodes.release(); c->h_succ.release(); c->h_count.release(); c->h_action.release();
@@ -198,6 +213,9 @@ int mplx_set_map(mplx_ctx *c, const int8_t *data, const int32_t *dim, const doub
   CU(cudaStreamSynchronize(c->stream));
   CU(c->map.reserve(nvox));
   CU(cudaMemcpyAsync(c->map.p, data, nvox, cudaMemcpyHostToDevice, c->stream));
+  CU(c->occ.reserve((nvox + 31) / 32));
+  CU(mplx::launch_pack_bits(c->map.p, nvox, c->occ.p, true, c->stream));
+  c->launches++;
   CU(cudaStreamSynchronize(c->stream));
   c->nvox = nvox;
   for (int k = 0; k < 3; k++) {
@@ -205,6 +223,7 @@ int mplx_set_map(mplx_ctx *c, const int8_t *data, const int32_t *dim, const doub
     c->P.origin[k] = k < c->dim ? origin[k] : 0.0;
   }
   c->P.res = res;
+  c->P.rinv = 1.0 / res;
   c->has_map = true;
   c->has_pot = false;
   c->has_region = false;
@@ -241,7 +260,7 @@ int mplx_set_search_region(mplx_ctx *c, const uint8_t *in_region) {
     CU(tmp.reserve(c->nvox));
     cudaError_t e = cudaMemcpyAsync(tmp.p, in_region, c->nvox, cudaMemcpyHostToDevice, c->stream);
     if (e == cudaSuccess) e = c->region.reserve((c->nvox + 31) / 32);
-    if (e == cudaSuccess) e = mplx::launch_pack_region(tmp.p, c->nvox, c->region.p, c->stream);
+    if (e == cudaSuccess) e = mplx::launch_pack_bits((const int8_t *)tmp.p, c->nvox, c->region.p, false, c->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
     tmp.release();
     CU(e);
@@ -266,6 +285,10 @@ int mplx_set_params(mplx_ctx *c, int control, double T, double w, double wyaw, d
   CU(cudaStreamSynchronize(c->stream));
   CU(c->U.reserve((size_t)nU * udim));
   CU(cudaMemcpyAsync(c->U.p, U, sizeof(double) * nU * udim, cudaMemcpyHostToDevice, c->stream));
+  CU(c->ttab.reserve((size_t)(mplx::kNMax + 1) * mplx::kTStride));
+  CU(c->tcount.reserve(mplx::kNMax + 1));
+  CU(mplx::launch_build_ttab(T, c->ttab.p, c->tcount.p, c->stream));
+  c->launches++;
   CU(cudaStreamSynchronize(c->stream));
   c->P.control = control;
   c->P.nU = nU;
@@ -299,7 +322,7 @@ int mplx_expand_device(mplx_ctx *c, const void *d_nodes, int n_nodes, const mplx
   if (!d_nodes) return fail(MPLX_ERR_ARG, "d_nodes is null");
   cudaStream_t st = stream ? (cudaStream_t)stream : c->stream;
   if (c->stats_on) CU(cudaMemsetAsync(c->stats.p, 0, 2 * sizeof(unsigned long long), st));
-  CU(mplx::launch_expand(c->P, (const mplx_waypoint *)d_nodes, n_nodes, *out, st));
+  CU(mplx::launch_expand(c->P, (const mplx_waypoint *)d_nodes, n_nodes, *out, st, c->force_seq));
   c->launches++;
   if (c->stats_on)
     CU(cudaMemcpyAsync(c->last_stats, c->stats.p, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
@@ -356,7 +379,7 @@ int mplx_expand(mplx_ctx *c, const mplx_waypoint *nodes, int n_nodes, const mplx
     d.key = out->key ? c->d_key.p : nullptr;
     d.lattice = out->lattice ? c->d_lattice.p : nullptr;
     if (c->stats_on) CU(cudaMemsetAsync(c->stats.p, 0, 2 * sizeof(unsigned long long), st));
-    CU(mplx::launch_expand(c->P, c->d_nodes.p, m, d, st));
+    CU(mplx::launch_expand(c->P, c->d_nodes.p, m, d, st, c->force_seq));
     c->launches++;
     if (c->stats_on)
       CU(cudaMemcpyAsync(c->last_stats, c->stats.p, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
@@ -392,6 +415,13 @@ int mplx_expand(mplx_ctx *c, const mplx_waypoint *nodes, int n_nodes, const mplx
     c->last_stats[0] = acc_stats[0];
     c->last_stats[1] = acc_stats[1];
   }
+  return MPLX_OK;
+}
+
+int mplx_set_kernel(mplx_ctx *c, int which) {
+  if (!c) return fail(MPLX_ERR_ARG, "null ctx");
+  if (which != 0 && which != 1) return fail(MPLX_ERR_ARG, "which must be 0 (auto: flat) or 1 (sequential)");
+  c->force_seq = which;
   return MPLX_OK;
 }
 

@@ -20,13 +20,23 @@ struct EnvParams {
   int mdim[3];
   double origin[3];
   double res;
+  double rinv;  // RN(1/res), host-computed (fast path of floatToInt)
   double pot_w, grad_w;
   const int8_t *map;           // x-fastest int8 grid in HBM
   const int8_t *pot;           // potential grid or nullptr
   const uint32_t *region_bits; // 1 bit / voxel (bit i of word i>>5) or nullptr
   const double *U;             // nU*udim
   unsigned long long *stats;   // [0]=samples visited, [1]=successors emitted; or nullptr
+  const uint32_t *occ_bits;    // 1 bit / voxel: map[idx] == 100 (isOccupied, map_util.h:48)
+  // Sample-time table of `for (t = 0; t < T; t += T/n)` (env_map.h:98-99): row n holds the
+  // running-sum times t_k, tcount[n] their number (n or n+1).  Depends on T only.
+  const double *ttab;          // [(kNMax+1) * kTStride]
+  const int *tcount;           // [kNMax+1]
+  int maxn;                    // largest n the flat sample phase accepts (<= kNMax)
 };
+
+constexpr int kNMax = 128;          // rows of the sample-time table
+constexpr int kTStride = kNMax + 2; // doubles per row
 
 #define MPLX_PI 3.14159265358979323846 /* M_PI */
 
@@ -50,8 +60,27 @@ __device__ __forceinline__ void hash_combine(uint64_t &h, int v) {
   h += 0xe6546b64ULL;
 }
 
-// `int id = std::round(x / res)` (waypoint.h:97,101,105,109,115)
-__device__ __forceinline__ int lattice_id(double x, double res) { return (int)round(x / res); }
+// ---- exact rounding with a division-free fast path -------------------------------------
+// The reference computes  k = (int)std::round(RN(x / r) [- 0.5])  (waypoint.h:97-121,
+// map_util.h:106).  IEEE division + round() + F2I cost ~40 instructions and saturate the
+// XU pipe, so we evaluate y' = RN(x * RN(1/r)) instead (|y' - RN(x/r)| <= 4e-16*|y|),
+// round it to nearest with the 1.5*2^52 magic constant (pure FP64-pipe adds) and accept the
+// result only when y' [-0.5] is farther than 1e-6 from a rounding tie and |y'| < 1e9 — then
+// both computations provably round to the same integer.  Anything closer to a tie (lattice
+// values such as 0.25/0.1 = 2.5 land exactly on ties) takes the exact slow path below.
+#define MPLX_MAGIC 6755399441055744.0 /* 1.5 * 2^52 */
+
+static __device__ __noinline__ int lattice_id_slow(double x, double res) { return (int)round(x / res); }
+static __device__ __noinline__ int cell_slow(double s, double res) { return (int)round(s / res - 0.5); }
+
+// `int id = std::round(x / res)` (waypoint.h:97,101,105,109,115); rinv = RN(1/res)
+__device__ __forceinline__ int lattice_id(double x, double res, double rinv) {
+  const double y = x * rinv;
+  const double m = y + MPLX_MAGIC;
+  const double f = y - (m - MPLX_MAGIC);
+  if (fabs(f) < 0.499999 && fabs(y) < 1e9) return __double2loint(m);
+  return lattice_id_slow(x, res);
+}
 
 // One axis of a primitive built by the state+control constructor (primitive.h:220-256):
 // ORD = number of state derivatives carried (VEL 1, ACC 2, JRK 3, SNP 4); the leading
@@ -72,17 +101,22 @@ struct Axis {
   // Primitive1D::p (primitive.h:128-131).  power(t,n) = ((1*t)*t).. = t*t*..*t (math.h:197-205)
   // so pw3=(t*t)*t etc. are shared by the caller.  Terms whose coefficient is the literal 0
   // contribute exactly +0 (t finite) and the running sum starts at +0.
+  // EXACT_ZERO=false drops the leading `(+0) +`: identical value except that a -0 first term
+  // stays -0 (irrelevant for the cell index, used only inside the sample loop).
   template <bool EXACT_ZERO>
   __device__ __forceinline__ double p(double t, double pw3, double pw4) const {
-    double s = 0.0;
-    if (ORD >= 4) s = s + c1 / 24 * pw4;
-    if (ORD >= 3) s = s + c2 / 6 * pw3;
-    if (ORD >= 2) s = s + c3 / 2 * t * t;
-    if (EXACT_ZERO || ORD >= 2)
+    if (EXACT_ZERO) {
+      double s = 0.0;
+      if (ORD >= 4) s = s + c1 / 24 * pw4;
+      if (ORD >= 3) s = s + c2 / 6 * pw3;
+      if (ORD >= 2) s = s + c3 / 2 * t * t;
       s = s + c4 * t;
-    else
-      s = c4 * t;
-    return s + c5;
+      return s + c5;
+    }
+    if (ORD == 1) return c4 * t + c5;
+    if (ORD == 2) return c3 / 2 * t * t + c4 * t + c5;
+    if (ORD == 3) return c2 / 6 * pw3 + c3 / 2 * t * t + c4 * t + c5;
+    return c1 / 24 * pw4 + c2 / 6 * pw3 + c3 / 2 * t * t + c4 * t + c5;
   }
   // Primitive1D::v (primitive.h:134-137)
   __device__ __forceinline__ double v(double t, double pw3) const {
@@ -160,7 +194,7 @@ struct Axis {
   // has a literal-0 factor and sums to +0, leaving (u*u)*T with u the control coefficient.
   __device__ __forceinline__ double J(double T) const {
     double u = ORD == 1 ? c4 : ORD == 2 ? c3 : ORD == 3 ? c2 : c1;
-    return 0.0 + u * u * T;
+    return u * u * T;  // (+0) + x == x for x >= +0
   }
 };
 

@@ -1,12 +1,23 @@
 // mplx_kernels.cu — expand(frontier x U): the batched body of env_map<Dim>::get_succ
 // (include/mpl_planner/env/env_map.h:147-172) for sm_100a.
 //
-// Work decomposition (v1): one thread per (frontier node, control) primitive; a CTA covers
-// NPB = 256/|U| whole nodes so that the stable, control-ordered compaction of a node's
-// successors (env_map.h:155-170 push_back order) is a CTA-local ballot/popcount.
-// The voxel grid / potential grid / tunnel bitmask live in HBM (staged once by mplx_set_*),
-// and are read with read-only (ld.global.nc) loads; every sample loop exits at the first
-// blocking sample exactly like traverse_primitive's `return inf` (env_map.h:104-121).
+// Work decomposition.  A CTA of 256 threads covers NPB = 256/|U| whole frontier nodes, one
+// thread per (node, control) primitive:
+//   phase A  build the primitive (primitive.h:220-256), evaluate the end state tn
+//            (:321-331), its lattice key (waypoint.h:93-125) and the dynamic validity
+//            (primitive.h:449-525) in registers;
+//   phase B  stable, control-ordered compaction of each node's successors with warp ballots
+//            (the push_back order of env_map.h:155-170) and write-out of tn/key/action;
+//   phase C  traverse_primitive (env_map.h:90-132).  "flat" kernel: the samples of the 32
+//            primitives of a warp are laid end to end and dealt to the lanes round-robin —
+//            coefficients staged in shared memory, sample times read from the table that
+//            reproduces the `t += dt` running sum — so every lane does useful work and the
+//            voxel loads of a warp are 32 independent requests (the per-primitive loop is a
+//            chain of dependent loads).  A per-primitive atomicMin records the first blocking
+//            sample (= the reference's early `return inf`).  The "seq" kernel keeps the literal
+//            per-thread loop; it serves |U| > 256 and is the in-kernel fallback for n > maxn.
+// The occupancy grid is read as 1 bit/voxel (16 MiB at 512^3: L2-resident); potential-field
+// planning reads the int8 grid.  No tensor cores: there is no dense contraction on this path.
 //
 // Build: nvcc -gencode arch=compute_100a,code=sm_100a -fmad=false  (see mplx_device.cuh).
 #include <cuda_runtime.h>
@@ -20,6 +31,8 @@
 namespace mplx {
 
 constexpr int kThreads = 256;
+constexpr int kWarps = kThreads / 32;
+constexpr int kNoBlock = 0x7fffffff;
 
 template <int DIM, int ORD, bool YAW>
 struct PrimState {
@@ -27,77 +40,204 @@ struct PrimState {
   double yaw_u, yaw0;  // pr_yaw_ = [0,0,0,0,u(Dim),yaw]  (primitive.h:34,235-248)
 };
 
-// traverse_primitive: include/mpl_planner/env/env_map.h:90-132
-template <int DIM, int ORD, bool YAW, bool STATS>
-__device__ __forceinline__ double traverse(const EnvParams &P, const PrimState<DIM, ORD, YAW> &pr,
-                                           unsigned &n_samples) {
-  const double T = P.T;
-  double max_v = 0;
-#pragma unroll
-  for (int i = 0; i < DIM; i++) {
-    double mv = pr.ax[i].max_vel(T);
-    if (mv > max_v) max_v = mv;
+// ---- voxel classification shared by both sample loops ------------------------------------
+// Returns true when the sample blocks the primitive (env_map.h:104-121); otherwise adds the
+// potential term to `term`.  idx is a valid in-map index.
+__device__ __forceinline__ bool voxel_blocks(const EnvParams &P, int idx, double dt, double vnorm_w,
+                                             double &term) {
+  if (P.region_bits != nullptr) {
+    if (!((__ldg(P.region_bits + (idx >> 5)) >> (idx & 31)) & 1u)) return true;
   }
-  int n = max(5, (int)ceil(max_v * T / P.res));
-  double c = 0;
-  const double dt = T / n;
-  const bool need_vel = YAW || (P.pot != nullptr && P.grad_w != 0.0);
-  for (double t = 0; t < T; t += dt) {
-    if (STATS) n_samples++;
-    const double t2 = t * t;
-    const double pw3 = t2 * t;
-    const double pw4 = pw3 * t;
-    int pn[DIM];
-    bool outside = false;
+  if (P.pot != nullptr) {
+    const int pv = (int)__ldg(P.pot + idx);
+    if (pv < 100 && pv > 0)
+      term += dt * (P.pot_w * pv + vnorm_w);
+    else if (pv >= 100)
+      return true;
+    return false;
+  }
+  return (__ldg(P.occ_bits + (idx >> 5)) >> (idx & 31)) & 1u;
+}
+
+// floatToInt + isOutside + getIndex (map_util.h:103-108, 51-55, 34-41) for one sample.
+// pk[] are the sample's position coordinates.  Returns the cell index or -1 when outside.
+template <int DIM>
+__device__ __forceinline__ int sample_index(const EnvParams &P, const double (&pk)[DIM]) {
+  int pn[DIM];
+  double sk[DIM];
+  bool inside = true, fast = true;
+#pragma unroll
+  for (int k = 0; k < DIM; k++) {
+    // round((p - origin)/res - 0.5), division-free fast path (see mplx_device.cuh)
+    sk[k] = pk[k] - P.origin[k];
+    const double x = sk[k] * P.rinv - 0.5;
+    const double m = x + MPLX_MAGIC;
+    const double kd = m - MPLX_MAGIC;
+    const double f = x - kd;
+    fast = fast && (fabs(f) < 0.499999);
+    // |kd| beyond the grid is outside whatever the low-order error; inside the grid
+    // |x| < 2^31 so the fast path is exact
+    inside = inside && (kd >= 0.0) && (kd < (double)P.mdim[k]);
+    pn[k] = __double2loint(m);
+  }
+  if (!fast) {
+    // within 1e-6 of a rounding tie (or astronomically far away): the exact expression
+    inside = true;
 #pragma unroll
     for (int k = 0; k < DIM; k++) {
-      double pk = pr.ax[k].template p<false>(t, pw3, pw4);
-      // floatToInt: map_util.h:103-108
-      pn[k] = (int)round((pk - P.origin[k]) / P.res - 0.5);
-      outside = outside || pn[k] < 0 || pn[k] >= P.mdim[k];
-    }
-    if (outside) return INFINITY;
-    // getIndex: map_util.h:34-41 (inside the map it cannot overflow: the grid is <2^31 cells)
-    int idx = pn[0] + P.mdim[0] * pn[1];
-    if (DIM == 3) idx += P.mdim[0] * P.mdim[1] * pn[2];
-    if (P.region_bits != nullptr) {
-      if (!((__ldg(P.region_bits + (idx >> 5)) >> (idx & 31)) & 1u)) return INFINITY;
-    }
-    double vel[DIM];
-    if (need_vel) {
-#pragma unroll
-      for (int k = 0; k < DIM; k++) vel[k] = pr.ax[k].v(t, pw3);
-    }
-    if (P.pot != nullptr) {
-      const int pv = (int)__ldg(P.pot + idx);
-      if (pv < 100 && pv > 0) {
-        double g = 0.0;
-        if (P.grad_w != 0.0) {
-          // pt.vel.norm(): Eigen's unrolled reduction a0 + (a1 + a2)
-          double n2 = DIM == 2 ? vel[0] * vel[0] + vel[1] * vel[1]
-                               : vel[0] * vel[0] + (vel[1] * vel[1] + vel[DIM - 1] * vel[DIM - 1]);
-          g = P.grad_w * sqrt(n2);
-        } else {
-          g = 0.0;  // gradient_weight_(0) * norm == +0 for finite norm
-        }
-        c += dt * (P.pot_w * pv + g);
-      } else if (pv >= 100)
-        return INFINITY;
-    } else if (__ldg(P.map + idx) == 100)
-      return INFINITY;
-    if (YAW) {
-      if (P.wyaw > 0) {
-        const double v0 = vel[0], v1 = vel[1];
-        if (sqrt(v0 * v0 + v1 * v1) > 1e-5) {
-          const double yaw = normalize_angle(pr.yaw_u * t + pr.yaw0);
-          double sn, cs;
-          sincos(yaw, &sn, &cs);
-          const double v_value = 1 - dot2_normalized(v0, v1, cs, sn);
-          c += P.wyaw * v_value * dt;
-        }
-      }
+      pn[k] = cell_slow(sk[k], P.res);
+      inside = inside && pn[k] >= 0 && pn[k] < P.mdim[k];
     }
   }
+  if (!inside) return -1;
+  int idx = pn[0] + P.mdim[0] * pn[1];
+  if (DIM == 3) idx += P.mdim[0] * P.mdim[1] * pn[DIM - 1];
+  return idx;
+}
+
+// The yaw-alignment term of env_map.h:122-129.
+__device__ __forceinline__ double yaw_term(const EnvParams &P, double v0, double v1, double yaw, double dt) {
+  if (sqrt(v0 * v0 + v1 * v1) > 1e-5) {
+    double sn, cs;
+    sincos(yaw, &sn, &cs);
+    const double v_value = 1 - dot2_normalized(v0, v1, cs, sn);
+    return P.wyaw * v_value * dt;
+  }
+  return 0.0;
+}
+
+// pt.vel.norm() scaled by gradient_weight_ (env_map.h:115-116); Eigen's unrolled reduction
+// associates a 3-vector sum as a0 + (a1 + a2).
+template <int DIM>
+__device__ __forceinline__ double grad_term(const EnvParams &P, const double (&vel)[DIM]) {
+  if (P.grad_w == 0.0) return 0.0;  // gradient_weight_(0) * norm == +0 for a finite norm
+  const double n2 = DIM == 2 ? vel[0] * vel[0] + vel[1] * vel[1]
+                             : vel[0] * vel[0] + (vel[1] * vel[1] + vel[DIM - 1] * vel[DIM - 1]);
+  return P.grad_w * sqrt(n2);
+}
+
+// Loop-invariant coefficient layout shared by both sample loops ("cf"):
+//   [axis 0..DIM-1: position quotients  (c1/24) (c2/6) (c3/2) c4 c5   — the last ORD+1 of them]
+//   [axis 0..DIM-1: velocity quotients  (c1/6) (c2/2) c3 c4           — the last ORD, only if need_vel]
+//   [yaw_u, yaw0                                                      — only if YAW]
+template <int DIM, int ORD, bool YAW>
+struct CoefLayout {
+  static constexpr int NCP = DIM * (ORD + 1);
+  static constexpr int NCV = DIM * ORD;
+  static constexpr int NCMAX = NCP + NCV + (YAW ? 2 : 0);
+  __host__ __device__ static int ncoef(bool need_vel) { return NCP + (need_vel ? NCV : 0) + (YAW ? 2 : 0); }
+};
+
+template <int DIM, int ORD, bool YAW>
+__device__ __forceinline__ void fill_coef(const PrimState<DIM, ORD, YAW> &pr, bool need_vel, double *cf) {
+  int c = 0;
+#pragma unroll
+  for (int k = 0; k < DIM; k++) {
+    if (ORD >= 4) cf[c++] = pr.ax[k].c1 / 24;
+    if (ORD >= 3) cf[c++] = pr.ax[k].c2 / 6;
+    if (ORD >= 2) cf[c++] = pr.ax[k].c3 / 2;
+    cf[c++] = pr.ax[k].c4;
+    cf[c++] = pr.ax[k].c5;
+  }
+  if (need_vel) {
+#pragma unroll
+    for (int k = 0; k < DIM; k++) {
+      if (ORD >= 4) cf[c++] = pr.ax[k].c1 / 6;
+      if (ORD >= 3) cf[c++] = pr.ax[k].c2 / 2;
+      if (ORD >= 2) cf[c++] = pr.ax[k].c3;
+      cf[c++] = pr.ax[k].c4;
+    }
+  }
+  if (YAW) {
+    cf[c++] = pr.yaw_u;
+    cf[c++] = pr.yaw0;
+  }
+}
+
+// Primitive1D::p (primitive.h:128-131) for all axes at time t, from the quotients.
+template <int DIM, int ORD>
+__device__ __forceinline__ void eval_pos(const double *cf, double t, double (&pk)[DIM]) {
+  const double pw3 = (t * t) * t;
+  const double pw4 = pw3 * t;
+  int c = 0;
+#pragma unroll
+  for (int a = 0; a < DIM; a++) {
+    double acc;
+    if (ORD == 1) {
+      acc = cf[c] * t + cf[c + 1];
+    } else if (ORD == 2) {
+      acc = cf[c] * t * t + cf[c + 1] * t + cf[c + 2];
+    } else if (ORD == 3) {
+      acc = cf[c] * pw3 + cf[c + 1] * t * t + cf[c + 2] * t + cf[c + 3];
+    } else {
+      acc = cf[c] * pw4 + cf[c + 1] * pw3 + cf[c + 2] * t * t + cf[c + 3] * t + cf[c + 4];
+    }
+    pk[a] = acc;
+    c += ORD + 1;
+  }
+}
+
+// Primitive1D::v (primitive.h:134-137) for all axes at time t (cf points at the velocity block).
+template <int DIM, int ORD>
+__device__ __forceinline__ void eval_vel(const double *cf, double t, double (&vel)[DIM]) {
+  const double pw3 = (t * t) * t;
+  int c = 0;
+#pragma unroll
+  for (int a = 0; a < DIM; a++) {
+    double acc = 0.0;
+    if (ORD == 1) {
+      acc = acc + cf[c];
+    } else if (ORD == 2) {
+      acc = acc + cf[c] * t + cf[c + 1];
+    } else if (ORD == 3) {
+      acc = acc + cf[c] * t * t + cf[c + 1] * t + cf[c + 2];
+    } else {
+      acc = acc + cf[c] * pw3 + cf[c + 1] * t * t + cf[c + 2] * t + cf[c + 3];
+    }
+    vel[a] = acc;
+    c += ORD;
+  }
+}
+
+// traverse_primitive, literal per-primitive loop: include/mpl_planner/env/env_map.h:90-132.
+// max_v is the caller's max_i pr.max_vel(i) (the reference recomputes it at :91-94).
+template <int DIM, int ORD, bool YAW>
+__device__ __forceinline__ double traverse_loop(const EnvParams &P, const double *cf, bool need_vel,
+                                                double max_v, unsigned &n_samples) {
+  using CL = CoefLayout<DIM, ORD, YAW>;
+  const double T = P.T;
+  const int n = max(5, (int)ceil(max_v * T / P.res));
+  double c = 0;
+  const double dt = T / n;
+  const int NC = CL::ncoef(need_vel);
+  for (double t = 0; t < T; t += dt) {
+    n_samples++;
+    double pk[DIM], vel[DIM];
+    eval_pos<DIM, ORD>(cf, t, pk);
+    const int idx = sample_index<DIM>(P, pk);
+    if (idx < 0) return INFINITY;
+    double gterm = 0.0;
+    if (need_vel) {
+      eval_vel<DIM, ORD>(cf + CL::NCP, t, vel);
+      gterm = grad_term<DIM>(P, vel);
+    }
+    double term = 0.0;
+    if (voxel_blocks(P, idx, dt, gterm, term)) return INFINITY;
+    c += term;
+    if (YAW) {
+      if (P.wyaw > 0) c += yaw_term(P, vel[0], vel[1], normalize_angle(cf[NC - 2] * t + cf[NC - 1]), dt);
+    }
+  }
+  return c;
+}
+
+// Out-of-line copy for the flat kernel's rare fallback (cf lives in shared memory there).
+template <int DIM, int ORD, bool YAW>
+__device__ __noinline__ double traverse_loop_cold(const EnvParams *P, const double *cf, bool need_vel,
+                                                  double max_v, unsigned *n_samples) {
+  unsigned ns = 0;
+  const double c = traverse_loop<DIM, ORD, YAW>(*P, cf, need_vel, max_v, ns);
+  *n_samples = ns;
   return c;
 }
 
@@ -123,196 +263,369 @@ __device__ __forceinline__ bool validate_yaw(const EnvParams &P, const PrimState
   return true;
 }
 
-template <int DIM, int ORD, bool YAW, bool STATS>
+struct OutPtrs {
+  int32_t *count;
+  mplx_waypoint *succ;
+  double *cost;
+  int32_t *action;
+  uint64_t *key;
+  int32_t *lattice;
+};
+
+// Phases A and B for one item (all threads of the CTA must call it: it contains a barrier).
+template <int DIM, int ORD, bool YAW>
+__device__ __forceinline__ void phase_ab(const EnvParams &P, const mplx_waypoint *__restrict__ nodes,
+                                         int n_nodes, int item, int items, int nU, int node0,
+                                         uint32_t *vbits, int words, const OutPtrs &o,
+                                         PrimState<DIM, ORD, YAW> &pr, bool &emit, bool &same,
+                                         double &max_v, size_t &slot) {
+  const int nl = item / nU;
+  const int ci = item - nl * nU;
+  const int ni = node0 + nl;
+  const bool active = item < items && ni < n_nodes;
+  emit = false;
+  same = true;
+  max_v = 0;
+  slot = 0;
+
+  mplx_waypoint tn;
+  int lat[MPLX_LATTICE_MAX];
+  uint64_t key = 0;
+  if (active) {
+    const mplx_waypoint *cp = nodes + ni;
+    const double *u = P.U + (size_t)ci * P.udim;
+    uint64_t hcurr = 0;
+    // Primitive(curr, U[i], dt): primitive.h:220-256 ; hash_value(curr): waypoint.h:93-125
+#pragma unroll
+    for (int k = 0; k < DIM; k++) {
+      const double p = cp->pos[k], v = cp->vel[k], a = cp->acc[k], j = cp->jrk[k];
+      pr.ax[k].build(__ldg(u + k), p, v, a, j);
+      hash_combine(hcurr, lattice_id(p, 0.01, 100.0));
+      if (ORD >= 2) hash_combine(hcurr, lattice_id(v, 0.1, 10.0));
+      if (ORD >= 3) hash_combine(hcurr, lattice_id(a, 0.1, 10.0));
+      if (ORD >= 4) hash_combine(hcurr, lattice_id(j, 0.1, 10.0));
+    }
+    if (YAW) {
+      pr.yaw_u = __ldg(u + DIM);
+      pr.yaw0 = cp->yaw;
+      hash_combine(hcurr, lattice_id(cp->yaw, 0.1, 10.0));
+    }
+    // tn = pr.evaluate(dt): primitive.h:321-331 (all four derivative vectors are filled)
+    const double T = P.T;
+    const double pw3T = (T * T) * T, pw4T = pw3T * T;
+    int nl_ = 0;
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+      if (k < DIM) {
+        tn.pos[k] = pr.ax[k].template p<true>(T, pw3T, pw4T);
+        tn.vel[k] = pr.ax[k].v(T, pw3T);
+        tn.acc[k] = pr.ax[k].a(T);
+        tn.jrk[k] = pr.ax[k].j(T);
+        int id = lattice_id(tn.pos[k], 0.01, 100.0);
+        hash_combine(key, id);
+        lat[nl_++] = id;
+        if (ORD >= 2) { id = lattice_id(tn.vel[k], 0.1, 10.0); hash_combine(key, id); lat[nl_++] = id; }
+        if (ORD >= 3) { id = lattice_id(tn.acc[k], 0.1, 10.0); hash_combine(key, id); lat[nl_++] = id; }
+        if (ORD >= 4) { id = lattice_id(tn.jrk[k], 0.1, 10.0); hash_combine(key, id); lat[nl_++] = id; }
+        same = same && (pr.ax[k].c5 == tn.pos[k]);  // curr.pos == tn.pos (env_map.h:163)
+      } else {
+        tn.pos[k] = tn.vel[k] = tn.acc[k] = tn.jrk[k] = 0.0;
+      }
+    }
+    tn.yaw = 0.0;
+    if (YAW) {
+      // pr_yaw_.p(t) = 0/120*.. + c4*t + c5 with the leading +0 sum (primitive.h:128-131,328)
+      tn.yaw = normalize_angle(0.0 + pr.yaw_u * T + pr.yaw0);
+      int id = lattice_id(tn.yaw, 0.1, 10.0);
+      hash_combine(key, id);
+      lat[nl_++] = id;
+    }
+#pragma unroll
+    for (int q = 0; q < MPLX_LATTICE_MAX; q++)
+      if (q >= nl_) lat[q] = 0;
+    tn.t = cp->t + T;  // env_map.h:161
+
+    // tn == curr (hash equality, waypoint.h:133-135) || !validate_primitive (primitive.h:449-475)
+    bool ok = key != hcurr;
+    if (ok && YAW) ok = validate_yaw<DIM, ORD, YAW>(P, pr);
+    // max_vel per axis serves validate_xxx(VEL) (primitive.h:482-496) and traverse (env_map.h:91-94)
+#pragma unroll
+    for (int k = 0; k < DIM; k++) {
+      const double mv = pr.ax[k].max_vel(T);
+      if (ORD >= 2 && P.v_max > 0) ok = ok && !(mv > P.v_max);
+      if (mv > max_v) max_v = mv;
+    }
+    if (ok && ORD >= 3 && P.a_max > 0) {
+#pragma unroll
+      for (int k = 0; k < DIM; k++) ok = ok && !(pr.ax[k].max_acc(T) > P.a_max);
+    }
+    if (ok && ORD >= 4 && P.j_max > 0) {
+#pragma unroll
+      for (int k = 0; k < DIM; k++) ok = ok && !(pr.ax[k].max_jrk(T) > P.j_max);
+    }
+    emit = ok;
+  }
+
+  // ---- phase B: stable per-node compaction (control order) ----
+  const unsigned bal = __ballot_sync(0xffffffffu, emit);
+  if ((threadIdx.x & 31) == 0 && (item >> 5) < words) vbits[item >> 5] = bal;
+  __syncthreads();
+  if (active) {
+    const int s = nl * nU;  // first item of my node
+    int rank = 0;
+    for (int wd = s >> 5; wd <= (item >> 5); wd++) {
+      uint32_t m = vbits[wd];
+      const int lo = wd << 5;
+      if (s > lo) m &= ~0u << (s - lo);
+      if (item < lo + 32) m &= (item - lo) ? (~0u >> (32 - (item - lo))) : 0u;
+      rank += __popc(m);
+    }
+    if (ci == nU - 1) o.count[ni] = rank + (emit ? 1 : 0);
+    if (emit) {
+      slot = (size_t)ni * nU + rank;
+      if (o.succ) o.succ[slot] = tn;
+      if (o.action) o.action[slot] = ci;
+      if (o.key) o.key[slot] = key;
+      if (o.lattice) {
+#pragma unroll
+        for (int q = 0; q < MPLX_LATTICE_MAX; q++) o.lattice[slot * MPLX_LATTICE_MAX + q] = lat[q];
+      }
+    }
+  }
+}
+
+// calculate_intrinsic_cost: env_base.h:343-345 ; Primitive::J: primitive.h:403-407
+template <int DIM, int ORD, bool YAW>
+__device__ __forceinline__ double intrinsic_cost(const EnvParams &P, const PrimState<DIM, ORD, YAW> &pr) {
+  double J = pr.ax[0].J(P.T);
+#pragma unroll
+  for (int k = 1; k < DIM; k++) J += pr.ax[k].J(P.T);
+  return J + P.w * P.T;
+}
+
+// ---- sequential kernel (any |U| <= kMaxU) ---------------------------------------------------
+template <int DIM, int ORD, bool YAW>
 __global__ void __launch_bounds__(kThreads)
-expand_kernel(const EnvParams P, const mplx_waypoint *__restrict__ nodes, int n_nodes, int npb,
-              int32_t *__restrict__ out_count, mplx_waypoint *__restrict__ out_succ,
-              double *__restrict__ out_cost, int32_t *__restrict__ out_action,
-              uint64_t *__restrict__ out_key, int32_t *__restrict__ out_lattice) {
+expand_seq_kernel(const __grid_constant__ EnvParams P, const mplx_waypoint *__restrict__ nodes, int n_nodes,
+                  int npb, const __grid_constant__ OutPtrs o) {
+  const bool need_vel = YAW || (P.pot != nullptr && P.grad_w != 0.0);
   __shared__ uint32_t vbits[kMaxU / 32 + 9];
   __shared__ unsigned long long s_stats[2];
   const int nU = P.nU;
   const int items = npb * nU;
   const int node0 = blockIdx.x * npb;
   const int words = (items + 31) >> 5;
-  if (STATS && threadIdx.x < 2) s_stats[threadIdx.x] = 0;
-
+  if (threadIdx.x < 2) s_stats[threadIdx.x] = 0;
   for (int base = 0; base < items; base += kThreads) {
-    const int item = base + threadIdx.x;
-    const int nl = item / nU;
-    const int ci = item - nl * nU;
-    const int ni = node0 + nl;
-    const bool active = item < items && ni < n_nodes;
-
-    bool emit = false;
-    double cost = 0;
-    mplx_waypoint tn;
-    int lat[MPLX_LATTICE_MAX];
-    uint64_t key = 0;
+    PrimState<DIM, ORD, YAW> pr;
+    bool emit, same;
+    double max_v;
+    size_t slot;
+    phase_ab<DIM, ORD, YAW>(P, nodes, n_nodes, base + threadIdx.x, items, nU, node0, vbits, words, o, pr, emit,
+                            same, max_v, slot);
     unsigned n_samples = 0;
-
-    if (active) {
-      const mplx_waypoint *cp = nodes + ni;
-      const double *u = P.U + (size_t)ci * P.udim;
-      PrimState<DIM, ORD, YAW> pr;
-      double cpos[DIM];
-      uint64_t hcurr = 0;
-      // Primitive(curr, U[i], dt): primitive.h:220-256 ; hash_value(curr): waypoint.h:93-125
-#pragma unroll
-      for (int k = 0; k < DIM; k++) {
-        const double p = cp->pos[k], v = cp->vel[k], a = cp->acc[k], j = cp->jrk[k];
-        cpos[k] = p;
-        pr.ax[k].build(__ldg(u + k), p, v, a, j);
-        hash_combine(hcurr, lattice_id(p, 0.01));
-        if (ORD >= 2) hash_combine(hcurr, lattice_id(v, 0.1));
-        if (ORD >= 3) hash_combine(hcurr, lattice_id(a, 0.1));
-        if (ORD >= 4) hash_combine(hcurr, lattice_id(j, 0.1));
-      }
-      if (YAW) {
-        pr.yaw_u = __ldg(u + DIM);
-        pr.yaw0 = cp->yaw;
-        hash_combine(hcurr, lattice_id(cp->yaw, 0.1));
-      }
-      // tn = pr.evaluate(dt): primitive.h:321-331 (all four derivative vectors are filled)
-      const double T = P.T;
-      const double pw3T = (T * T) * T, pw4T = pw3T * T;
-      int nl_ = 0;
-#pragma unroll
-      for (int k = 0; k < 3; k++) {
-        if (k < DIM) {
-          tn.pos[k] = pr.ax[k].template p<true>(T, pw3T, pw4T);
-          tn.vel[k] = pr.ax[k].v(T, pw3T);
-          tn.acc[k] = pr.ax[k].a(T);
-          tn.jrk[k] = pr.ax[k].j(T);
-          int id = lattice_id(tn.pos[k], 0.01);
-          hash_combine(key, id);
-          lat[nl_++] = id;
-          if (ORD >= 2) { id = lattice_id(tn.vel[k], 0.1); hash_combine(key, id); lat[nl_++] = id; }
-          if (ORD >= 3) { id = lattice_id(tn.acc[k], 0.1); hash_combine(key, id); lat[nl_++] = id; }
-          if (ORD >= 4) { id = lattice_id(tn.jrk[k], 0.1); hash_combine(key, id); lat[nl_++] = id; }
-        } else {
-          tn.pos[k] = tn.vel[k] = tn.acc[k] = tn.jrk[k] = 0.0;
-        }
-      }
-      tn.yaw = 0.0;
-      if (YAW) {
-        // pr_yaw_.p(t) = 0/120*.. + c4*t + c5 with the leading +0 sum (primitive.h:128-131,328)
-        tn.yaw = normalize_angle(0.0 + pr.yaw_u * T + pr.yaw0);
-        int id = lattice_id(tn.yaw, 0.1);
-        hash_combine(key, id);
-        lat[nl_++] = id;
-      }
-#pragma unroll
-      for (int q = 0; q < MPLX_LATTICE_MAX; q++)
-        if (q >= nl_) lat[q] = 0;
-      tn.t = cp->t + T;  // env_map.h:161
-
-      // tn == curr (hash equality, waypoint.h:133-135) || !validate_primitive (primitive.h:449-475)
-      bool ok = key != hcurr;
-      if (ok && YAW) ok = validate_yaw<DIM, ORD, YAW>(P, pr);
-      if (ok && ORD >= 2 && P.v_max > 0) {
-#pragma unroll
-        for (int k = 0; k < DIM; k++) ok = ok && !(pr.ax[k].max_vel(T) > P.v_max);
-      }
-      if (ok && ORD >= 3 && P.a_max > 0) {
-#pragma unroll
-        for (int k = 0; k < DIM; k++) ok = ok && !(pr.ax[k].max_acc(T) > P.a_max);
-      }
-      if (ok && ORD >= 4 && P.j_max > 0) {
-#pragma unroll
-        for (int k = 0; k < DIM; k++) ok = ok && !(pr.ax[k].max_jrk(T) > P.j_max);
-      }
-      emit = ok;
-      if (ok) {
-        bool same = true;  // curr.pos == tn.pos (env_map.h:163)
-#pragma unroll
-        for (int k = 0; k < DIM; k++) same = same && (cpos[k] == tn.pos[k]);
-        cost = same ? 0.0 : traverse<DIM, ORD, YAW, STATS>(P, pr, n_samples);
-        if (!isinf(cost)) {
-          // calculate_intrinsic_cost: env_base.h:343-345 ; Primitive::J: primitive.h:403-407
-          double J = pr.ax[0].J(T);
-#pragma unroll
-          for (int k = 1; k < DIM; k++) J += pr.ax[k].J(T);
-          cost += J + P.w * T;
-        }
-      }
+    if (emit) {
+      double cf[CoefLayout<DIM, ORD, YAW>::NCMAX];
+      fill_coef<DIM, ORD, YAW>(pr, need_vel, cf);
+      double cost = same ? 0.0 : traverse_loop<DIM, ORD, YAW>(P, cf, need_vel, max_v, n_samples);
+      if (!isinf(cost)) cost += intrinsic_cost<DIM, ORD, YAW>(P, pr);
+      if (o.cost) o.cost[slot] = cost;
     }
-
-    // ---- stable per-node compaction (control order) -------------------------------------
-    const unsigned bal = __ballot_sync(0xffffffffu, emit);
-    if ((threadIdx.x & 31) == 0 && (item >> 5) < words) vbits[item >> 5] = bal;
-    __syncthreads();
-    if (active) {
-      const int s = nl * nU;  // first item of my node
-      int rank = 0;
-      for (int wd = s >> 5; wd <= (item >> 5); wd++) {
-        uint32_t m = vbits[wd];
-        const int lo = wd << 5;
-        if (s > lo) m &= ~0u << (s - lo);
-        if (item < lo + 32) m &= (item - lo) ? (~0u >> (32 - (item - lo))) : 0u;
-        rank += __popc(m);
-      }
-      if (ci == nU - 1) out_count[ni] = rank + (emit ? 1 : 0);
-      if (emit) {
-        const size_t slot = (size_t)ni * nU + rank;
-        if (out_succ) out_succ[slot] = tn;
-        if (out_cost) out_cost[slot] = cost;
-        if (out_action) out_action[slot] = ci;
-        if (out_key) out_key[slot] = key;
-        if (out_lattice) {
-#pragma unroll
-          for (int q = 0; q < MPLX_LATTICE_MAX; q++) out_lattice[slot * MPLX_LATTICE_MAX + q] = lat[q];
-        }
-      }
-    }
-    if (STATS) {
+    if (P.stats) {
       atomicAdd(&s_stats[0], (unsigned long long)n_samples);
       if (emit) atomicAdd(&s_stats[1], 1ull);
     }
     __syncthreads();
   }
-  if (STATS && threadIdx.x < 2 && P.stats) atomicAdd(&P.stats[threadIdx.x], s_stats[threadIdx.x]);
+  if (threadIdx.x < 2 && P.stats) atomicAdd(&P.stats[threadIdx.x], s_stats[threadIdx.x]);
+}
+
+// ---- flat kernel (|U| <= 256) -----------------------------------------------------------------
+// Per-warp shared-memory slab (doubles first so everything stays 8-byte aligned):
+//   coef [32][NC]  loop-invariant polynomial quotients of each lane's primitive
+//   cost [32]      accumulated potential / yaw cost        dt [32]  T/n
+//   start[32] n[32] first[32]  (int)                       owner[32*maxns] (uint8)
+template <int DIM, int ORD, bool YAW>
+struct FlatLayout : CoefLayout<DIM, ORD, YAW> {
+  using CoefLayout<DIM, ORD, YAW>::ncoef;
+  __host__ __device__ static size_t warp_bytes(bool need_vel, int maxns) {
+    size_t b = (size_t)32 * ncoef(need_vel) * 8 + 32 * 8 * 2 + 32 * 4 * 3 + (size_t)32 * maxns;
+    return (b + 15) & ~(size_t)15;
+  }
+};
+
+template <int DIM, int ORD, bool YAW>
+__global__ void __launch_bounds__(kThreads, 3)
+expand_flat_kernel(const __grid_constant__ EnvParams P, const mplx_waypoint *__restrict__ nodes, int n_nodes,
+                   int npb, const __grid_constant__ OutPtrs o, int maxns, int need_vel_i) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  __shared__ uint32_t vbits[9];
+  __shared__ unsigned long long s_stats[2];
+  using L = FlatLayout<DIM, ORD, YAW>;
+  const bool need_vel = need_vel_i != 0;
+  const int NC = L::ncoef(need_vel);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  unsigned char *wb = smem + (size_t)warp * L::warp_bytes(need_vel, maxns);
+  double *w_coef = reinterpret_cast<double *>(wb);
+  double *w_cost = w_coef + 32 * NC;
+  double *w_dt = w_cost + 32;
+  int *w_start = reinterpret_cast<int *>(w_dt + 32);
+  int *w_n = w_start + 32;
+  int *w_first = w_n + 32;
+  unsigned char *w_owner = reinterpret_cast<unsigned char *>(w_first + 32);
+
+  const int nU = P.nU;
+  const int items = npb * nU;  // <= 256
+  const int node0 = blockIdx.x * npb;
+  const int words = (items + 31) >> 5;
+  if (threadIdx.x < 2) s_stats[threadIdx.x] = 0;
+
+  PrimState<DIM, ORD, YAW> pr;
+  bool emit, same;
+  double max_v;
+  size_t slot;
+  phase_ab<DIM, ORD, YAW>(P, nodes, n_nodes, threadIdx.x, items, nU, node0, vbits, words, o, pr, emit, same,
+                          max_v, slot);
+
+  // ---- phase C set-up: coefficient slot, n, sample count ----
+  const double T = P.T;
+  fill_coef<DIM, ORD, YAW>(pr, need_vel, w_coef + lane * NC);
+  int n = 0, ns = 0;
+  bool seq = false;
+  double cost_seq = 0.0;
+  unsigned seq_samples = 0;
+  if (emit && !same) {
+    n = max(5, (int)ceil(max_v * T / P.res));  // env_map.h:95
+    if (n <= P.maxn)
+      ns = __ldg(P.tcount + n);
+    else {
+      seq = true;  // beyond the table: literal loop in this lane, coefficients from its smem slot
+      cost_seq = traverse_loop_cold<DIM, ORD, YAW>(&P, w_coef + lane * NC, need_vel, max_v, &seq_samples);
+    }
+  }
+  int incl = ns;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const int v = __shfl_up_sync(0xffffffffu, incl, d);
+    if (lane >= d) incl += v;
+  }
+  const int start = incl - ns;
+  const int S = __shfl_sync(0xffffffffu, incl, 31);
+  w_cost[lane] = 0.0;
+  w_dt[lane] = ns ? T / n : 0.0;  // env_map.h:98
+  w_start[lane] = start;
+  w_n[lane] = n;
+  w_first[lane] = kNoBlock;
+  for (int k = 0; k < ns; k++) w_owner[start + k] = (unsigned char)lane;
+  __syncwarp();
+
+  // ---- phase C: the warp's samples, dealt round-robin to its lanes ----
+  for (int s = lane; s < S; s += 32) {
+    const int i = w_owner[s];
+    const int k = s - w_start[i];
+    if (*(volatile int *)(w_first + i) < k) continue;  // an earlier sample already blocks: result is inf
+    const double t = __ldg(P.ttab + w_n[i] * kTStride + k);
+    const double *cf = w_coef + i * NC;
+    double pk[DIM];
+    eval_pos<DIM, ORD>(cf, t, pk);
+    const int idx = sample_index<DIM>(P, pk);
+    if (idx < 0) {
+      atomicMin(w_first + i, k);
+      continue;
+    }
+    double vel[DIM];
+    double gterm = 0.0;
+    if (need_vel) {
+      eval_vel<DIM, ORD>(cf + L::NCP, t, vel);
+      gterm = grad_term<DIM>(P, vel);
+    }
+    const double dt = w_dt[i];
+    double term = 0.0;
+    if (voxel_blocks(P, idx, dt, gterm, term)) {
+      atomicMin(w_first + i, k);
+      continue;
+    }
+    if (YAW) {
+      if (P.wyaw > 0) {
+        const double yaw_u = cf[NC - 2], yaw0 = cf[NC - 1];
+        term += yaw_term(P, vel[0], vel[1], normalize_angle(yaw_u * t + yaw0), dt);
+      }
+    }
+    if (term != 0.0) atomicAdd(w_cost + i, term);
+  }
+  __syncwarp();
+
+  if (emit) {
+    const int fb = w_first[lane];
+    double cost = same ? 0.0 : seq ? cost_seq : (fb != kNoBlock ? (double)INFINITY : w_cost[lane]);
+    if (!isinf(cost)) cost += intrinsic_cost<DIM, ORD, YAW>(P, pr);
+    if (o.cost) o.cost[slot] = cost;
+    if (P.stats) {
+      // samples the reference loop visits: up to and including the first blocking one
+      const unsigned visited = seq ? seq_samples : (fb != kNoBlock ? (unsigned)fb + 1u : (unsigned)ns);
+      atomicAdd(&s_stats[0], (unsigned long long)visited);
+      atomicAdd(&s_stats[1], 1ull);
+    }
+  }
+  if (P.stats) {
+    __syncthreads();
+    if (threadIdx.x < 2) atomicAdd(&P.stats[threadIdx.x], s_stats[threadIdx.x]);
+  }
 }
 
 template <int DIM, int ORD, bool YAW>
 static cudaError_t launch_t(const EnvParams &P, const mplx_waypoint *d_nodes, int n_nodes,
-                            const mplx_succ_out &o, cudaStream_t st) {
+                            const mplx_succ_out &so, cudaStream_t st, int force_seq) {
+  const OutPtrs o{so.count, so.succ, so.cost, so.action, so.key, so.lattice};
   const int npb = P.nU >= kThreads ? 1 : kThreads / P.nU;
   const int grid = (n_nodes + npb - 1) / npb;
-  if (P.stats)
-    expand_kernel<DIM, ORD, YAW, true><<<grid, kThreads, 0, st>>>(
-        P, d_nodes, n_nodes, npb, o.count, o.succ, o.cost, o.action, o.key, o.lattice);
-  else
-    expand_kernel<DIM, ORD, YAW, false><<<grid, kThreads, 0, st>>>(
-        P, d_nodes, n_nodes, npb, o.count, o.succ, o.cost, o.action, o.key, o.lattice);
+  if (P.nU > kThreads || force_seq) {
+    expand_seq_kernel<DIM, ORD, YAW><<<grid, kThreads, 0, st>>>(P, d_nodes, n_nodes, npb, o);
+    return cudaGetLastError();
+  }
+  using L = FlatLayout<DIM, ORD, YAW>;
+  const bool need_vel = YAW || (P.pot != nullptr && P.grad_w != 0.0);
+  const int maxns = P.maxn + 1;
+  const size_t smem = kWarps * L::warp_bytes(need_vel, maxns);
+  static thread_local size_t configured = 0;  // per template instantiation and host thread
+  if (smem > 48 * 1024 && smem > configured) {
+    cudaError_t e = cudaFuncSetAttribute(expand_flat_kernel<DIM, ORD, YAW>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    configured = smem;
+  }
+  expand_flat_kernel<DIM, ORD, YAW><<<grid, kThreads, smem, st>>>(P, d_nodes, n_nodes, npb, o, maxns,
+                                                                   need_vel ? 1 : 0);
   return cudaGetLastError();
 }
 
 template <int DIM>
 static cudaError_t launch_d(const EnvParams &P, const mplx_waypoint *d_nodes, int n_nodes,
-                            const mplx_succ_out &o, cudaStream_t st) {
+                            const mplx_succ_out &o, cudaStream_t st, int fs) {
   const bool yaw = (P.control & 16) != 0;
   switch (P.control & 15) {
-    case MPLX_VEL: return yaw ? launch_t<DIM, 1, true>(P, d_nodes, n_nodes, o, st) : launch_t<DIM, 1, false>(P, d_nodes, n_nodes, o, st);
-    case MPLX_ACC: return yaw ? launch_t<DIM, 2, true>(P, d_nodes, n_nodes, o, st) : launch_t<DIM, 2, false>(P, d_nodes, n_nodes, o, st);
-    case MPLX_JRK: return yaw ? launch_t<DIM, 3, true>(P, d_nodes, n_nodes, o, st) : launch_t<DIM, 3, false>(P, d_nodes, n_nodes, o, st);
-    case MPLX_SNP: return yaw ? launch_t<DIM, 4, true>(P, d_nodes, n_nodes, o, st) : launch_t<DIM, 4, false>(P, d_nodes, n_nodes, o, st);
+    case MPLX_VEL: return yaw ? launch_t<DIM, 1, true>(P, d_nodes, n_nodes, o, st, fs) : launch_t<DIM, 1, false>(P, d_nodes, n_nodes, o, st, fs);
+    case MPLX_ACC: return yaw ? launch_t<DIM, 2, true>(P, d_nodes, n_nodes, o, st, fs) : launch_t<DIM, 2, false>(P, d_nodes, n_nodes, o, st, fs);
+    case MPLX_JRK: return yaw ? launch_t<DIM, 3, true>(P, d_nodes, n_nodes, o, st, fs) : launch_t<DIM, 3, false>(P, d_nodes, n_nodes, o, st, fs);
+    case MPLX_SNP: return yaw ? launch_t<DIM, 4, true>(P, d_nodes, n_nodes, o, st, fs) : launch_t<DIM, 4, false>(P, d_nodes, n_nodes, o, st, fs);
   }
   return cudaErrorInvalidValue;
 }
 
 cudaError_t launch_expand(const EnvParams &P, const mplx_waypoint *d_nodes, int n_nodes,
-                          const mplx_succ_out &o, cudaStream_t st) {
+                          const mplx_succ_out &o, cudaStream_t st, int force_seq) {
   if (n_nodes <= 0) return cudaSuccess;
-  return P.dim == 2 ? launch_d<2>(P, d_nodes, n_nodes, o, st) : launch_d<3>(P, d_nodes, n_nodes, o, st);
+  return P.dim == 2 ? launch_d<2>(P, d_nodes, n_nodes, o, st, force_seq)
+                    : launch_d<3>(P, d_nodes, n_nodes, o, st, force_seq);
 }
 
-// ---- set-up kernels -------------------------------------------------------------------
+// ---- set-up kernels -------------------------------------------------------------------------
 
-// std::vector<bool> search_region_ (env_base.h:400) arrives as one byte per voxel; pack it
-// to 1 bit per voxel so the per-sample test is a 4-byte read-only load.
-__global__ void pack_region_kernel(const uint8_t *__restrict__ bytes, size_t nvox,
-                                   uint32_t *__restrict__ bits) {
+// std::vector<bool> search_region_ (env_base.h:400) arrives as one byte per voxel; the grid
+// arrives as int8.  Both are packed to 1 bit per voxel (OCC: bit = (map == 100), isOccupied
+// map_util.h:48) so the per-sample test is a 4-byte read-only load from an L2-resident array.
+template <bool OCC>
+__global__ void pack_bits_kernel(const int8_t *__restrict__ bytes, size_t nvox, uint32_t *__restrict__ bits) {
   const size_t nwords = (nvox + 31) >> 5;
   for (size_t wd = (size_t)blockIdx.x * blockDim.x + threadIdx.x; wd < nwords;
        wd += (size_t)gridDim.x * blockDim.x) {
@@ -321,18 +634,44 @@ __global__ void pack_region_kernel(const uint8_t *__restrict__ bytes, size_t nvo
 #pragma unroll 8
     for (int b = 0; b < 32; b++) {
       const size_t i = b0 + b;
-      if (i < nvox && bytes[i]) m |= 1u << b;
+      if (i < nvox && (OCC ? bytes[i] == 100 : bytes[i] != 0)) m |= 1u << b;
     }
     bits[wd] = m;
   }
 }
 
-cudaError_t launch_pack_region(const uint8_t *d_bytes, size_t nvox, uint32_t *d_bits, cudaStream_t st) {
+cudaError_t launch_pack_bits(const int8_t *d_bytes, size_t nvox, uint32_t *d_bits, bool occ, cudaStream_t st) {
   const size_t nwords = (nvox + 31) >> 5;
   int grid = (int)((nwords + 255) / 256);
   if (grid > 148 * 16) grid = 148 * 16;
   if (grid < 1) grid = 1;
-  pack_region_kernel<<<grid, 256, 0, st>>>(d_bytes, nvox, d_bits);
+  if (occ)
+    pack_bits_kernel<true><<<grid, 256, 0, st>>>(d_bytes, nvox, d_bits);
+  else
+    pack_bits_kernel<false><<<grid, 256, 0, st>>>(d_bytes, nvox, d_bits);
+  return cudaGetLastError();
+}
+
+// Sample-time table: thread n runs the reference loop `for (t = 0; t < T; t += T/n)`
+// (env_map.h:98-99) once and records every t_k and the iteration count.
+__global__ void build_ttab_kernel(double T, double *__restrict__ ttab, int *__restrict__ tcount) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n > kNMax) return;
+  if (n < 1) {
+    tcount[n] = 0;
+    return;
+  }
+  const double dt = T / n;
+  int k = 0;
+  for (double t = 0; t < T; t += dt) {
+    if (k < kTStride) ttab[n * kTStride + k] = t;
+    k++;
+  }
+  tcount[n] = k;
+}
+
+cudaError_t launch_build_ttab(double T, double *d_ttab, int *d_tcount, cudaStream_t st) {
+  build_ttab_kernel<<<(kNMax + 1 + 127) / 128, 128, 0, st>>>(T, d_ttab, d_tcount);
   return cudaGetLastError();
 }
 

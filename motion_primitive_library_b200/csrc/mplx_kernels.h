@@ -10,7 +10,12 @@ namespace mplx {
 struct EnvParams;
 constexpr int kMaxU = 1024;  // |U| upper bound (125 is the largest set the reference's users build)
 
+// force_seq != 0 selects the literal per-thread sample loop (expand_seq_kernel) instead of
+// the flat kernel; results are identical.
 cudaError_t launch_expand(const EnvParams &P, const mplx_waypoint *d_nodes, int n_nodes,
-                          const mplx_succ_out &o, cudaStream_t st);
-cudaError_t launch_pack_region(const uint8_t *d_bytes, size_t nvox, uint32_t *d_bits, cudaStream_t st);
+                          const mplx_succ_out &o, cudaStream_t st, int force_seq);
+// bytes -> 1 bit/voxel: occ ? (byte == 100) : (byte != 0)
+cudaError_t launch_pack_bits(const int8_t *d_bytes, size_t nvox, uint32_t *d_bits, bool occ, cudaStream_t st);
+// sample-time table of `for (t = 0; t < T; t += T/n)` for n = 0..kNMax
+cudaError_t launch_build_ttab(double T, double *d_ttab, int *d_tcount, cudaStream_t st);
 }  // namespace mplx

@@ -235,6 +235,10 @@ class env_map:
         e = self.expand(node)
         return e.node(0)
 
+    def set_kernel(self, which: int):
+        """0 = auto (flat sample-parallel kernel), 1 = sequential per-primitive loop."""
+        abi.check(self._lib.mplx_set_kernel(self._h, int(which)))
+
     def enable_stats(self, on=True):
         abi.check(self._lib.mplx_enable_stats(self._h, 1 if on else 0))
 

@@ -40,12 +40,16 @@ def gpu_env(sc, region=None):
     return e
 
 
-def run_parity(sc, n, region=None, exact_cost=False, seed=7):
+def run_parity(sc, n, region=None, exact_cost=False, seed=7, kernels=(0, 1)):
+    """Both kernels (0 = flat sample-parallel, 1 = sequential per-primitive loop) against the oracle."""
     nodes = sc.frontier(n, seed=seed)
     orc = ob.OracleEnv.from_scenario(sc, region=region).expand(nodes, nthreads=8)
-    g = gpu_env(sc, region).expand(nodes, want=WANT)
-    st = assert_expansion_equal(g, orc, exact_cost=exact_cost)
-    assert st["successors"] > 0
+    env = gpu_env(sc, region)
+    for which in kernels:
+        env.set_kernel(which)
+        g = env.expand(nodes, want=WANT)
+        st = assert_expansion_equal(g, orc, exact_cost=exact_cost)
+        assert st["successors"] > 0
     return st, g, orc
 
 
@@ -170,9 +174,12 @@ def test_2d_vel_and_3d_snp_and_jrkyaw():
         nodes["yaw"] = rng.integers(-7, 8, n) * 0.4
         nodes["t"] = rng.integers(0, 5, n) * 1.0
         orc = ob.OracleEnv.from_scenario(sc).expand(nodes, nthreads=8)
-        g = gpu_env(sc).expand(nodes, want=WANT)
-        st = assert_expansion_equal(g, orc, exact_cost=(control & 16) == 0)
-        assert st["successors"] > n
+        env = gpu_env(sc)
+        for which in (0, 1):
+            env.set_kernel(which)
+            g = env.expand(nodes, want=WANT)
+            st = assert_expansion_equal(g, orc, exact_cost=(control & 16) == 0)
+            assert st["successors"] > n
 
 
 def test_empty_and_ragged_batches_and_pinned_buffers():
@@ -212,3 +219,36 @@ def test_setter_invalidation_and_stats():
     sc.v_max = 1.0
     assert_expansion_equal(e.expand(nodes, want=WANT), ob.OracleEnv.from_scenario(sc).expand(nodes), exact_cost=True)
     assert e.launch_count() >= 2
+
+
+def test_unbounded_velocity_falls_back_past_the_sample_table():
+    """v_max <= 0 (unlimited, env_base.h:380) with fast nodes: n = ceil(max_v*T/res) exceeds the
+    128-row sample-time table for some primitives -> in-kernel sequential fallback."""
+    from motion_primitive_library_b200.scenarios import control_set
+
+    sc = _custom(3, ACC, control_set(1.0, 3, 3), 64, 0.05)
+    sc.v_max = -1.0
+    rng = np.random.default_rng(5)
+    n = 600
+    nodes = np.zeros(n, dtype=ob.WAYPOINT_DTYPE)
+    nodes["pos"][:, :3] = np.round(rng.uniform(-1.2, 1.2, (n, 3)) / 0.05) * 0.05
+    nodes["vel"][:, :3] = rng.integers(-9, 10, (n, 3)) * 1.0  # up to 9 m/s / 0.05 m = n up to 200
+    orc = ob.OracleEnv.from_scenario(sc).expand(nodes, nthreads=8)
+    env = gpu_env(sc)
+    env.enable_stats(True)
+    g = env.expand(nodes, want=WANT)
+    assert_expansion_equal(g, orc, exact_cost=True)
+    samples, succ = env.last_stats()
+    t = ob.OracleEnv.from_scenario(sc).timed(nodes)
+    assert samples == t["samples"] and succ == t["successors"]
+
+
+def test_many_controls_uses_sequential_kernel():
+    """|U| = 343 > 256 primitives per node: served by the sequential kernel."""
+    from motion_primitive_library_b200.scenarios import control_set
+
+    sc = _custom(3, ACC, control_set(1.5, 7, 3), 48, 0.2, v_max=3.0)
+    nodes = sc.frontier(300, seed=9)
+    orc = ob.OracleEnv.from_scenario(sc).expand(nodes, nthreads=8)
+    g = gpu_env(sc).expand(nodes, want=WANT)
+    assert_expansion_equal(g, orc, exact_cost=True)
