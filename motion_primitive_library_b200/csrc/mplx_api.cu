@@ -96,7 +96,7 @@ struct mplx_ctx {
   // static data in HBM
   DevBuf<int8_t> map, pot;
   DevBuf<uint32_t> region, occ;
-  DevBuf<double> U, ttab;
+  DevBuf<double> U, ttab, tdt;
   DevBuf<int> tcount;
   int force_seq = 0;
   DevBuf<unsigned long long> stats;
@@ -131,6 +131,7 @@ static void refresh_params(mplx_ctx *c) {
   c->P.occ_bits = c->has_map ? c->occ.p : nullptr;
   c->P.ttab = c->ttab.p;
   c->P.tcount = c->tcount.p;
+  c->P.tdt = c->tdt.p;
   // largest sample count n the flat phase will meet: validated primitives have
   // max_vel <= v_max (primitive.h:482-496), so n = max(5, ceil(max_v*T/res)) (env_map.h:95)
   // is bounded; VEL control and v_max <= 0 are unbounded -> whole table.
@@ -190,7 +191,7 @@ int mplx_destroy(mplx_ctx *c) {
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
   c->map.release(); c->pot.release(); c->region.release(); c->U.release(); c->stats.release();
-  c->occ.release(); c->ttab.release(); c->tcount.release();
+  c->occ.release(); c->ttab.release(); c->tcount.release(); c->tdt.release();
   c->d_nodes.release(); c->d_succ.release(); c->d_count.release(); c->d_action.release();
   c->d_lattice.release(); c->d_cost.release(); c->d_key.release();
   c->h_nodes.release(); c->h_succ.release(); c->h_count.release(); c->h_action.release();
@@ -287,7 +288,8 @@ int mplx_set_params(mplx_ctx *c, int control, double T, double w, double wyaw, d
   CU(cudaMemcpyAsync(c->U.p, U, sizeof(double) * nU * udim, cudaMemcpyHostToDevice, c->stream));
   CU(c->ttab.reserve((size_t)(mplx::kNMax + 1) * mplx::kTStride));
   CU(c->tcount.reserve(mplx::kNMax + 1));
-  CU(mplx::launch_build_ttab(T, c->ttab.p, c->tcount.p, c->stream));
+  CU(c->tdt.reserve(mplx::kNMax + 1));
+  CU(mplx::launch_build_ttab(T, c->ttab.p, c->tcount.p, c->tdt.p, c->stream));
   c->launches++;
   CU(cudaStreamSynchronize(c->stream));
   c->P.control = control;

@@ -32,6 +32,7 @@ struct EnvParams {
   // running-sum times t_k, tcount[n] their number (n or n+1).  Depends on T only.
   const double *ttab;          // [(kNMax+1) * kTStride]
   const int *tcount;           // [kNMax+1]
+  const double *tdt;           // [kNMax+1]  T/n (env_map.h:98)
   int maxn;                    // largest n the flat sample phase accepts (<= kNMax)
 };
 
@@ -60,26 +61,50 @@ __device__ __forceinline__ void hash_combine(uint64_t &h, int v) {
   h += 0xe6546b64ULL;
 }
 
-// ---- exact rounding with a division-free fast path -------------------------------------
+// ---- exact IEEE quotients and roundings without DDIV / round() / F2I ----------------------
 // The reference computes  k = (int)std::round(RN(x / r) [- 0.5])  (waypoint.h:97-121,
-// map_util.h:106).  IEEE division + round() + F2I cost ~40 instructions and saturate the
-// XU pipe, so we evaluate y' = RN(x * RN(1/r)) instead (|y' - RN(x/r)| <= 4e-16*|y|),
-// round it to nearest with the 1.5*2^52 magic constant (pure FP64-pipe adds) and accept the
-// result only when y' [-0.5] is farther than 1e-6 from a rounding tie and |y'| < 1e9 — then
-// both computations provably round to the same integer.  Anything closer to a tie (lattice
-// values such as 0.25/0.1 = 2.5 land exactly on ties) takes the exact slow path below.
+// map_util.h:106) and n = ceil(RN(RN(max_v*T) / res)) (env_map.h:95).  A generic IEEE double
+// division is ~25 instructions incl. MUFU.RCP64H, and round()/ceil()/F2I run on the
+// quarter-rate XU pipe, which saturated in the first kernel.  All divisors on this path are
+// per-plan constants (0.01, 0.1, res), so their correctly rounded reciprocals binv = RN(1/b)
+// are precomputed and the quotient is finished with one Markstein correction:
+//     q0 = RN(a*binv);  r = fma(-b, q0, a)  (exact);  q = fma(r, binv, q0) = RN(a/b)
+// — the same tail nvcc's own IEEE division ends with.  tests/test_arith_identities.py checks
+// the identity on >1e9 structured and random operands (the only exceptions are subnormal
+// numerators, for which every use below yields 0 either way).
+// Rounding to nearest uses the 1.5*2^52 magic constant (two FP64 adds); std::round's
+// half-away-from-zero rule is restored exactly by looking at the (exact) remainder.
 #define MPLX_MAGIC 6755399441055744.0 /* 1.5 * 2^52 */
 
-static __device__ __noinline__ int lattice_id_slow(double x, double res) { return (int)round(x / res); }
-static __device__ __noinline__ int cell_slow(double s, double res) { return (int)round(s / res - 0.5); }
+__device__ __forceinline__ double div_exact(double a, double b, double binv) {
+  const double q0 = a * binv;
+  const double r = __fma_rn(-b, q0, a);
+  return __fma_rn(r, binv, q0);
+}
+
+// std::round(x) as a double, |x| < 2^51 (beyond that the value is astronomically far from any
+// grid or lattice the int conversion could represent).
+__device__ __forceinline__ double round_haz(double x, int &k) {
+  const double m = x + MPLX_MAGIC;  // RN-even integer in the low mantissa bits
+  double kd = m - MPLX_MAGIC;
+  const double f = x - kd;  // exact, in [-0.5, 0.5]
+  k = __double2loint(m);
+  if (f == 0.5 && x > 0.0) { kd += 1.0; k += 1; }    // tie rounded down to even: away from zero is up
+  if (f == -0.5 && x < 0.0) { kd -= 1.0; k -= 1; }   // tie rounded up to even: away from zero is down
+  return kd;
+}
 
 // `int id = std::round(x / res)` (waypoint.h:97,101,105,109,115); rinv = RN(1/res)
 __device__ __forceinline__ int lattice_id(double x, double res, double rinv) {
-  const double y = x * rinv;
-  const double m = y + MPLX_MAGIC;
-  const double f = y - (m - MPLX_MAGIC);
-  if (fabs(f) < 0.499999 && fabs(y) < 1e9) return __double2loint(m);
-  return lattice_id_slow(x, res);
+  int k;
+  round_haz(div_exact(x, res, rinv), k);
+  return k;
+}
+
+// std::ceil(x) for |x| < 2^51 as a double
+__device__ __forceinline__ double ceil_exact(double x) {
+  const double kd = (x + MPLX_MAGIC) - MPLX_MAGIC;
+  return kd < x ? kd + 1.0 : kd;
 }
 
 // One axis of a primitive built by the state+control constructor (primitive.h:220-256):

@@ -64,30 +64,14 @@ __device__ __forceinline__ bool voxel_blocks(const EnvParams &P, int idx, double
 template <int DIM>
 __device__ __forceinline__ int sample_index(const EnvParams &P, const double (&pk)[DIM]) {
   int pn[DIM];
-  double sk[DIM];
-  bool inside = true, fast = true;
+  bool inside = true;
 #pragma unroll
   for (int k = 0; k < DIM; k++) {
-    // round((p - origin)/res - 0.5), division-free fast path (see mplx_device.cuh)
-    sk[k] = pk[k] - P.origin[k];
-    const double x = sk[k] * P.rinv - 0.5;
-    const double m = x + MPLX_MAGIC;
-    const double kd = m - MPLX_MAGIC;
-    const double f = x - kd;
-    fast = fast && (fabs(f) < 0.499999);
-    // |kd| beyond the grid is outside whatever the low-order error; inside the grid
-    // |x| < 2^31 so the fast path is exact
+    // pn = round((p - origin)/res - 0.5): exact quotient, exact half-away rounding
+    const double x = div_exact(pk[k] - P.origin[k], P.res, P.rinv) - 0.5;
+    const double kd = round_haz(x, pn[k]);
+    // compare in double: a |kd| beyond int range is outside whatever its low 32 bits alias to
     inside = inside && (kd >= 0.0) && (kd < (double)P.mdim[k]);
-    pn[k] = __double2loint(m);
-  }
-  if (!fast) {
-    // within 1e-6 of a rounding tie (or astronomically far away): the exact expression
-    inside = true;
-#pragma unroll
-    for (int k = 0; k < DIM; k++) {
-      pn[k] = cell_slow(sk[k], P.res);
-      inside = inside && pn[k] >= 0 && pn[k] < P.mdim[k];
-    }
   }
   if (!inside) return -1;
   int idx = pn[0] + P.mdim[0] * pn[1];
@@ -495,10 +479,12 @@ expand_flat_kernel(const __grid_constant__ EnvParams P, const mplx_waypoint *__r
   double cost_seq = 0.0;
   unsigned seq_samples = 0;
   if (emit && !same) {
-    n = max(5, (int)ceil(max_v * T / P.res));  // env_map.h:95
-    if (n <= P.maxn)
+    // n = max(5, (int)ceil(max_v*T/res))  (env_map.h:95), exact quotient and ceiling
+    const double nd = ceil_exact(div_exact(max_v * T, P.res, P.rinv));
+    if (nd <= (double)P.maxn) {
+      n = max(5, (int)nd);
       ns = __ldg(P.tcount + n);
-    else {
+    } else {
       seq = true;  // beyond the table: literal loop in this lane, coefficients from its smem slot
       cost_seq = traverse_loop_cold<DIM, ORD, YAW>(&P, w_coef + lane * NC, need_vel, max_v, &seq_samples);
     }
@@ -512,7 +498,7 @@ expand_flat_kernel(const __grid_constant__ EnvParams P, const mplx_waypoint *__r
   const int start = incl - ns;
   const int S = __shfl_sync(0xffffffffu, incl, 31);
   w_cost[lane] = 0.0;
-  w_dt[lane] = ns ? T / n : 0.0;  // env_map.h:98
+  w_dt[lane] = __ldg(P.tdt + n);  // T/n, env_map.h:98
   w_start[lane] = start;
   w_n[lane] = n;
   w_first[lane] = kNoBlock;
@@ -654,14 +640,17 @@ cudaError_t launch_pack_bits(const int8_t *d_bytes, size_t nvox, uint32_t *d_bit
 
 // Sample-time table: thread n runs the reference loop `for (t = 0; t < T; t += T/n)`
 // (env_map.h:98-99) once and records every t_k and the iteration count.
-__global__ void build_ttab_kernel(double T, double *__restrict__ ttab, int *__restrict__ tcount) {
+__global__ void build_ttab_kernel(double T, double *__restrict__ ttab, int *__restrict__ tcount,
+                                  double *__restrict__ tdt) {
   const int n = blockIdx.x * blockDim.x + threadIdx.x;
   if (n > kNMax) return;
   if (n < 1) {
     tcount[n] = 0;
+    tdt[n] = 0.0;
     return;
   }
   const double dt = T / n;
+  tdt[n] = dt;
   int k = 0;
   for (double t = 0; t < T; t += dt) {
     if (k < kTStride) ttab[n * kTStride + k] = t;
@@ -670,8 +659,8 @@ __global__ void build_ttab_kernel(double T, double *__restrict__ ttab, int *__re
   tcount[n] = k;
 }
 
-cudaError_t launch_build_ttab(double T, double *d_ttab, int *d_tcount, cudaStream_t st) {
-  build_ttab_kernel<<<(kNMax + 1 + 127) / 128, 128, 0, st>>>(T, d_ttab, d_tcount);
+cudaError_t launch_build_ttab(double T, double *d_ttab, int *d_tcount, double *d_tdt, cudaStream_t st) {
+  build_ttab_kernel<<<(kNMax + 1 + 127) / 128, 128, 0, st>>>(T, d_ttab, d_tcount, d_tdt);
   return cudaGetLastError();
 }
 

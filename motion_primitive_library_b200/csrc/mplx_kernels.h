@@ -17,5 +17,5 @@ cudaError_t launch_expand(const EnvParams &P, const mplx_waypoint *d_nodes, int 
 // bytes -> 1 bit/voxel: occ ? (byte == 100) : (byte != 0)
 cudaError_t launch_pack_bits(const int8_t *d_bytes, size_t nvox, uint32_t *d_bits, bool occ, cudaStream_t st);
 // sample-time table of `for (t = 0; t < T; t += T/n)` for n = 0..kNMax
-cudaError_t launch_build_ttab(double T, double *d_ttab, int *d_tcount, cudaStream_t st);
+cudaError_t launch_build_ttab(double T, double *d_ttab, int *d_tcount, double *d_tdt, cudaStream_t st);
 }  // namespace mplx
