@@ -61,17 +61,25 @@ __device__ __forceinline__ bool voxel_blocks(const EnvParams &P, int idx, double
 
 // floatToInt + isOutside + getIndex (map_util.h:103-108, 51-55, 34-41) for one sample.
 // pk[] are the sample's position coordinates.  Returns the cell index or -1 when outside.
+//
+// With the exact quotient y = RN((p - origin)/res) the reference's
+//     pn = (int)std::round(RN(y - 0.5));   inside <=> 0 <= pn < dim
+// is equivalent to
+//     inside <=> 2^-55 < y < dim;          pn = floor(y)
+// because y - 0.5 is exact for y >= 0.5, rounds into (-0.5, 0) for 2^-55 < y < 0.5 and to
+// exactly -0.5 (-> -1, half away from zero) for 0 <= y <= 2^-55; a tie x = J - 0.5 with J >= 1
+// rounds up to J = floor(y).  (tests/arith_identities.cpp: check_cell_rule.)
 template <int DIM>
 __device__ __forceinline__ int sample_index(const EnvParams &P, const double (&pk)[DIM]) {
   int pn[DIM];
   bool inside = true;
 #pragma unroll
   for (int k = 0; k < DIM; k++) {
-    // pn = round((p - origin)/res - 0.5): exact quotient, exact half-away rounding
-    const double x = div_exact(pk[k] - P.origin[k], P.res, P.rinv) - 0.5;
-    const double kd = round_haz(x, pn[k]);
-    // compare in double: a |kd| beyond int range is outside whatever its low 32 bits alias to
-    inside = inside && (kd >= 0.0) && (kd < (double)P.mdim[k]);
+    const double y = div_exact(pk[k] - P.origin[k], P.res, P.rinv);
+    inside = inside && (y > 0x1p-55) && (y < (double)P.mdim[k]);
+    const double m = y + MPLX_MAGIC;      // nearest integer in the low mantissa bits
+    const double kd = m - MPLX_MAGIC;
+    pn[k] = __double2loint(m) - (kd > y ? 1 : 0);  // floor(y)
   }
   if (!inside) return -1;
   int idx = pn[0] + P.mdim[0] * pn[1];
@@ -428,18 +436,18 @@ expand_seq_kernel(const __grid_constant__ EnvParams P, const mplx_waypoint *__re
 // Per-warp shared-memory slab (doubles first so everything stays 8-byte aligned):
 //   coef [32][NC]  loop-invariant polynomial quotients of each lane's primitive
 //   cost [32]      accumulated potential / yaw cost        dt [32]  T/n
-//   start[32] n[32] first[32]  (int)                       owner[32*maxns] (uint8)
+//   n[32] first[32]  (int)        owner[32*maxns] (uint16: lane<<8 | sample k; k <= kNMax < 256)
 template <int DIM, int ORD, bool YAW>
 struct FlatLayout : CoefLayout<DIM, ORD, YAW> {
   using CoefLayout<DIM, ORD, YAW>::ncoef;
   __host__ __device__ static size_t warp_bytes(bool need_vel, int maxns) {
-    size_t b = (size_t)32 * ncoef(need_vel) * 8 + 32 * 8 * 2 + 32 * 4 * 3 + (size_t)32 * maxns;
+    size_t b = (size_t)32 * ncoef(need_vel) * 8 + 32 * 8 * 2 + 32 * 4 * 2 + (size_t)32 * maxns * 2;
     return (b + 15) & ~(size_t)15;
   }
 };
 
 template <int DIM, int ORD, bool YAW>
-__global__ void __launch_bounds__(kThreads, 3)
+__global__ void __launch_bounds__(kThreads, 4)
 expand_flat_kernel(const __grid_constant__ EnvParams P, const mplx_waypoint *__restrict__ nodes, int n_nodes,
                    int npb, const __grid_constant__ OutPtrs o, int maxns, int need_vel_i) {
   extern __shared__ __align__(16) unsigned char smem[];
@@ -453,10 +461,9 @@ expand_flat_kernel(const __grid_constant__ EnvParams P, const mplx_waypoint *__r
   double *w_coef = reinterpret_cast<double *>(wb);
   double *w_cost = w_coef + 32 * NC;
   double *w_dt = w_cost + 32;
-  int *w_start = reinterpret_cast<int *>(w_dt + 32);
-  int *w_n = w_start + 32;
+  int *w_n = reinterpret_cast<int *>(w_dt + 32);
   int *w_first = w_n + 32;
-  unsigned char *w_owner = reinterpret_cast<unsigned char *>(w_first + 32);
+  unsigned short *w_owner = reinterpret_cast<unsigned short *>(w_first + 32);
 
   const int nU = P.nU;
   const int items = npb * nU;  // <= 256
@@ -499,25 +506,29 @@ expand_flat_kernel(const __grid_constant__ EnvParams P, const mplx_waypoint *__r
   const int S = __shfl_sync(0xffffffffu, incl, 31);
   w_cost[lane] = 0.0;
   w_dt[lane] = __ldg(P.tdt + n);  // T/n, env_map.h:98
-  w_start[lane] = start;
   w_n[lane] = n;
   w_first[lane] = kNoBlock;
-  for (int k = 0; k < ns; k++) w_owner[start + k] = (unsigned char)lane;
+  for (int k = 0; k < ns; k++) w_owner[start + k] = (unsigned short)((lane << 8) | k);
   __syncwarp();
 
-  // ---- phase C: the warp's samples, dealt round-robin to its lanes ----
-  for (int s = lane; s < S; s += 32) {
-    const int i = w_owner[s];
-    const int k = s - w_start[i];
-    if (*(volatile int *)(w_first + i) < k) continue;  // an earlier sample already blocks: result is inf
+  // ---- phase C: the warp's samples, dealt round-robin to its lanes, two per lane per trip ----
+  // One sample: returns whether it blocks its primitive (env_map.h:104-121) and its cost term.
+  auto do_sample = [&](int s, bool valid, int &i, int &k, bool &blocked, double &term) {
+    blocked = false;
+    term = 0.0;
+    const unsigned ow = valid ? (unsigned)w_owner[s] : 0u;
+    i = (int)(ow >> 8);
+    k = (int)(ow & 255u);
+    // an earlier sample of this primitive already blocks: the result is inf whatever this one says
+    if (!valid || *(volatile int *)(w_first + i) < k) return;
     const double t = __ldg(P.ttab + w_n[i] * kTStride + k);
     const double *cf = w_coef + i * NC;
     double pk[DIM];
     eval_pos<DIM, ORD>(cf, t, pk);
     const int idx = sample_index<DIM>(P, pk);
     if (idx < 0) {
-      atomicMin(w_first + i, k);
-      continue;
+      blocked = true;
+      return;
     }
     double vel[DIM];
     double gterm = 0.0;
@@ -526,18 +537,24 @@ expand_flat_kernel(const __grid_constant__ EnvParams P, const mplx_waypoint *__r
       gterm = grad_term<DIM>(P, vel);
     }
     const double dt = w_dt[i];
-    double term = 0.0;
     if (voxel_blocks(P, idx, dt, gterm, term)) {
-      atomicMin(w_first + i, k);
-      continue;
+      blocked = true;
+      return;
     }
     if (YAW) {
-      if (P.wyaw > 0) {
-        const double yaw_u = cf[NC - 2], yaw0 = cf[NC - 1];
-        term += yaw_term(P, vel[0], vel[1], normalize_angle(yaw_u * t + yaw0), dt);
-      }
+      if (P.wyaw > 0) term += yaw_term(P, vel[0], vel[1], normalize_angle(cf[NC - 2] * t + cf[NC - 1]), dt);
     }
-    if (term != 0.0) atomicAdd(w_cost + i, term);
+  };
+  for (int s = lane; s < S; s += 64) {
+    int iA, kA, iB, kB;
+    bool bA, bB;
+    double tA, tB;
+    do_sample(s, true, iA, kA, bA, tA);
+    do_sample(s + 32, s + 32 < S, iB, kB, bB, tB);
+    if (bA) atomicMin(w_first + iA, kA);
+    if (bB) atomicMin(w_first + iB, kB);
+    if (tA != 0.0) atomicAdd(w_cost + iA, tA);
+    if (tB != 0.0) atomicAdd(w_cost + iB, tB);
   }
   __syncwarp();
 

@@ -30,6 +30,61 @@ static inline double ceil_exact(double x) {
   return kd < x ? kd + 1.0 : kd;
 }
 
+// sample_index's cell rule (mplx_kernels.cu): for the quotient y = RN((p-origin)/res),
+//   reference: pn = (int)std::round(RN(y - 0.5)); inside <=> 0 <= pn < dim   (map_util.h:103-108,51-55)
+//   kernel:    inside <=> 2^-55 < y < dim ; pn = floor(y)
+static long check_cell_rule() {
+  long bad = 0;
+  const int dims[] = {1, 2, 5, 199, 256, 512, 799, 100000};
+  auto one = [&](double y) {
+    for (int dim : dims) {
+      const double x = y - 0.5;
+      const double rr = std::round(x);
+      const bool in_ref = rr >= 0 && rr < dim;
+      const bool in_k = (y > 0x1p-55) && (y < (double)dim);
+      if (in_ref != in_k) { bad++; continue; }
+      if (in_ref) {
+        const double m = y + MAGIC, kd = m - MAGIC;
+        uint64_t bits;
+        std::memcpy(&bits, &m, 8);
+        const int pn = (int)(uint32_t)bits - (kd > y ? 1 : 0);
+        if (pn != (int)rr) bad++;
+      }
+    }
+  };
+  std::mt19937_64 rng(7);
+  std::uniform_real_distribution<double> U(0, 1);
+  for (int J = -3; J <= 100002; J++) {
+    if (J > 900 && J < 99990) continue;
+    for (double off : {0.0, 0.25, 0.5, 0.75}) {
+      double y = J + off;
+      one(y);
+      double a = y, b = y;
+      for (int i = 0; i < 3; i++) {
+        a = std::nextafter(a, 1e300);
+        b = std::nextafter(b, -1e300);
+        one(a);
+        one(b);
+      }
+    }
+    for (int i = 0; i < 20; i++) one(J + U(rng));
+  }
+  for (int e = -1080; e <= 60; e++)
+    for (double mnt : {1.0, 1.25, 1.5, 1.9999999999999998}) {
+      one(std::ldexp(mnt, e));
+      one(-std::ldexp(mnt, e));
+    }
+  one(0.0);
+  one(-0.0);
+  one(0x1p-55);
+  one(std::nextafter(0x1p-55, 1.0));
+  one(std::nextafter(0x1p-55, 0.0));
+  one(std::nan(""));
+  one(INFINITY);
+  one(-INFINITY);
+  return bad;
+}
+
 int main(int argc, char **argv) {
   const long nrand = argc > 1 ? atol(argv[1]) : 2000000;
   const long kmax = argc > 2 ? atol(argv[2]) : 60000;
@@ -85,6 +140,7 @@ int main(int argc, char **argv) {
       if (ceil_exact(x) != std::ceil(x)) bad_ceil++;
     }
   }
-  printf("cases %ld bad_div %ld bad_round %ld bad_ceil %ld\n", tot, bad_div, bad_round, bad_ceil);
-  return (bad_div || bad_round || bad_ceil) ? 1 : 0;
+  const long bad_cell = check_cell_rule();
+  printf("cases %ld bad_div %ld bad_round %ld bad_ceil %ld bad_cell %ld\n", tot, bad_div, bad_round, bad_ceil, bad_cell);
+  return (bad_div || bad_round || bad_ceil || bad_cell) ? 1 : 0;
 }
