@@ -1,0 +1,687 @@
+// mpl_host.hpp — host side of the planner above the libmplx C ABI, C++17, no Eigen/Boost.
+//
+// Mirrors the reference's C++ surface for the node-expansion path and its caller, with the
+// reference's names and argument meaning (citations are path:line in the reference checkout):
+//   MPL::MapUtil<Dim>          include/mpl_collision/map_util.h
+//   Waypoint<Dim>, hash_value  include/mpl_basis/waypoint.h
+//   MPL::env_base<Dim>         include/mpl_planner/common/env_base.h   (params, is_goal, get_heur, get_succ)
+//   MPL::env_map_gpu<Dim>      replaces env_map<Dim> (include/mpl_planner/env/env_map.h): get_succ via libmplx
+//   MPL::StateSpace / State    include/mpl_planner/common/state_space.h (A* part)
+//   MPL::GraphSearch::Astar    include/mpl_planner/common/graph_search.h:39-182, recoverTraj :369-455
+//   MPL::MapPlanner::plan      include/mpl_planner/common/planner_base.h:275-325, src/mpl_planner/map_planner.cpp:14-18
+// The search bookkeeping (hash map, priority queue) stays on the host, as in the reference; only
+// get_succ crosses the boundary.  The only addition is env_base::prefetch(): a hint that lets a
+// batching env expand the likely-next open nodes in the same launch.  get_succ is a pure function
+// of (node, env), so speculation cannot change which nodes A* expands or in which order.
+#pragma once
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <limits>
+#include <memory>
+#include <stdexcept>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/mplx.h"
+
+typedef double decimal_t;
+
+namespace Control {
+enum Control { NONE = 0, VEL = 0x01, ACC = 0x03, JRK = 0x07, SNP = 0x0f, VELxYAW = 0x11, ACCxYAW = 0x13, JRKxYAW = 0x17, SNPxYAW = 0x1f };
+}
+
+template <int N>
+struct Vecf {
+  decimal_t d[N];
+  Vecf() { for (int i = 0; i < N; i++) d[i] = 0; }
+  decimal_t &operator()(int i) { return d[i]; }
+  const decimal_t &operator()(int i) const { return d[i]; }
+  Vecf operator-(const Vecf &o) const { Vecf r; for (int i = 0; i < N; i++) r.d[i] = d[i] - o.d[i]; return r; }
+  Vecf operator+(const Vecf &o) const { Vecf r; for (int i = 0; i < N; i++) r.d[i] = d[i] + o.d[i]; return r; }
+  Vecf operator*(decimal_t k) const { Vecf r; for (int i = 0; i < N; i++) r.d[i] = d[i] * k; return r; }
+  Vecf operator/(decimal_t k) const { Vecf r; for (int i = 0; i < N; i++) r.d[i] = d[i] / k; return r; }
+  decimal_t lpNormInf() const { decimal_t m = 0; for (int i = 0; i < N; i++) m = std::max(m, std::abs(d[i])); return m; }
+};
+template <int N>
+struct Veci {
+  int d[N];
+  Veci() { for (int i = 0; i < N; i++) d[i] = 0; }
+  int &operator()(int i) { return d[i]; }
+  const int &operator()(int i) const { return d[i]; }
+  bool operator!=(const Veci &o) const { for (int i = 0; i < N; i++) if (d[i] != o.d[i]) return true; return false; }
+};
+template <typename T>
+using vec_E = std::vector<T>;
+using VecDf = std::vector<decimal_t>;
+
+/// Waypoint<Dim>: include/mpl_basis/waypoint.h:23-58
+template <int Dim>
+struct Waypoint {
+  Vecf<Dim> pos, vel, acc, jrk;
+  decimal_t yaw{0}, t{0};
+  int control{Control::NONE};
+  bool enable_t{false};
+  Waypoint() {}
+  explicit Waypoint(int c) : control(c) {}
+  bool use_pos() const { return control & 1; }
+  bool use_vel() const { return control & 2; }
+  bool use_acc() const { return control & 4; }
+  bool use_jrk() const { return control & 8; }
+  bool use_yaw() const { return control & 16; }
+};
+
+/// boost::hash_combine, 64-bit, Boost 1.56-1.80 (see DESIGN.md §2 for the version caveat)
+inline void hash_combine(std::size_t &h, int v) {
+  std::uint64_t k = (std::uint64_t)(std::int64_t)v;
+  const std::uint64_t m = 0xc6a4a7935bd1e995ULL;
+  k *= m; k ^= k >> 47; k *= m; h ^= k; h *= m; h += 0xe6546b64ULL;
+}
+/// hash_value(Waypoint): include/mpl_basis/waypoint.h:93-125 (host copy: start/goal nodes only;
+/// successor keys come back from the device)
+template <int Dim>
+std::size_t hash_value(const Waypoint<Dim> &key) {
+  std::size_t val = 0;
+  for (int i = 0; i < Dim; i++) {
+    if (key.use_pos()) { int id = std::round(key.pos(i) / 0.01); hash_combine(val, id); }
+    if (key.use_vel()) { int id = std::round(key.vel(i) / 0.1); hash_combine(val, id); }
+    if (key.use_acc()) { int id = std::round(key.acc(i) / 0.1); hash_combine(val, id); }
+    if (key.use_jrk()) { int id = std::round(key.jrk(i) / 0.1); hash_combine(val, id); }
+  }
+  if (key.use_yaw()) { int id = std::round(key.yaw / 0.1); hash_combine(val, id); }
+  if (key.enable_t) { int id = std::round(key.t / 0.1); hash_combine(val, id); }
+  return val;
+}
+
+namespace MPL {
+using Tmap = std::vector<signed char>;
+
+/// MapUtil<Dim>: include/mpl_collision/map_util.h (storage + the lookups the planner's host side uses)
+template <int Dim>
+class MapUtil {
+ public:
+  Tmap getMap() { return map_; }
+  const Tmap &map() const { return map_; }
+  decimal_t getRes() { return res_; }
+  Veci<Dim> getDim() { return dim_; }
+  Vecf<Dim> getOrigin() { return origin_d_; }
+  int getIndex(const Veci<Dim> &pn) {
+    return Dim == 2 ? pn(0) + dim_(0) * pn(1) : pn(0) + dim_(0) * pn(1) + dim_(0) * dim_(1) * pn(Dim - 1);
+  }
+  bool isFree(int idx) { return map_[idx] < val_occ && map_[idx] >= val_free; }
+  bool isOccupied(int idx) { return map_[idx] == val_occ; }
+  bool isOutside(const Veci<Dim> &pn) {
+    for (int i = 0; i < Dim; i++) if (pn(i) < 0 || pn(i) >= dim_(i)) return true;
+    return false;
+  }
+  bool isFree(const Veci<Dim> &pn) { return isOutside(pn) ? false : isFree(getIndex(pn)); }
+  bool isOccupied(const Veci<Dim> &pn) { return isOutside(pn) ? false : isOccupied(getIndex(pn)); }
+  void setMap(const Vecf<Dim> &ori, const Veci<Dim> &dim, const Tmap &map, decimal_t res) {
+    map_ = map; dim_ = dim; origin_d_ = ori; res_ = res; version_++;
+  }
+  Veci<Dim> floatToInt(const Vecf<Dim> &pt) {
+    Veci<Dim> pn;
+    for (int i = 0; i < Dim; i++) pn(i) = std::round((pt(i) - origin_d_(i)) / res_ - 0.5);
+    return pn;
+  }
+  /// rayTrace: map_util.h:120-137
+  vec_E<Veci<Dim>> rayTrace(const Vecf<Dim> &pt1, const Vecf<Dim> &pt2) {
+    Vecf<Dim> diff = pt2 - pt1;
+    decimal_t k = 0.8;
+    int max_diff = (diff / res_).lpNormInf() / k;
+    decimal_t s = 1.0 / max_diff;
+    Vecf<Dim> step = diff * s;
+    vec_E<Veci<Dim>> pns;
+    Veci<Dim> prev_pn;
+    for (int i = 0; i < Dim; i++) prev_pn(i) = -1;
+    for (int n = 1; n < max_diff; n++) {
+      Vecf<Dim> pt = pt1 + step * n;
+      Veci<Dim> new_pn = floatToInt(pt);
+      if (isOutside(new_pn)) break;
+      if (new_pn != prev_pn) pns.push_back(new_pn);
+      prev_pn = new_pn;
+    }
+    return pns;
+  }
+  void freeUnknown() { for (auto &v : map_) if (v == val_unknown) v = val_free; version_++; }
+  unsigned long version() const { return version_; }
+
+ protected:
+  decimal_t res_{1};
+  Vecf<Dim> origin_d_;
+  Veci<Dim> dim_;
+  Tmap map_;
+  unsigned long version_{0};
+  int8_t val_occ = 100, val_free = 0, val_unknown = -1;
+};
+typedef MapUtil<2> OccMapUtil;
+typedef MapUtil<3> VoxelMapUtil;
+
+/// env_base<Dim>: include/mpl_planner/common/env_base.h (the members the A* path touches)
+template <int Dim>
+class env_base {
+ public:
+  virtual ~env_base() {}
+  /// env_base.h:23-41
+  virtual bool is_goal(const Waypoint<Dim> &state) const {
+    if (state.t >= t_max_) return true;
+    bool goaled = (state.pos - goal_node_.pos).lpNormInf() <= tol_pos_;
+    if (goaled && tol_vel_ >= 0) goaled = (state.vel - goal_node_.vel).lpNormInf() <= tol_vel_;
+    if (goaled && tol_acc_ >= 0) goaled = (state.acc - goal_node_.acc).lpNormInf() <= tol_acc_;
+    if (goaled && tol_yaw_ >= 0) goaled = std::abs(state.yaw - goal_node_.yaw) <= tol_yaw_;
+    return goaled;
+  }
+  /// env_base.h:48-64 (heur_ignore_dynamics_ == true, the default: :368)
+  virtual decimal_t get_heur(const Waypoint<Dim> &state) const {
+    if (hash_value(goal_node_) == hash_value(state)) return 0;
+    if (v_max_ > 0) return w_ * (state.pos - goal_node_.pos).lpNormInf() / v_max_;
+    return w_ * (state.pos - goal_node_.pos).lpNormInf();
+  }
+  void set_u(const vec_E<VecDf> &U) { U_ = U; touch(); }
+  void set_v_max(decimal_t v) { v_max_ = v; touch(); }
+  void set_a_max(decimal_t a) { a_max_ = a; touch(); }
+  void set_j_max(decimal_t j) { j_max_ = j; touch(); }
+  void set_yaw_max(decimal_t yaw) { yaw_max_ = yaw; touch(); }
+  void set_dt(decimal_t dt) { dt_ = dt; touch(); }
+  void set_tol_pos(decimal_t pos) { tol_pos_ = pos; }
+  void set_tol_vel(decimal_t vel) { tol_vel_ = vel; }
+  void set_tol_acc(decimal_t acc) { tol_acc_ = acc; }
+  void set_tol_yaw(decimal_t yaw) { tol_yaw_ = yaw; }
+  void set_w(decimal_t w) { w_ = w; touch(); }
+  void set_wyaw(decimal_t wyaw) { wyaw_ = wyaw; touch(); }
+  void set_t_max(int t) { t_max_ = t; }
+  bool set_goal(const Waypoint<Dim> &state) { goal_node_ = state; return true; }
+  virtual void set_potential_weight(decimal_t) {}
+  virtual void set_gradient_weight(decimal_t) {}
+  virtual void set_potential_map(const std::vector<int8_t> &) {}
+  void set_search_region(const std::vector<bool> &r) { search_region_ = r; touch(); }
+  decimal_t get_dt() const { return dt_; }
+  virtual bool is_free(const Vecf<Dim> &) const { return true; }
+  /// env_base.h:358-362
+  virtual void get_succ(const Waypoint<Dim> &curr, vec_E<Waypoint<Dim>> &succ, std::vector<decimal_t> &succ_cost,
+                        std::vector<int> &action_idx) const = 0;
+  /// Extension: candidates the search is likely to expand next (results are pure, so a batching
+  /// env may expand them together with the next get_succ call; default: ignore).
+  virtual void prefetch(const vec_E<Waypoint<Dim>> &) const {}
+  virtual void begin_plan() const {}
+
+  bool heur_ignore_dynamics_{true};
+  decimal_t w_{10.0}, wyaw_{1.0};
+  decimal_t tol_pos_{0.5}, tol_vel_{-1.0}, tol_acc_{-1.0}, tol_yaw_{-1.0};
+  decimal_t v_max_{-1.0}, a_max_{-1.0}, j_max_{-1.0}, yaw_max_{-1.0};
+  decimal_t t_max_{std::numeric_limits<decimal_t>::infinity()};
+  decimal_t dt_{1.0};
+  vec_E<VecDf> U_;
+  Waypoint<Dim> goal_node_;
+  std::vector<bool> search_region_;
+  mutable vec_E<Vecf<Dim>> expanded_nodes_;
+
+ protected:
+  void touch() { params_version_++; }
+  unsigned long params_version_{1};
+};
+
+/// The host-only members of env_map<Dim> (include/mpl_planner/env/env_map.h:25-51): goal test with
+/// ray-trace and the start-point free test.  They run on the host against the MapUtil copy.
+template <int Dim>
+class env_map_host : public env_base<Dim> {
+ public:
+  explicit env_map_host(std::shared_ptr<MapUtil<Dim>> map_util) : map_util_(map_util) {}
+  /// env_map.h:25-45
+  bool is_goal(const Waypoint<Dim> &state) const override {
+    bool goaled = (state.pos - this->goal_node_.pos).lpNormInf() <= this->tol_pos_;
+    if (goaled && this->tol_vel_ >= 0) goaled = (state.vel - this->goal_node_.vel).lpNormInf() <= this->tol_vel_;
+    if (goaled && this->tol_acc_ >= 0) goaled = (state.acc - this->goal_node_.acc).lpNormInf() <= this->tol_acc_;
+    if (goaled && this->tol_yaw_ >= 0) goaled = std::abs(state.yaw - this->goal_node_.yaw) <= this->tol_yaw_;
+    if (goaled) {
+      auto pns = map_util_->rayTrace(state.pos, this->goal_node_.pos);
+      for (const auto &it : pns) if (map_util_->isOccupied(it)) return false;
+    }
+    return goaled;
+  }
+  /// env_map.h:48-51
+  bool is_free(const Vecf<Dim> &pt) const override { return map_util_->isFree(map_util_->floatToInt(pt)); }
+
+ protected:
+  std::shared_ptr<MapUtil<Dim>> map_util_;
+};
+
+/// env_map_gpu<Dim>: env_map<Dim> (include/mpl_planner/env/env_map.h) with get_succ served by
+/// libmplx (CUDA).  Throws std::runtime_error when the engine cannot be created: no CPU fallback.
+template <int Dim>
+class env_map_gpu : public env_map_host<Dim> {
+  using env_map_host<Dim>::map_util_;
+
+ public:
+  explicit env_map_gpu(std::shared_ptr<MapUtil<Dim>> map_util, int device = 0) : env_map_host<Dim>(map_util) {
+    if (mplx_create(Dim, device, &ctx_) != MPLX_OK) throw std::runtime_error(mplx_last_error());
+  }
+  ~env_map_gpu() override { mplx_destroy(ctx_); }
+  env_map_gpu(const env_map_gpu &) = delete;
+
+  void set_potential_map(const std::vector<int8_t> &map) override { potential_map_ = map; this->touch(); }
+  void set_potential_weight(decimal_t w) override { potential_weight_ = w; this->touch(); }
+  void set_gradient_weight(decimal_t w) override { gradient_weight_ = w; this->touch(); }
+  void set_control(int control) { control_ = control; this->touch(); }
+  /// nodes speculatively expanded per launch (1 = plain one-node get_succ)
+  void set_speculation(int k) { speculate_ = std::max(1, k); }
+
+  void begin_plan() const override { cache_.clear(); stats_nodes_ = stats_calls_ = stats_hits_ = 0; }
+
+  /// env_map.h:147-172.  Served from the speculation cache when possible.
+  void get_succ(const Waypoint<Dim> &curr, vec_E<Waypoint<Dim>> &succ, std::vector<decimal_t> &succ_cost,
+                std::vector<int> &action_idx) const override {
+    succ.clear(); succ_cost.clear(); action_idx.clear();
+    this->expanded_nodes_.push_back(curr.pos);  // env_map.h:154, at real pop time
+    const std::size_t key = hash_value(curr);
+    auto it = cache_.find(key);
+    if (it == cache_.end()) {
+      vec_E<Waypoint<Dim>> batch{curr};
+      for (const auto &c : pending_) {
+        if ((int)batch.size() >= speculate_) break;
+        const std::size_t k = hash_value(c);
+        if (k != key && !cache_.count(k)) batch.push_back(c);
+      }
+      pending_.clear();
+      expand_batch(batch);
+      it = cache_.find(key);
+    } else {
+      stats_hits_++;
+    }
+    const Entry &e = it->second;
+    for (std::size_t j = 0; j < e.cost.size(); j++) {
+      succ.push_back(from_pod(e.succ[j], curr.control));
+      succ_cost.push_back(e.cost[j]);
+      action_idx.push_back(e.action[j]);
+    }
+    cache_.erase(it);  // A* expands a node once
+  }
+  void prefetch(const vec_E<Waypoint<Dim>> &cands) const override { pending_ = cands; }
+
+  long stats_nodes() const { return stats_nodes_; }
+  long stats_calls() const { return stats_calls_; }
+  long stats_hits() const { return stats_hits_; }
+  long launches() const { return (long)mplx_launch_count(ctx_); }
+
+ private:
+  struct Entry { std::vector<mplx_waypoint> succ; std::vector<double> cost; std::vector<int> action; };
+  static void check(int rc) { if (rc != MPLX_OK) throw std::runtime_error(mplx_last_error()); }
+  static mplx_waypoint to_pod(const Waypoint<Dim> &w) {
+    mplx_waypoint p{};
+    for (int d = 0; d < Dim; d++) { p.pos[d] = w.pos(d); p.vel[d] = w.vel(d); p.acc[d] = w.acc(d); p.jrk[d] = w.jrk(d); }
+    p.yaw = w.yaw; p.t = w.t;
+    return p;
+  }
+  static Waypoint<Dim> from_pod(const mplx_waypoint &p, int control) {
+    Waypoint<Dim> w(control);
+    for (int d = 0; d < Dim; d++) { w.pos(d) = p.pos[d]; w.vel(d) = p.vel[d]; w.acc(d) = p.acc[d]; w.jrk(d) = p.jrk[d]; }
+    w.yaw = p.yaw; w.t = p.t;
+    return w;
+  }
+  void sync() const {
+    if (map_version_ != map_util_->version()) {
+      const Veci<Dim> dim = map_util_->getDim();
+      const Vecf<Dim> ori = map_util_->getOrigin();
+      check(mplx_set_map(ctx_, map_util_->map().data(), dim.d, ori.d, map_util_->getRes()));
+      map_version_ = map_util_->version();
+      sent_version_ = 0;
+    }
+    if (sent_version_ != this->params_version_) {
+      if (this->U_.empty()) throw std::runtime_error("env_map_gpu: set_u() was not called");
+      const int udim = (int)this->U_.front().size();
+      std::vector<double> U;
+      for (const auto &u : this->U_) for (int k = 0; k < udim; k++) U.push_back(u[k]);
+      check(mplx_set_params(ctx_, control_, this->dt_, this->w_, this->wyaw_, this->v_max_, this->a_max_,
+                            this->j_max_, this->yaw_max_, U.data(), (int)this->U_.size(), udim));
+      check(mplx_set_potential(ctx_, potential_map_.empty() ? nullptr : potential_map_.data(), potential_weight_,
+                               gradient_weight_));
+      if (this->search_region_.empty()) check(mplx_set_search_region(ctx_, nullptr));
+      else {
+        std::vector<uint8_t> r(this->search_region_.begin(), this->search_region_.end());
+        check(mplx_set_search_region(ctx_, r.data()));
+      }
+      sent_version_ = this->params_version_;
+    }
+  }
+  void expand_batch(const vec_E<Waypoint<Dim>> &batch) const {
+    sync();
+    const int n = (int)batch.size(), nU = (int)this->U_.size();
+    in_.resize(n);
+    for (int i = 0; i < n; i++) in_[i] = to_pod(batch[i]);
+    count_.resize(n); succ_.resize((std::size_t)n * nU); cost_.resize((std::size_t)n * nU); action_.resize((std::size_t)n * nU);
+    mplx_succ_out out{count_.data(), succ_.data(), cost_.data(), action_.data(), nullptr, nullptr};
+    check(mplx_expand(ctx_, in_.data(), n, &out));
+    for (int i = 0; i < n; i++) {
+      Entry e;
+      const std::size_t o = (std::size_t)i * nU;
+      e.succ.assign(succ_.begin() + o, succ_.begin() + o + count_[i]);
+      e.cost.assign(cost_.begin() + o, cost_.begin() + o + count_[i]);
+      e.action.assign(action_.begin() + o, action_.begin() + o + count_[i]);
+      cache_[hash_value(batch[i])] = std::move(e);
+    }
+    stats_nodes_ += n;
+    stats_calls_++;
+  }
+
+  mplx_ctx *ctx_ = nullptr;
+  int control_ = Control::NONE, speculate_ = 1;
+  std::vector<int8_t> potential_map_;
+  decimal_t potential_weight_{0.1}, gradient_weight_{0.0};
+  mutable unsigned long map_version_ = ~0ul, sent_version_ = 0;
+  mutable std::unordered_map<std::size_t, Entry> cache_;
+  mutable vec_E<Waypoint<Dim>> pending_;
+  mutable std::vector<mplx_waypoint> in_, succ_;
+  mutable std::vector<int32_t> count_, action_;
+  mutable std::vector<double> cost_;
+  mutable long stats_nodes_ = 0, stats_calls_ = 0, stats_hits_ = 0;
+};
+
+/// State: include/mpl_planner/common/state_space.h:36-74 (A* members)
+template <int Dim>
+struct State {
+  Waypoint<Dim> coord;
+  std::size_t key;
+  std::vector<std::size_t> pred_key;
+  std::vector<int> pred_action_id;
+  std::vector<decimal_t> pred_action_cost;
+  int heap_idx = -1;
+  decimal_t fval = 0;
+  decimal_t g = std::numeric_limits<decimal_t>::infinity();
+  decimal_t rhs = std::numeric_limits<decimal_t>::infinity();
+  decimal_t h = std::numeric_limits<decimal_t>::infinity();
+  bool iterationopened = false, iterationclosed = false;
+  State(const Waypoint<Dim> &c, std::size_t k) : coord(c), key(k) {}
+};
+
+/// priorityQueue: boost::heap::d_ary_heap<pair<f, State*>, arity<2>, mutable_<true>,
+/// compare<compare_pair>> (state_space.h:16-34) restated: binary heap with position handles;
+/// push = append + sift up, pop = swap root with last + sift down, increase = sift up; a child
+/// replaces its parent unless it compares strictly lower.
+template <int Dim>
+class PriorityQueue {
+ public:
+  using S = State<Dim>;
+  /// compare_pair (state_space.h:16-27): true when p1 has LOWER priority than p2
+  static bool lower(const S *p1, const S *p2) {
+    if (p1->fval == p2->fval) return std::min(p1->g, p1->rhs) > std::min(p2->g, p2->rhs);
+    return p1->fval > p2->fval;
+  }
+  bool empty() const { return q_.empty(); }
+  std::size_t size() const { return q_.size(); }
+  S *top() const { return q_.front(); }
+  const std::vector<S *> &raw() const { return q_; }
+  void push(S *s) { s->heap_idx = (int)q_.size(); q_.push_back(s); siftup(s->heap_idx); }
+  void pop() {
+    swap_at(0, (int)q_.size() - 1);
+    q_.back()->heap_idx = -1;
+    q_.pop_back();
+    if (!q_.empty()) siftdown(0);
+  }
+  void increase(S *s) { siftup(s->heap_idx); }
+
+ private:
+  void swap_at(int a, int b) { std::swap(q_[a], q_[b]); q_[a]->heap_idx = a; q_[b]->heap_idx = b; }
+  void siftup(int i) {
+    while (i != 0) {
+      int p = (i - 1) / 2;
+      if (lower(q_[p], q_[i])) { swap_at(p, i); i = p; } else return;
+    }
+  }
+  void siftdown(int i) {
+    const int n = (int)q_.size();
+    while (2 * i + 1 < n) {
+      int c = 2 * i + 1;
+      if (c + 1 < n && lower(q_[c], q_[c + 1])) c = c + 1;  // first maximum among the children
+      if (!lower(q_[c], q_[i])) { swap_at(c, i); i = c; } else return;
+    }
+  }
+  std::vector<S *> q_;
+};
+
+/// StateSpace: state_space.h:81-114 (A* part)
+template <int Dim>
+struct StateSpace {
+  PriorityQueue<Dim> pq_;
+  std::unordered_map<std::size_t, std::unique_ptr<State<Dim>>> hm_;
+  decimal_t eps_;
+  decimal_t dt_{1};
+  std::vector<State<Dim> *> best_child_;
+  int expand_iteration_ = 0;
+  explicit StateSpace(decimal_t eps = 1) : eps_(eps) {}
+};
+
+/// One edge of the recovered trajectory (the reference stores Primitive<Dim>; a primitive built
+/// by the state+control constructor is fully described by its start node and action id,
+/// env_base.h:228-231).
+template <int Dim>
+struct Edge { Waypoint<Dim> from; int action_id; };
+
+/// GraphSearch::Astar: include/mpl_planner/common/graph_search.h:39-182
+template <int Dim>
+class GraphSearch {
+ public:
+  explicit GraphSearch(bool verbose = false, int lookahead = 0) : verbose_(verbose), lookahead_(lookahead) {}
+
+  decimal_t Astar(const Waypoint<Dim> &start_coord, const std::shared_ptr<env_base<Dim>> &ENV,
+                  std::shared_ptr<StateSpace<Dim>> &ss_ptr, std::vector<Edge<Dim>> &traj, int max_expand = -1) {
+    using S = State<Dim>;
+    const decimal_t inf = std::numeric_limits<decimal_t>::infinity();
+    traj.clear();
+    if (ENV->is_goal(start_coord)) return 0;
+    const std::size_t start_key = hash_value(start_coord);
+    S *currNode_ptr = nullptr;
+    if (ss_ptr->pq_.empty()) {
+      auto &slot = ss_ptr->hm_[start_key];
+      slot.reset(new S(start_coord, start_key));
+      currNode_ptr = slot.get();
+      currNode_ptr->g = 0;
+      currNode_ptr->h = ss_ptr->eps_ == 0 ? 0 : ENV->get_heur(start_coord);
+      currNode_ptr->fval = currNode_ptr->g + ss_ptr->eps_ * currNode_ptr->h;
+      ss_ptr->pq_.push(currNode_ptr);
+      currNode_ptr->iterationopened = true;
+      currNode_ptr->iterationclosed = false;
+    }
+    int expand_iteration = 0;
+    vec_E<Waypoint<Dim>> succ_coord;
+    std::vector<decimal_t> succ_cost;
+    std::vector<int> succ_act_id;
+    vec_E<Waypoint<Dim>> cands;
+    while (true) {
+      expand_iteration++;
+      currNode_ptr = ss_ptr->pq_.top();
+      if (lookahead_ > 0) {
+        // hint: the open nodes nearest the root of the heap are the likeliest next pops
+        cands.clear();
+        const auto &raw = ss_ptr->pq_.raw();
+        for (std::size_t i = 1; i < raw.size() && (int)cands.size() < lookahead_; i++) cands.push_back(raw[i]->coord);
+        ENV->prefetch(cands);
+      }
+      ss_ptr->pq_.pop();
+      currNode_ptr->iterationclosed = true;
+
+      ENV->get_succ(currNode_ptr->coord, succ_coord, succ_cost, succ_act_id);
+
+      for (unsigned s = 0; s < succ_coord.size(); ++s) {
+        if (std::isinf(succ_cost[s])) continue;  // graph_search.h:81
+        const std::size_t skey = hash_value(succ_coord[s]);
+        auto &slot = ss_ptr->hm_[skey];
+        if (!slot) {
+          slot.reset(new S(succ_coord[s], skey));
+          slot->h = ss_ptr->eps_ == 0 ? 0 : ENV->get_heur(slot->coord);
+        }
+        S *succNode_ptr = slot.get();
+        succNode_ptr->pred_key.push_back(currNode_ptr->key);
+        succNode_ptr->pred_action_cost.push_back(succ_cost[s]);
+        succNode_ptr->pred_action_id.push_back(succ_act_id[s]);
+        decimal_t tentative_gval = currNode_ptr->g + succ_cost[s];
+        if (tentative_gval < succNode_ptr->g) {
+          succNode_ptr->g = tentative_gval;
+          decimal_t fval = succNode_ptr->g + (ss_ptr->eps_) * succNode_ptr->h;
+          if (succNode_ptr->iterationopened && !succNode_ptr->iterationclosed) {
+            succNode_ptr->fval = fval;
+            ss_ptr->pq_.increase(succNode_ptr);
+          } else {
+            succNode_ptr->fval = fval;
+            ss_ptr->pq_.push(succNode_ptr);
+            succNode_ptr->iterationopened = true;
+          }
+        }
+      }
+      if (ENV->is_goal(currNode_ptr->coord)) break;
+      if (max_expand > 0 && expand_iteration >= max_expand) {
+        if (verbose_) printf("MaxExpandStep [%d] Reached!!!!!!\n\n", max_expand);
+        ss_ptr->expand_iteration_ = expand_iteration;
+        return inf;
+      }
+      if (ss_ptr->pq_.empty()) {
+        if (verbose_) printf("Priority queue is empty!!!!!!\n\n");
+        ss_ptr->expand_iteration_ = expand_iteration;
+        return inf;
+      }
+    }
+    ss_ptr->expand_iteration_ = expand_iteration;
+    if (recoverTraj(currNode_ptr, ss_ptr, start_key, traj)) return currNode_ptr->g;
+    return inf;
+  }
+
+ private:
+  /// recoverTraj: graph_search.h:369-455
+  bool recoverTraj(State<Dim> *currNode_ptr, std::shared_ptr<StateSpace<Dim>> ss_ptr, std::size_t start_key,
+                   std::vector<Edge<Dim>> &traj) {
+    const decimal_t inf = std::numeric_limits<decimal_t>::infinity();
+    ss_ptr->best_child_.clear();
+    bool find_traj = false;
+    std::vector<Edge<Dim>> prs;
+    while (!currNode_ptr->pred_key.empty()) {
+      ss_ptr->best_child_.push_back(currNode_ptr);
+      int min_id = -1;
+      decimal_t min_rhs = inf, min_g = inf;
+      for (unsigned int i = 0; i < currNode_ptr->pred_key.size(); i++) {
+        State<Dim> *pred = ss_ptr->hm_[currNode_ptr->pred_key[i]].get();
+        if (min_rhs > pred->g + currNode_ptr->pred_action_cost[i]) {
+          min_rhs = pred->g + currNode_ptr->pred_action_cost[i];
+          min_g = pred->g;
+          min_id = i;
+        } else if (!std::isinf(currNode_ptr->pred_action_cost[i]) &&
+                   min_rhs == pred->g + currNode_ptr->pred_action_cost[i]) {
+          if (min_g < pred->g) {
+            min_g = pred->g;
+            min_id = i;
+          }
+        }
+      }
+      if (min_id >= 0) {
+        int action_idx = currNode_ptr->pred_action_id[min_id];
+        currNode_ptr = ss_ptr->hm_[currNode_ptr->pred_key[min_id]].get();
+        prs.push_back(Edge<Dim>{currNode_ptr->coord, action_idx});  // forward_action(coord, action): env_base.h:228-231
+      } else
+        break;
+      if (currNode_ptr->key == start_key) {
+        ss_ptr->best_child_.push_back(currNode_ptr);
+        find_traj = true;
+        break;
+      }
+    }
+    std::reverse(prs.begin(), prs.end());
+    std::reverse(ss_ptr->best_child_.begin(), ss_ptr->best_child_.end());
+    traj = find_traj ? prs : std::vector<Edge<Dim>>();
+    return find_traj;
+  }
+  bool verbose_;
+  int lookahead_;
+};
+
+/// PlannerBase + MapPlanner: include/mpl_planner/common/planner_base.h, planner/map_planner.h
+template <int Dim>
+class PlannerBase {
+ public:
+  explicit PlannerBase(bool verbose = false) : planner_verbose_(verbose) {}
+  virtual ~PlannerBase() {}
+  bool initialized() { return !(ss_ptr_ == nullptr); }
+  std::vector<Edge<Dim>> getTraj() const { return traj_; }
+  decimal_t getTrajCost() const { return traj_cost_; }
+  int getExpandedNum() const { return ss_ptr_ ? ss_ptr_->expand_iteration_ : 0; }
+  vec_E<Vecf<Dim>> getExpandedNodes() const { return ENV_->expanded_nodes_; }
+  /// getCloseSet (planner_base.h): states with iterationclosed
+  std::vector<const State<Dim> *> getCloseSetStates() const {
+    std::vector<const State<Dim> *> v;
+    for (const auto &it : ss_ptr_->hm_) if (it.second && it.second->iterationclosed) v.push_back(it.second.get());
+    return v;
+  }
+  std::size_t getOpenSetSize() const {
+    std::size_t n = 0;
+    for (const auto &it : ss_ptr_->hm_) if (it.second && it.second->iterationopened && !it.second->iterationclosed) n++;
+    return n;
+  }
+  void setVmax(decimal_t v) { ENV_->set_v_max(v); }
+  void setAmax(decimal_t a) { ENV_->set_a_max(a); }
+  void setJmax(decimal_t j) { ENV_->set_j_max(j); }
+  void setYawmax(decimal_t yaw) { ENV_->set_yaw_max(yaw); }
+  void setTmax(decimal_t t) { ENV_->set_t_max(t); }
+  void setDt(decimal_t dt) { ENV_->set_dt(dt); }
+  void setW(decimal_t w) { ENV_->set_w(w); }
+  void setWyaw(decimal_t w) { ENV_->set_wyaw(w); }
+  void setEpsilon(decimal_t eps) { epsilon_ = eps; }
+  void setMaxNum(int num) { max_num_ = num; }
+  void setU(const vec_E<VecDf> &U) { ENV_->set_u(U); }
+  void setTol(decimal_t tol_pos, decimal_t tol_vel = -1, decimal_t tol_acc = -1) {
+    ENV_->set_tol_pos(tol_pos); ENV_->set_tol_vel(tol_vel); ENV_->set_tol_acc(tol_acc);
+  }
+  void setLookahead(int k) { lookahead_ = k; }
+
+  /// planner_base.h:275-325 (A* branch)
+  bool plan(const Waypoint<Dim> &start, const Waypoint<Dim> &goal) {
+    if (!ENV_->is_free(start.pos)) {
+      printf("[PlannerBase] start is not free!\n");
+      return false;
+    }
+    GraphSearch<Dim> planner(planner_verbose_, lookahead_);
+    ss_ptr_.reset(new StateSpace<Dim>(epsilon_));
+    ENV_->set_goal(goal);
+    ENV_->expanded_nodes_.clear();
+    ENV_->begin_plan();
+    ss_ptr_->dt_ = ENV_->get_dt();
+    traj_cost_ = planner.Astar(start, ENV_, ss_ptr_, traj_, max_num_);
+    if (std::isinf(traj_cost_)) return false;
+    return true;
+  }
+
+ protected:
+  std::shared_ptr<env_base<Dim>> ENV_;
+  std::shared_ptr<StateSpace<Dim>> ss_ptr_;
+  std::vector<Edge<Dim>> traj_;
+  decimal_t traj_cost_ = 0;
+  decimal_t epsilon_ = 1.0;
+  int max_num_ = -1;
+  int lookahead_ = 0;
+  bool planner_verbose_;
+};
+
+template <int Dim>
+class MapPlanner : public PlannerBase<Dim> {
+ public:
+  explicit MapPlanner(bool verbose = false) : PlannerBase<Dim>(verbose) {}
+  /// src/mpl_planner/map_planner.cpp:14-18 — installs the GPU env instead of env_map<Dim>
+  virtual void setMapUtil(const std::shared_ptr<MapUtil<Dim>> &map_util, int device = 0) {
+    gpu_env_.reset(new env_map_gpu<Dim>(map_util, device));
+    this->ENV_ = gpu_env_;
+    map_util_ = map_util;
+  }
+  /// Any env_base implementation (the closed-set equality tests install a CPU checker env here).
+  void setEnv(const std::shared_ptr<env_base<Dim>> &env) { this->ENV_ = env; gpu_env_.reset(); }
+  void setControl(int control) { if (gpu_env_) gpu_env_->set_control(control); }
+  void setSpeculation(int k) { if (gpu_env_) gpu_env_->set_speculation(k); this->setLookahead(k > 1 ? 4 * k : 0); }
+  void setPotentialWeight(decimal_t w) { this->ENV_->set_potential_weight(w); }
+  void setGradientWeight(decimal_t w) { this->ENV_->set_gradient_weight(w); }
+  env_map_gpu<Dim> *gpu_env() { return gpu_env_.get(); }
+
+ protected:
+  std::shared_ptr<MapUtil<Dim>> map_util_;
+  std::shared_ptr<env_map_gpu<Dim>> gpu_env_;
+};
+typedef MapPlanner<2> OccMapPlanner;
+typedef MapPlanner<3> VoxelMapPlanner;
+}  // namespace MPL

@@ -130,3 +130,50 @@ def wp(pos, vel=None, acc=None, jrk=None, yaw=0.0, t=0.0):
             w[name][: len(v)] = v
     w["yaw"], w["t"] = yaw, t
     return w
+
+
+# ---- oracle/_ref: the unmodified reference headers behind the same C ABI -------------------------
+REF_LIB = ORACLE_DIR / "_ref" / "libmplref.so"
+_ref = None
+
+
+def ref_available() -> bool:
+    return REF_LIB.exists()
+
+
+def ref_lib():
+    """oracle/_ref/libmplref.so (built by `make -C oracle ref` where /root/reference exists)."""
+    global _ref
+    if _ref is None:
+        L = C.CDLL(str(REF_LIB))
+        vp = C.c_void_p
+        L.ref_expand_batch.argtypes = [C.POINTER(OrcEnv), vp, C.c_int, vp, vp, vp, vp, vp, C.c_int]
+        L.ref_expand_batch.restype = C.c_int
+        L.ref_expand_batch_timed.argtypes = [C.POINTER(OrcEnv), vp, C.c_int, C.c_int, C.POINTER(C.c_int64),
+                                             C.POINTER(C.c_double)]
+        L.ref_expand_batch_timed.restype = C.c_int
+        L.ref_info.argtypes = []
+        L.ref_info.restype = C.c_char_p
+        _ref = L
+    return _ref
+
+
+def ref_expand(env: "OracleEnv", nodes, nthreads=1):
+    """Run the REFERENCE's env_map<Dim>::get_succ on `nodes` with the parameters held by `env`."""
+    nodes = np.ascontiguousarray(nodes, dtype=WAYPOINT_DTYPE).reshape(-1)
+    n, nU = nodes.size, env.nU
+    succ = np.zeros(n * nU, dtype=WAYPOINT_DTYPE)
+    cost = np.zeros(n * nU)
+    action = np.zeros(n * nU, dtype=np.int32)
+    key = np.zeros(n * nU, dtype=np.uint64)
+    count = np.zeros(n, dtype=np.int32)
+    ref_lib().ref_expand_batch(C.byref(env.e), nodes.ctypes.data, n, succ.ctypes.data, cost.ctypes.data,
+                               action.ctypes.data, key.ctypes.data, count.ctypes.data, nthreads)
+    return dict(count=count, succ=succ, cost=cost, action=action, key=key, lattice=None, nU=nU)
+
+
+def ref_timed(env: "OracleEnv", nodes, nthreads=1):
+    nodes = np.ascontiguousarray(nodes, dtype=WAYPOINT_DTYPE).reshape(-1)
+    a, s = C.c_int64(), C.c_double()
+    ref_lib().ref_expand_batch_timed(C.byref(env.e), nodes.ctypes.data, nodes.size, nthreads, C.byref(a), C.byref(s))
+    return dict(seconds=s.value, successors=a.value)
