@@ -71,47 +71,75 @@ def make_env(sc, device):
 
 
 class ClockSampler:
-    """nvidia-smi clocks/throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    """SM clock and throttle reasons sampled DURING the timed region (B200_PROFILING.md).
 
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-         "clocks_event_reasons.sw_power_cap")
+    Polls NVML from a background thread (a timed region of a few ms is far shorter than
+    nvidia-smi's minimum loop period); falls back to `nvidia-smi -lms` when pynvml is missing."""
+
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
 
     def __init__(self, gpu_index=0):
-        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
-        self.p = None
         self.idx = gpu_index
+        self.samples = []
+        self._stop = False
+        self._thr = None
+        self._h = None
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            # CUDA_VISIBLE_DEVICES may remap ordinals: resolve through the PCI bus id of the torch device
+            import torch
+
+            bus = torch.cuda.get_device_properties(gpu_index).pci_bus_id if hasattr(
+                torch.cuda.get_device_properties(gpu_index), "pci_bus_id") else None
+            self._h = pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
+            if bus is not None:
+                for i in range(pynvml.nvmlDeviceGetCount()):
+                    h = pynvml.nvmlDeviceGetHandleByIndex(i)
+                    if pynvml.nvmlDeviceGetPciInfo(h).bus == bus:
+                        self._h = h
+            self.sm_max = float(pynvml.nvmlDeviceGetMaxClockInfo(self._h, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self.nv = None
+
+    def _poll(self):
+        nv = self.nv
+        while not self._stop:
+            try:
+                sm = nv.nvmlDeviceGetClockInfo(self._h, nv.NVML_CLOCK_SM)
+                rs = nv.nvmlDeviceGetCurrentClocksEventReasons(self._h) if hasattr(
+                    nv, "nvmlDeviceGetCurrentClocksEventReasons") else nv.nvmlDeviceGetCurrentClocksThrottleReasons(self._h)
+                pw = nv.nvmlDeviceGetPowerUsage(self._h) / 1000.0
+                self.samples.append((float(sm), int(rs), pw))
+            except Exception:
+                break
+            time.sleep(0.0005)
 
     def start(self):
-        try:
-            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                       "-lms", "100", "-i", str(self.idx)], stdout=self.f, stderr=subprocess.DEVNULL)
-        except OSError:
-            self.p = None
+        if self.nv is None:
+            return
+        import threading
+
+        self._thr = threading.Thread(target=self._poll, daemon=True)
+        self._thr.start()
 
     def stop(self):
-        if self.p is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.p.terminate()
-        try:
-            self.p.wait(timeout=5)
-        except subprocess.TimeoutExpired:
-            self.p.kill()
-        self.f.flush()
-        rows = [r.split(",") for r in Path(self.f.name).read_text().strip().splitlines() if r.count(",") >= 8]
-        os.unlink(self.f.name)
-        if not rows:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
-        sm = sorted(float(r[1]) for r in rows)
+        if self.nv is None or self._thr is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvml unavailable"]}
+        self._stop = True
+        self._thr.join(timeout=2)
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.sm_max, "reasons": ["no samples"]}
+        sm = sorted(s[0] for s in self.samples)
         reasons = set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in rows:
-            for k, nm in enumerate(names):
-                if r[5 + k].strip().lower().startswith("active"):
+        for _, rs, _ in self.samples:
+            for bit, nm in self.REASONS.items():
+                if rs & bit:
                     reasons.add(nm)
-        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(rows[0][2]), "samples": len(rows),
-                "power_w_max": max(float(r[3]) for r in rows), "reasons": sorted(reasons)}
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": self.sm_max, "samples": len(self.samples),
+                "power_w_max": max(s[2] for s in self.samples), "reasons": sorted(reasons), "source": "nvml"}
 
 
 def algorithmic_bytes(nU, mean_samples_per_node, mean_succ_per_node, has_region):
@@ -279,11 +307,57 @@ def main():
     elapsed_ms = float(t_el.item())
     value = world * n * args.steps / (elapsed_ms * 1e-3)
 
-    # ---- e2e: the reference-facing C-ABI call with HOST (pinned) buffers, copies inside the timed region
+    # ---- e2e: the reference-facing C-ABI calls with HOST (pinned) buffers, copies inside the timed region.
+    #   e2e        mplx_expand_packed, flags=DROP_INF: what the A* host consumes per successor — state fields
+    #              marked by the control flag + cost + action + key, +inf successors dropped on the device
+    #              (graph_search.h:81), double-buffered over two streams.  This is the call the planner makes.
+    #   e2e_full   mplx_expand: the literal get_succ contract (112 B Waypoint + cost + action + key, inf kept).
     e2e = None
+    e2e_full = None
     if not args.no_e2e:
+        from motion_primitive_library_b200.abi import PackedOut
+
+        def timed_host(step, steps):
+            for _ in range(2):
+                step()
+            torch.cuda.synchronize()
+            if world > 1:
+                dist.barrier()
+            l0 = env.launch_count()
+            t0 = time.perf_counter()
+            for _ in range(steps):
+                step()
+            torch.cuda.synchronize()
+            t1 = time.perf_counter()
+            t_e = torch.tensor([t1 - t0], dtype=torch.float64, device="cuda")
+            if world > 1:
+                dist.all_reduce(t_e, op=dist.ReduceOp.MAX)
+            return float(t_e.item()), env.launch_count() - l0
+
+        e2e_steps = max(3, min(args.steps, 10))
         h_nodes = env._pinned_empty(n, WAYPOINT_DTYPE)
         h_nodes[:] = nodes_np
+        nstate = sc.Dim * bin(sc.control & 15).count("1") + (1 if sc.control & 16 else 0)
+        pb = dict(count=env._pinned_empty(n, np.int32), offset=env._pinned_empty(n, np.int64),
+                  state=env._pinned_empty(slots * nstate, np.float64), cost=env._pinned_empty(slots, np.float64),
+                  action=env._pinned_empty(slots, np.uint16), key=env._pinned_empty(slots, np.uint64))
+        out_p = PackedOut(pb["count"].ctypes.data, pb["offset"].ctypes.data, pb["state"].ctypes.data,
+                          pb["cost"].ctypes.data, pb["action"].ctypes.data, pb["key"].ctypes.data, slots, 0, 0)
+
+        def step_packed():
+            abi.check(lib.mplx_expand_packed(env.handle, h_nodes.ctypes.data, n, abi.PACK_DROP_INF, C.byref(out_p)))
+
+        secs, launches = timed_host(step_packed, e2e_steps)
+        kept = int(out_p.total)
+        assert int(pb["count"].sum()) == kept and 0 < kept <= succ_total  # the result is read on the host
+        e2e = {"value": world * n * e2e_steps / secs, "unit": UNIT, "h2d_bytes_per_step": int(n * 112),
+               "d2h_bytes_per_step": int(n * 12 + kept * (8 * nstate + 8 + 2 + 8)), "steps": e2e_steps,
+               "ms_per_step": 1e3 * secs / e2e_steps, "launches": int(launches),
+               "records_per_step": kept,
+               "call": "mplx_expand_packed(flags=MPLX_PACK_DROP_INF), pinned host buffers: per finite successor "
+                       f"{nstate} state doubles + cost + key + u16 action; per node count + offset"}
+        del pb
+
         h_count = env._pinned_empty(n, np.int32)
         h_succ = env._pinned_empty(slots, WAYPOINT_DTYPE)
         h_cost = env._pinned_empty(slots, np.float64)
@@ -295,30 +369,12 @@ def main():
         def step_host():
             abi.check(lib.mplx_expand(env.handle, h_nodes.ctypes.data, n, C.byref(out_h)))
 
-        e2e_steps = max(3, min(args.steps, 10))
-        for _ in range(2):
-            step_host()
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        l0 = env.launch_count()
-        t0 = time.perf_counter()
-        for _ in range(e2e_steps):
-            step_host()
-        torch.cuda.synchronize()
-        t1 = time.perf_counter()
-        e2e_launches = env.launch_count() - l0
-        t_e = torch.tensor([t1 - t0], dtype=torch.float64, device="cuda")
-        if world > 1:
-            dist.all_reduce(t_e, op=dist.ReduceOp.MAX)
-        checksum = int(h_count.sum())  # the step's result is read on the host
-        assert checksum == succ_total, (checksum, succ_total)
-        e2e = {"value": world * n * e2e_steps / float(t_e.item()), "unit": UNIT,
-               "h2d_bytes_per_step": int(n * 112),
-               "d2h_bytes_per_step": int(n * 4 + slots * (112 + 8 + 4 + 8)),
-               "steps": e2e_steps, "ms_per_step": 1e3 * float(t_e.item()) / e2e_steps,
-               "launches": int(e2e_launches), "buffers": "pinned host (mplx_host_alloc), full 132 B successor records"}
-        gpu_launches += 0  # e2e launches reported separately above
+        secs, launches = timed_host(step_host, max(3, e2e_steps // 2))
+        assert int(h_count.sum()) == succ_total
+        e2e_full = {"value": world * n * max(3, e2e_steps // 2) / secs, "unit": UNIT,
+                    "h2d_bytes_per_step": int(n * 112), "d2h_bytes_per_step": int(n * 4 + slots * (112 + 8 + 4 + 8)),
+                    "ms_per_step": 1e3 * secs / max(3, e2e_steps // 2), "launches": int(launches),
+                    "call": "mplx_expand: full get_succ contract, 132 B per successor slot, +inf kept"}
 
     if rank != 0:
         if world > 1:
@@ -362,7 +418,8 @@ def main():
                    "primitives_per_sec": value * nU, "parallelism": f"replicas x{world}, frontier sharded",
                    "l2": f"per-step working set {(n * 112 + slots * 132 + int(np.prod(sc.dim_cells))) / 1e6:.0f} MB "
                          f"(frontier + successor records + map) exceeds the 126 MB L2"},
-        "clocks": clocks, "e2e": e2e, "gpu_launches": int(gpu_launches), "roofline": roofline,
+        "clocks": clocks, "e2e": e2e, "e2e_full_contract": e2e_full, "gpu_launches": int(gpu_launches),
+        "roofline": roofline,
         "cpu_baseline": cpu_baseline,
     }
     print(json.dumps(line), flush=True)

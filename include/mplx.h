@@ -122,6 +122,38 @@ int mplx_expand(mplx_ctx *ctx, const mplx_waypoint *nodes, int n_nodes, const mp
 int mplx_expand_device(mplx_ctx *ctx, const void *d_nodes, int n_nodes, const mplx_succ_out *out,
                        void *stream);
 
+/* ---- packed result stream (hosts across PCIe) ------------------------------------------ */
+
+/* Drop successors whose edge cost is +inf (A* skips them: graph_search.h:81; LPA* keeps them). */
+#define MPLX_PACK_DROP_INF 1
+
+/* Dense result of mplx_expand_packed.  Record r of node i, r in [offset[i], offset[i]+count[i]),
+ * in increasing control index.  `state` holds only the Waypoint fields the control flag marks as
+ * state (use_pos, use_vel, use_acc, use_jrk, use_yaw: include/mpl_basis/waypoint.h:47-56), as
+ * nstate = Dim*popcount(control&15) + (yaw?1:0) doubles per record laid out
+ * [pos[Dim], vel[Dim], (acc[Dim]), (jrk[Dim]), (yaw)].  The remaining Waypoint fields of a
+ * successor are copies, not results: evaluated derivative above the state order = 0 + U[action]
+ * (next one) or 0, yaw = 0 without a yaw control, t = curr.t + dt (env_map.h:161).
+ * state/cost/action/key may be NULL to skip; capacity is in records. */
+typedef struct {
+  int32_t *count;   /* [n_nodes]                                              */
+  int64_t *offset;  /* [n_nodes] first record of node i                        */
+  double *state;    /* [capacity*nstate]                                       */
+  double *cost;     /* [capacity]   succ_cost                                  */
+  uint16_t *action; /* [capacity]   action_idx                                 */
+  uint64_t *key;    /* [capacity]   hash_value(succ), waypoint.h:93            */
+  int64_t capacity; /* in: records the arrays can hold (n_nodes*nU always suffices) */
+  int64_t total;    /* out: records written                                    */
+  int32_t nstate;   /* out: doubles per state record                           */
+} mplx_packed_out;
+
+/* Batched env_map::get_succ with HOST buffers and the packed result stream: chunks of the
+ * batch are expanded, packed on the device and copied back double-buffered over two streams,
+ * so the PCIe transfer of one chunk overlaps the expansion of the next.  Pinned host buffers
+ * (mplx_host_alloc) are needed for that overlap; pageable ones work but serialise. */
+int mplx_expand_packed(mplx_ctx *ctx, const mplx_waypoint *nodes, int n_nodes, int flags,
+                       mplx_packed_out *out);
+
 /* Kernel selection (diagnostics): 0 = auto (the flat sample-parallel kernel whenever
  * |U| <= 256), 1 = the sequential kernel that keeps traverse_primitive's literal per-primitive
  * loop (env_map.h:99-130).  Both produce identical results. */

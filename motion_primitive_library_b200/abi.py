@@ -37,6 +37,7 @@ EXPORTED_SYMBOLS = (
     "mplx_set_params",
     "mplx_expand",
     "mplx_expand_device",
+    "mplx_expand_packed",
     "mplx_set_kernel",
     "mplx_sync",
     "mplx_launch_count",
@@ -60,6 +61,25 @@ class SuccOut(C.Structure):
         ("key", C.c_void_p),
         ("lattice", C.c_void_p),
     ]
+
+
+class PackedOut(C.Structure):
+    """mplx_packed_out"""
+
+    _fields_ = [
+        ("count", C.c_void_p),
+        ("offset", C.c_void_p),
+        ("state", C.c_void_p),
+        ("cost", C.c_void_p),
+        ("action", C.c_void_p),
+        ("key", C.c_void_p),
+        ("capacity", C.c_int64),
+        ("total", C.c_int64),
+        ("nstate", C.c_int32),
+    ]
+
+
+PACK_DROP_INF = 1
 
 
 class MplxError(RuntimeError):
@@ -103,6 +123,8 @@ def load() -> C.CDLL:
     lib.mplx_expand.restype = i32
     lib.mplx_expand_device.argtypes = [vp, vp, i32, C.POINTER(SuccOut), vp]
     lib.mplx_expand_device.restype = i32
+    lib.mplx_expand_packed.argtypes = [vp, vp, i32, i32, C.POINTER(PackedOut)]
+    lib.mplx_expand_packed.restype = i32
     lib.mplx_set_kernel.argtypes = [vp, i32]
     lib.mplx_set_kernel.restype = i32
     lib.mplx_sync.argtypes = [vp]

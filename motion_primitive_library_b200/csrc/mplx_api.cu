@@ -13,13 +13,10 @@
 #include <vector>
 
 #include "../../include/mplx.h"
-#include "mplx_device.cuh"
-#include "mplx_kernels.h"
+#include "mplx_internal.h"
 
-namespace {
-
+namespace mplx {
 thread_local char g_err[512] = "";
-
 int fail(int code, const char *fmt, ...) {
   va_list ap;
   va_start(ap, fmt);
@@ -27,96 +24,10 @@ int fail(int code, const char *fmt, ...) {
   va_end(ap);
   return code;
 }
+}  // namespace mplx
+using mplx::g_err;
 
-#define CU(call)                                                                              \
-  do {                                                                                        \
-    cudaError_t e_ = (call);                                                                  \
-    if (e_ != cudaSuccess) {                                                                  \
-      cudaGetLastError();                                                                     \
-      return fail(e_ == cudaErrorMemoryAllocation ? MPLX_ERR_ALLOC : MPLX_ERR_CUDA,           \
-                  "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
-    }                                                                                         \
-  } while (0)
-
-template <typename T>
-struct DevBuf {
-  T *p = nullptr;
-  size_t cap = 0;  // elements
-  cudaError_t reserve(size_t n) {
-    if (n <= cap) return cudaSuccess;
-    if (p) cudaFree(p);
-    p = nullptr;
-    cap = 0;
-    cudaError_t e = cudaMalloc((void **)&p, n * sizeof(T));
-    if (e == cudaSuccess) cap = n;
-    return e;
-  }
-  void release() {
-    if (p) cudaFree(p);
-    p = nullptr;
-    cap = 0;
-  }
-};
-
-template <typename T>
-struct PinBuf {
-  T *p = nullptr;
-  size_t cap = 0;
-  cudaError_t reserve(size_t n) {
-    if (n <= cap) return cudaSuccess;
-    if (p) cudaFreeHost(p);
-    p = nullptr;
-    cap = 0;
-    cudaError_t e = cudaHostAlloc((void **)&p, n * sizeof(T), cudaHostAllocDefault);
-    if (e == cudaSuccess) cap = n;
-    return e;
-  }
-  void release() {
-    if (p) cudaFreeHost(p);
-    p = nullptr;
-    cap = 0;
-  }
-};
-
-bool is_pinned(const void *p) {
-  if (!p) return false;
-  cudaPointerAttributes a;
-  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
-    cudaGetLastError();
-    return false;
-  }
-  return a.type == cudaMemoryTypeHost;
-}
-
-}  // namespace
-
-struct mplx_ctx {
-  int dim = 0, device = 0;
-  cudaStream_t stream = nullptr;
-  // static data in HBM
-  DevBuf<int8_t> map, pot;
-  DevBuf<uint32_t> region, occ;
-  DevBuf<double> U, ttab, tdt;
-  DevBuf<int> tcount;
-  int force_seq = 0;
-  DevBuf<unsigned long long> stats;
-  bool has_map = false, has_pot = false, has_region = false, has_params = false, stats_on = false;
-  size_t nvox = 0;
-  mplx::EnvParams P;
-  // per-call staging (host-buffer entry point)
-  DevBuf<mplx_waypoint> d_nodes, d_succ;
-  DevBuf<int32_t> d_count, d_action, d_lattice;
-  DevBuf<double> d_cost;
-  DevBuf<uint64_t> d_key;
-  PinBuf<mplx_waypoint> h_nodes, h_succ;
-  PinBuf<int32_t> h_count, h_action, h_lattice;
-  PinBuf<double> h_cost;
-  PinBuf<uint64_t> h_key;
-  int64_t launches = 0;
-  unsigned long long last_stats[2] = {0, 0};
-};
-
-static int bind(mplx_ctx *ctx) {
+int mplx_bind(mplx_ctx *ctx) {
   if (!ctx) return fail(MPLX_ERR_ARG, "null ctx");
   CU(cudaSetDevice(ctx->device));
   return MPLX_OK;
@@ -192,6 +103,7 @@ int mplx_destroy(mplx_ctx *c) {
   cudaStreamSynchronize(c->stream);
   c->map.release(); c->pot.release(); c->region.release(); c->U.release(); c->stats.release();
   c->occ.release(); c->ttab.release(); c->tcount.release(); c->tdt.release();
+  c->cb[0].release(); c->cb[1].release();
   c->d_nodes.release(); c->d_succ.release(); c->d_count.release(); c->d_action.release();
   c->d_lattice.release(); c->d_cost.release(); c->d_key.release();
   c->h_nodes.release(); c->h_succ.release(); c->h_count.release(); c->h_action.release();
@@ -202,7 +114,7 @@ int mplx_destroy(mplx_ctx *c) {
 }
 
 int mplx_set_map(mplx_ctx *c, const int8_t *data, const int32_t *dim, const double *origin, double res) {
-  if (int r = bind(c)) return r;
+  if (int r = mplx_bind(c)) return r;
   if (!data || !dim || !origin) return fail(MPLX_ERR_ARG, "null argument");
   if (!(res > 0)) return fail(MPLX_ERR_ARG, "res must be > 0");
   size_t nvox = 1;
@@ -233,7 +145,7 @@ int mplx_set_map(mplx_ctx *c, const int8_t *data, const int32_t *dim, const doub
 }
 
 int mplx_set_potential(mplx_ctx *c, const int8_t *data, double pw, double gw) {
-  if (int r = bind(c)) return r;
+  if (int r = mplx_bind(c)) return r;
   if (!c->has_map) return fail(MPLX_ERR_ARG, "mplx_set_map must be called first");
   c->P.pot_w = pw;
   c->P.grad_w = gw;
@@ -251,7 +163,7 @@ int mplx_set_potential(mplx_ctx *c, const int8_t *data, double pw, double gw) {
 }
 
 int mplx_set_search_region(mplx_ctx *c, const uint8_t *in_region) {
-  if (int r = bind(c)) return r;
+  if (int r = mplx_bind(c)) return r;
   if (!c->has_map) return fail(MPLX_ERR_ARG, "mplx_set_map must be called first");
   if (!in_region) {
     c->has_region = false;
@@ -274,7 +186,7 @@ int mplx_set_search_region(mplx_ctx *c, const uint8_t *in_region) {
 
 int mplx_set_params(mplx_ctx *c, int control, double T, double w, double wyaw, double v_max,
                     double a_max, double j_max, double yaw_max, const double *U, int nU, int udim) {
-  if (int r = bind(c)) return r;
+  if (int r = mplx_bind(c)) return r;
   const int base = control & 15;
   if ((control & ~31) || (base != MPLX_VEL && base != MPLX_ACC && base != MPLX_JRK && base != MPLX_SNP))
     return fail(MPLX_ERR_ARG, "control 0x%x is not a Control::Control value (control.h:10-20)", control);
@@ -308,17 +220,21 @@ int mplx_set_params(mplx_ctx *c, int control, double T, double w, double wyaw, d
   return MPLX_OK;
 }
 
-static int check_ready(mplx_ctx *c, int n_nodes, const mplx_succ_out *out) {
+int mplx_check_ready(mplx_ctx *c, int n_nodes) {
   if (!c->has_map) return fail(MPLX_ERR_ARG, "no map: call mplx_set_map first");
   if (!c->has_params) return fail(MPLX_ERR_ARG, "no params: call mplx_set_params first");
   if (n_nodes < 0) return fail(MPLX_ERR_ARG, "n_nodes < 0");
-  if (!out || !out->count) return fail(MPLX_ERR_ARG, "out->count is required");
   if ((size_t)n_nodes * c->P.nU >= ((size_t)1 << 31)) return fail(MPLX_ERR_ARG, "batch too large");
+  return MPLX_OK;
+}
+static int check_ready(mplx_ctx *c, int n_nodes, const mplx_succ_out *out) {
+  if (int r = mplx_check_ready(c, n_nodes)) return r;
+  if (!out || !out->count) return fail(MPLX_ERR_ARG, "out->count is required");
   return MPLX_OK;
 }
 
 int mplx_expand_device(mplx_ctx *c, const void *d_nodes, int n_nodes, const mplx_succ_out *out, void *stream) {
-  if (int r = bind(c)) return r;
+  if (int r = mplx_bind(c)) return r;
   if (int r = check_ready(c, n_nodes, out)) return r;
   if (n_nodes == 0) return MPLX_OK;
   if (!d_nodes) return fail(MPLX_ERR_ARG, "d_nodes is null");
@@ -332,7 +248,7 @@ int mplx_expand_device(mplx_ctx *c, const void *d_nodes, int n_nodes, const mplx
 }
 
 int mplx_expand(mplx_ctx *c, const mplx_waypoint *nodes, int n_nodes, const mplx_succ_out *out) {
-  if (int r = bind(c)) return r;
+  if (int r = mplx_bind(c)) return r;
   if (int r = check_ready(c, n_nodes, out)) return r;
   if (n_nodes == 0) return MPLX_OK;
   if (!nodes) return fail(MPLX_ERR_ARG, "nodes is null");
@@ -428,7 +344,7 @@ int mplx_set_kernel(mplx_ctx *c, int which) {
 }
 
 int mplx_sync(mplx_ctx *c) {
-  if (int r = bind(c)) return r;
+  if (int r = mplx_bind(c)) return r;
   CU(cudaStreamSynchronize(c->stream));
   return MPLX_OK;
 }
@@ -436,14 +352,14 @@ int mplx_sync(mplx_ctx *c) {
 int64_t mplx_launch_count(const mplx_ctx *c) { return c ? c->launches : 0; }
 
 int mplx_enable_stats(mplx_ctx *c, int on) {
-  if (int r = bind(c)) return r;
+  if (int r = mplx_bind(c)) return r;
   c->stats_on = on != 0;
   refresh_params(c);
   return MPLX_OK;
 }
 
 int mplx_last_stats(mplx_ctx *c, int64_t *samples, int64_t *successors) {
-  if (int r = bind(c)) return r;
+  if (int r = mplx_bind(c)) return r;
   CU(cudaStreamSynchronize(c->stream));
   if (samples) *samples = (int64_t)c->last_stats[0];
   if (successors) *successors = (int64_t)c->last_stats[1];

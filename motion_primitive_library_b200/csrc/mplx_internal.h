@@ -1,0 +1,134 @@
+// mplx_internal.h — ctx layout and small helpers shared by the libmplx translation units.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/mplx.h"
+#include "mplx_device.cuh"
+#include "mplx_kernels.h"
+
+namespace mplx {
+int fail(int code, const char *fmt, ...);
+}
+using mplx::fail;
+
+#define CU(call)                                                                              \
+  do {                                                                                        \
+    cudaError_t e_ = (call);                                                                  \
+    if (e_ != cudaSuccess) {                                                                  \
+      cudaGetLastError();                                                                     \
+      return fail(e_ == cudaErrorMemoryAllocation ? MPLX_ERR_ALLOC : MPLX_ERR_CUDA,           \
+                  "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    }                                                                                         \
+  } while (0)
+
+template <typename T>
+struct DevBuf {
+  T *p = nullptr;
+  size_t cap = 0;  // elements
+  cudaError_t reserve(size_t n) {
+    if (n <= cap) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+    cudaError_t e = cudaMalloc((void **)&p, n * sizeof(T));
+    if (e == cudaSuccess) cap = n;
+    return e;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+  }
+};
+
+template <typename T>
+struct PinBuf {
+  T *p = nullptr;
+  size_t cap = 0;
+  cudaError_t reserve(size_t n) {
+    if (n <= cap) return cudaSuccess;
+    if (p) cudaFreeHost(p);
+    p = nullptr;
+    cap = 0;
+    cudaError_t e = cudaHostAlloc((void **)&p, n * sizeof(T), cudaHostAllocDefault);
+    if (e == cudaSuccess) cap = n;
+    return e;
+  }
+  void release() {
+    if (p) cudaFreeHost(p);
+    p = nullptr;
+    cap = 0;
+  }
+};
+
+inline bool is_pinned(const void *p) {
+  if (!p) return false;
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  return a.type == cudaMemoryTypeHost;
+}
+
+// One set of per-chunk device buffers + its stream: two sets let chunk k+1 compute while
+// chunk k's results cross PCIe (mplx_expand_packed).
+struct ChunkBufs {
+  cudaStream_t st = nullptr;
+  cudaEvent_t ready = nullptr;
+  DevBuf<mplx_waypoint> nodes, succ;
+  DevBuf<int32_t> count, action;
+  DevBuf<double> cost;
+  DevBuf<uint64_t> key;
+  // packed stream
+  DevBuf<int32_t> kcount;
+  DevBuf<long long> offset, total;
+  DevBuf<double> pstate, pcost;
+  DevBuf<uint16_t> paction;
+  DevBuf<uint64_t> pkey;
+  PinBuf<long long> h_total;
+  void release() {
+    nodes.release(); succ.release(); count.release(); action.release(); cost.release(); key.release();
+    kcount.release(); offset.release(); total.release(); pstate.release(); pcost.release(); paction.release();
+    pkey.release(); h_total.release();
+    if (ready) cudaEventDestroy(ready);
+    if (st) cudaStreamDestroy(st);
+    ready = nullptr;
+    st = nullptr;
+  }
+};
+
+struct mplx_ctx {
+  int dim = 0, device = 0;
+  cudaStream_t stream = nullptr;
+  // static data in HBM
+  DevBuf<int8_t> map, pot;
+  DevBuf<uint32_t> region, occ;
+  DevBuf<double> U, ttab, tdt;
+  DevBuf<int> tcount;
+  int force_seq = 0;
+  DevBuf<unsigned long long> stats;
+  bool has_map = false, has_pot = false, has_region = false, has_params = false, stats_on = false;
+  size_t nvox = 0;
+  mplx::EnvParams P;
+  // per-call staging (host-buffer entry point)
+  DevBuf<mplx_waypoint> d_nodes, d_succ;
+  DevBuf<int32_t> d_count, d_action, d_lattice;
+  DevBuf<double> d_cost;
+  DevBuf<uint64_t> d_key;
+  PinBuf<mplx_waypoint> h_nodes, h_succ;
+  PinBuf<int32_t> h_count, h_action, h_lattice;
+  PinBuf<double> h_cost;
+  PinBuf<uint64_t> h_key;
+  ChunkBufs cb[2];
+  int64_t launches = 0;
+  unsigned long long last_stats[2] = {0, 0};
+};
+
+extern "C" {
+int mplx_bind(mplx_ctx *ctx);
+int mplx_check_ready(mplx_ctx *c, int n_nodes);
+}

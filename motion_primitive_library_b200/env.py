@@ -14,7 +14,7 @@ from dataclasses import dataclass
 import numpy as np
 
 from . import abi
-from .abi import LATTICE_MAX, WAYPOINT_DTYPE, SuccOut
+from .abi import LATTICE_MAX, WAYPOINT_DTYPE, PackedOut, SuccOut
 
 
 class MapUtil:
@@ -215,6 +215,30 @@ class env_map:
         out = SuccOut(abi.ptr(count), abi.ptr(succ), abi.ptr(cost), abi.ptr(action), abi.ptr(key), abi.ptr(lattice))
         abi.check(self._lib.mplx_expand(self._h, nodes.ctypes.data, n, C.byref(out)))
         return Expansion(nU, count, succ, cost, action, key, lattice)
+
+    def expand_packed(self, nodes: np.ndarray, drop_inf: bool = False, pinned: bool = True, buffers=None):
+        """mplx_expand_packed: dense {state, cost, action, key} records (see include/mplx.h).
+        Returns a dict with count, offset, state[total, nstate], cost, action, key, total."""
+        self._sync_params()
+        nodes = np.ascontiguousarray(nodes, dtype=WAYPOINT_DTYPE).reshape(-1)
+        n, nU = nodes.size, self.U_.shape[0]
+        nstate = self.Dim * bin(self.control & 15).count("1") + (1 if self.control & 16 else 0)
+        cap = n * nU
+        if buffers is None:
+            alloc = self._pinned_empty if pinned else (lambda shape, dt: np.empty(shape, dtype=dt))
+            buffers = dict(count=alloc(n, np.int32), offset=alloc(n, np.int64), state=alloc(cap * nstate, np.float64),
+                           cost=alloc(cap, np.float64), action=alloc(cap, np.uint16), key=alloc(cap, np.uint64))
+        b = buffers
+        out = PackedOut(abi.ptr(b["count"]), abi.ptr(b["offset"]), abi.ptr(b.get("state")), abi.ptr(b.get("cost")),
+                        abi.ptr(b.get("action")), abi.ptr(b.get("key")), cap, 0, 0)
+        abi.check(self._lib.mplx_expand_packed(self._h, nodes.ctypes.data, n, abi.PACK_DROP_INF if drop_inf else 0,
+                                               C.byref(out)))
+        tot = int(out.total)
+        return dict(count=b["count"], offset=b["offset"], total=tot, nstate=int(out.nstate),
+                    state=None if b.get("state") is None else b["state"][: tot * out.nstate].reshape(tot, out.nstate),
+                    cost=None if b.get("cost") is None else b["cost"][:tot],
+                    action=None if b.get("action") is None else b["action"][:tot],
+                    key=None if b.get("key") is None else b["key"][:tot], buffers=b)
 
     def _pinned_empty(self, shape, dt):
         dt = np.dtype(dt)

@@ -16,8 +16,8 @@ struct Ref {
   std::shared_ptr<MPL::env_map<Dim>> env;
   int control;
 
-  explicit Ref(const orc_env *e) : control(e->control) {
-    mu.reset(new MPL::MapUtil<Dim>);
+  static std::shared_ptr<MPL::MapUtil<Dim>> make_map(const orc_env *e) {
+    std::shared_ptr<MPL::MapUtil<Dim>> m(new MPL::MapUtil<Dim>);
     Vecf<Dim> ori;
     Veci<Dim> dim;
     size_t n = 1;
@@ -27,7 +27,16 @@ struct Ref {
       n *= (size_t)e->mdim[k];
     }
     MPL::Tmap data(e->map, e->map + n);
-    mu->setMap(ori, dim, data, e->res);
+    m->setMap(ori, dim, data, e->res);
+    return m;
+  }
+
+  // The env holds the MapUtil by shared_ptr (env_map.h:288): worker threads share one read-only
+  // grid, exactly as several planners sharing a map_util would in the reference.
+  explicit Ref(const orc_env *e, std::shared_ptr<MPL::MapUtil<Dim>> shared = nullptr) : control(e->control) {
+    mu = shared ? shared : make_map(e);
+    size_t n = 1;
+    for (int k = 0; k < Dim; k++) n *= (size_t)e->mdim[k];
     env.reset(new MPL::env_map<Dim>(mu));
     vec_E<VecDf> U;
     for (int i = 0; i < e->nU; i++) {
@@ -92,8 +101,9 @@ struct Ref {
 template <int Dim>
 int batch(const orc_env *e, const orc_waypoint *nodes, int n, orc_waypoint *succ, double *cost, int32_t *action,
           uint64_t *key, int32_t *count, int nthreads) {
+  auto shared = Ref<Dim>::make_map(e);
   auto work = [&](int lo, int hi) {
-    Ref<Dim> r(e);  // one env per thread: get_succ is not re-entrant (env_base.h:402-404)
+    Ref<Dim> r(e, shared);  // one env per thread: get_succ is not re-entrant (env_base.h:402-404)
     for (int i = lo; i < hi; i++) {
       size_t o = (size_t)i * e->nU;
       count[i] = r.get_succ(&nodes[i], succ + o, cost + o, action + o, key ? key + o : nullptr);
@@ -114,7 +124,8 @@ template <int Dim>
 int timed(const orc_env *e, const orc_waypoint *nodes, int n, int nthreads, int64_t *total_succ, double *seconds) {
   if (nthreads < 1) nthreads = 1;
   std::vector<std::unique_ptr<Ref<Dim>>> envs;
-  for (int t = 0; t < nthreads; t++) envs.emplace_back(new Ref<Dim>(e));  // set-up (map copy) outside the clock
+  auto shared = Ref<Dim>::make_map(e);
+  for (int t = 0; t < nthreads; t++) envs.emplace_back(new Ref<Dim>(e, shared));  // set-up outside the clock
   std::vector<int64_t> ns(nthreads, 0);
   auto work = [&](int t, int lo, int hi) {
     std::vector<orc_waypoint> succ(e->nU);

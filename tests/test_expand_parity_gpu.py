@@ -252,3 +252,59 @@ def test_many_controls_uses_sequential_kernel():
     orc = ob.OracleEnv.from_scenario(sc).expand(nodes, nthreads=8)
     g = gpu_env(sc).expand(nodes, want=WANT)
     assert_expansion_equal(g, orc, exact_cost=True)
+
+
+def _check_packed(env, sc, orc, nodes, drop_inf):
+    p = env.expand_packed(nodes, drop_inf=drop_inf)
+    nU, D = orc["nU"], sc.Dim
+    fields = ["pos", "vel", "acc", "jrk"][: bin(sc.control & 15).count("1")]
+    keep_all = (np.arange(nU)[None, :] < orc["count"][:, None])
+    if drop_inf:
+        keep_all &= ~np.isinf(orc["cost"].reshape(-1, nU))
+    np.testing.assert_array_equal(p["count"], keep_all.sum(1))
+    assert p["total"] == int(keep_all.sum())
+    # every node's records are contiguous at offset[i]; the segments tile [0,total) exactly
+    order = np.argsort(p["offset"], kind="stable")
+    nz = order[p["count"][order] > 0]
+    assert (p["offset"][nz] == np.concatenate([[0], np.cumsum(p["count"][nz])[:-1]])).all()
+    sel = np.nonzero(keep_all.reshape(-1))[0]
+    # gather the packed records in (node, control) order
+    idx = np.concatenate([p["offset"][i] + np.arange(p["count"][i]) for i in range(len(nodes))]) if len(nodes) else []
+    exp_state = np.concatenate([orc["succ"][f][sel][:, :D] for f in fields] +
+                               ([orc["succ"]["yaw"][sel][:, None]] if sc.control & 16 else []), axis=1)
+    assert p["nstate"] == exp_state.shape[1]
+    assert p["state"][idx].tobytes() == np.ascontiguousarray(exp_state).tobytes()
+    np.testing.assert_array_equal(p["action"][idx], orc["action"][sel].astype(np.uint16))
+    np.testing.assert_array_equal(p["key"][idx], orc["key"][sel])
+    g, o = p["cost"][idx], orc["cost"][sel]
+    np.testing.assert_array_equal(np.isinf(g), np.isinf(o))
+    np.testing.assert_allclose(g[~np.isinf(o)], o[~np.isinf(o)], rtol=1e-6, atol=0)
+
+
+def test_packed_stream_matches_oracle():
+    """mplx_expand_packed: dense state/cost/action/key records, with and without +inf successors,
+    across several pipeline chunks (60k nodes > 19k-node chunks)."""
+    from motion_primitive_library_b200 import scenarios as S
+
+    for sc, n in ((S.scaled(S.cfg_headline(), 96), 60000), (S.scaled(S.cfg3(), 64), 9000), (S.scaled(S.cfg4(), 64), 3000)):
+        nodes = sc.frontier(n, seed=21)
+        orc = ob.OracleEnv.from_scenario(sc).expand(nodes, nthreads=8, lattice=False)
+        env = gpu_env(sc)
+        for drop in (False, True):
+            _check_packed(env, sc, orc, nodes, drop)
+    # 2-D, pageable buffers, tiny and empty batches
+    c = fixtures.corridor()
+    from motion_primitive_library_b200.scenarios import Scenario
+
+    sc = Scenario("corridor", tuple(int(x) for x in c["dim"]), c["res"], tuple(c["origin"]), ACC, fixtures.U_2d(),
+                  v_max=1.0, a_max=1.0)
+    sc._grid = c["grid"]
+    env = gpu_env(sc)
+    for n in (0, 1, 5, 700):
+        nodes = sc.frontier(n, seed=3) if n else np.zeros(0, dtype=ob.WAYPOINT_DTYPE)
+        orc = ob.OracleEnv.from_scenario(sc).expand(nodes, lattice=False)
+        p = env.expand_packed(nodes, drop_inf=True, pinned=False)
+        if n:
+            _check_packed(env, sc, orc, nodes, True)
+        else:
+            assert p["total"] == 0
