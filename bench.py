@@ -44,6 +44,7 @@ def parse():
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--kernel", type=int, default=0, help="0 = auto (register kernel), 1 = literal loop, 2 = register, 3 = flat")
     return ap.parse_args()
 
 
@@ -249,6 +250,7 @@ def main():
 
     # ---- inputs: every rank holds the full map (replica) and its own slice of the frontier ----
     env = make_env(sc, local)
+    env.set_kernel(args.kernel)
     n, nU = args.nodes, sc.nU
     nodes_np = sc.frontier(n, seed=7 + rank)
     slots = n * nU
@@ -390,7 +392,7 @@ def main():
     achieved = bytes_per_exp * n / (k_ms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s", "frac": achieved / peak_gbs,
                 "traffic": None, "peak_source": "measured" if pk.exists() else "fallback",
-                "kernel": "mplx::expand_flat_kernel", "kernel_ms": k_ms,
+                "kernel": "mplx::expand_reg_kernel" if args.kernel in (0, 2) else f"kernel {args.kernel}", "kernel_ms": k_ms,
                 "algorithmic_bytes_per_expansion": bytes_per_exp,
                 "mean_samples_per_expansion": mean_samples, "mean_successors_per_expansion": mean_succ}
     prof = ROOT / "profiles" / "traffic.json"

@@ -154,9 +154,10 @@ typedef struct {
 int mplx_expand_packed(mplx_ctx *ctx, const mplx_waypoint *nodes, int n_nodes, int flags,
                        mplx_packed_out *out);
 
-/* Kernel selection (diagnostics): 0 = auto (the flat sample-parallel kernel whenever
- * |U| <= 256), 1 = the sequential kernel that keeps traverse_primitive's literal per-primitive
- * loop (env_map.h:99-130).  Both produce identical results. */
+/* Kernel selection (diagnostics): 0 = auto (the register kernel whenever |U| <= 256),
+ * 1 = the sequential kernel that keeps traverse_primitive's literal per-primitive loop
+ * (env_map.h:99-130), 2 = the register kernel, 3 = the flat (sample-parallel, shared-memory
+ * staged) kernel.  All produce identical results. */
 int mplx_set_kernel(mplx_ctx *ctx, int which);
 
 /* Synchronise the ctx stream. */

@@ -41,22 +41,42 @@ struct PrimState {
 };
 
 // ---- voxel classification shared by both sample loops ------------------------------------
-// Returns true when the sample blocks the primitive (env_map.h:104-121); otherwise adds the
-// potential term to `term`.  idx is a valid in-map index.
-__device__ __forceinline__ bool voxel_blocks(const EnvParams &P, int idx, double dt, double vnorm_w,
-                                             double &term) {
-  if (P.region_bits != nullptr) {
-    if (!((__ldg(P.region_bits + (idx >> 5)) >> (idx & 31)) & 1u)) return true;
-  }
+// Two steps so that a caller can issue the loads of several samples before consuming any:
+// voxel_fetch reads the raw words/bytes of a valid in-map index, voxel_classify applies
+// env_map.h:104-121 to them (returns true when the sample blocks the primitive, otherwise adds
+// the potential term to `term`).
+struct VoxelRaw {
+  uint32_t region_word, occ_word;
+  int pot;
+};
+__device__ __forceinline__ VoxelRaw voxel_fetch(const EnvParams &P, int idx) {
+  VoxelRaw r;
+  r.region_word = 0xffffffffu;
+  r.occ_word = 0;
+  r.pot = 0;
+  if (P.region_bits != nullptr) r.region_word = __ldg(P.region_bits + (idx >> 5));
+  if (P.pot != nullptr)
+    r.pot = (int)__ldg(P.pot + idx);
+  else
+    r.occ_word = __ldg(P.occ_bits + (idx >> 5));
+  return r;
+}
+__device__ __forceinline__ bool voxel_classify(const EnvParams &P, const VoxelRaw &r, int idx, double dt,
+                                               double vnorm_w, double &term) {
+  if (!((r.region_word >> (idx & 31)) & 1u)) return true;  // outside the tunnel (env_map.h:104-106)
   if (P.pot != nullptr) {
-    const int pv = (int)__ldg(P.pot + idx);
-    if (pv < 100 && pv > 0)
-      term += dt * (P.pot_w * pv + vnorm_w);
-    else if (pv >= 100)
+    if (r.pot < 100 && r.pot > 0)
+      term += dt * (P.pot_w * r.pot + vnorm_w);
+    else if (r.pot >= 100)
       return true;
     return false;
   }
-  return (__ldg(P.occ_bits + (idx >> 5)) >> (idx & 31)) & 1u;
+  return (r.occ_word >> (idx & 31)) & 1u;
+}
+__device__ __forceinline__ bool voxel_blocks(const EnvParams &P, int idx, double dt, double vnorm_w,
+                                             double &term) {
+  const VoxelRaw r = voxel_fetch(P, idx);
+  return voxel_classify(P, r, idx, dt, vnorm_w, term);
 }
 
 // floatToInt + isOutside + getIndex (map_util.h:103-108, 51-55, 34-41) for one sample.
@@ -432,6 +452,108 @@ expand_seq_kernel(const __grid_constant__ EnvParams P, const mplx_waypoint *__re
   if (threadIdx.x < 2 && P.stats) atomicAdd(&P.stats[threadIdx.x], s_stats[threadIdx.x]);
 }
 
+// ---- register kernel (|U| <= 256): thread = primitive through all three phases ----------------
+// Phase C keeps the primitive's quotients in registers and walks the reference's own loop
+// `for (t = 0; t < T; t += dt)` (env_map.h:99) four samples at a time: the four cell indices are
+// computed and their voxel loads issued back to back, then the samples are classified IN ORDER,
+// so the first blocking sample ends the primitive exactly where the reference returns inf, the
+// potential / yaw sums accumulate in the reference's order, and up to three samples past a block
+// are computed for nothing (they are bounds-checked like any other).  No shared-memory staging,
+// no atomics; lanes whose primitive is invalid or short idle while the longest one finishes.
+template <int DIM, int ORD, bool YAW, int UNR>
+__device__ __forceinline__ double traverse_regs(const EnvParams &P, const double (&cf)[CoefLayout<DIM, ORD, YAW>::NCMAX],
+                                                bool need_vel, double dt, unsigned &n_samples) {
+  using CL = CoefLayout<DIM, ORD, YAW>;
+  const double T = P.T;
+  const int NC = CL::ncoef(need_vel);
+  double c = 0;
+  double t = 0;
+  while (t < T) {
+    double ts[UNR];
+    int idx[UNR];
+    VoxelRaw raw[UNR];
+#pragma unroll
+    for (int j = 0; j < UNR; j++) {
+      ts[j] = t;
+      idx[j] = -2;
+      if (t < T) {
+        double pk[DIM];
+        eval_pos<DIM, ORD>(cf, t, pk);
+        idx[j] = sample_index<DIM>(P, pk);
+      }
+      t += dt;  // the reference's running sum; harmless past T
+    }
+#pragma unroll
+    for (int j = 0; j < UNR; j++) {
+      raw[j].region_word = 0xffffffffu;
+      raw[j].occ_word = 0;
+      raw[j].pot = 0;
+      if (idx[j] >= 0) raw[j] = voxel_fetch(P, idx[j]);
+    }
+#pragma unroll
+    for (int j = 0; j < UNR; j++) {
+      if (idx[j] == -2) return c;  // t_j >= T: the loop has ended
+      n_samples++;
+      if (idx[j] < 0) return INFINITY;
+      double vel[DIM];
+      double gterm = 0.0;
+      if (need_vel) {
+        eval_vel<DIM, ORD>(cf + CL::NCP, ts[j], vel);
+        gterm = grad_term<DIM>(P, vel);
+      }
+      double term = 0.0;
+      if (voxel_classify(P, raw[j], idx[j], dt, gterm, term)) return INFINITY;
+      c += term;
+      if (YAW) {
+        if (P.wyaw > 0) c += yaw_term(P, vel[0], vel[1], normalize_angle(cf[NC - 2] * ts[j] + cf[NC - 1]), dt);
+      }
+    }
+  }
+  return c;
+}
+
+template <int DIM, int ORD, bool YAW, int UNR, int MINB>
+__global__ void __launch_bounds__(kThreads, MINB)
+expand_reg_kernel(const __grid_constant__ EnvParams P, const mplx_waypoint *__restrict__ nodes, int n_nodes,
+                  int npb, const __grid_constant__ OutPtrs o) {
+  __shared__ uint32_t vbits[9];
+  __shared__ unsigned long long s_stats[2];
+  const bool need_vel = YAW || (P.pot != nullptr && P.grad_w != 0.0);
+  const int nU = P.nU;
+  const int items = npb * nU;  // <= 256
+  const int node0 = blockIdx.x * npb;
+  const int words = (items + 31) >> 5;
+  if (threadIdx.x < 2) s_stats[threadIdx.x] = 0;
+  PrimState<DIM, ORD, YAW> pr;
+  bool emit, same;
+  double max_v;
+  size_t slot;
+  phase_ab<DIM, ORD, YAW>(P, nodes, n_nodes, threadIdx.x, items, nU, node0, vbits, words, o, pr, emit, same,
+                          max_v, slot);
+  unsigned n_samples = 0;
+  if (emit) {
+    double cost = 0.0;
+    if (!same) {
+      double cf[CoefLayout<DIM, ORD, YAW>::NCMAX];
+      fill_coef<DIM, ORD, YAW>(pr, need_vel, cf);
+      // n = max(5, (int)ceil(max_v*T/res)), dt = T/n  (env_map.h:95,98): exact quotient + ceiling;
+      // T/n from the table for n <= kNMax, a true division beyond it
+      const double nd = ceil_exact(div_exact(max_v * P.T, P.res, P.rinv));
+      const int n = nd < 5.0 ? 5 : (nd < 2.0e9 ? (int)nd : 2000000000);
+      const double dt = n <= kNMax ? __ldg(P.tdt + n) : P.T / n;
+      cost = traverse_regs<DIM, ORD, YAW, UNR>(P, cf, need_vel, dt, n_samples);
+    }
+    if (!isinf(cost)) cost += intrinsic_cost<DIM, ORD, YAW>(P, pr);
+    if (o.cost) o.cost[slot] = cost;
+  }
+  if (P.stats) {
+    atomicAdd(&s_stats[0], (unsigned long long)n_samples);
+    if (emit) atomicAdd(&s_stats[1], 1ull);
+    __syncthreads();
+    if (threadIdx.x < 2) atomicAdd(&P.stats[threadIdx.x], s_stats[threadIdx.x]);
+  }
+}
+
 // ---- flat kernel (|U| <= 256) -----------------------------------------------------------------
 // Per-warp shared-memory slab (doubles first so everything stays 8-byte aligned):
 //   coef [32][NC]  loop-invariant polynomial quotients of each lane's primitive
@@ -512,49 +634,62 @@ expand_flat_kernel(const __grid_constant__ EnvParams P, const mplx_waypoint *__r
   __syncwarp();
 
   // ---- phase C: the warp's samples, dealt round-robin to its lanes, two per lane per trip ----
-  // One sample: returns whether it blocks its primitive (env_map.h:104-121) and its cost term.
-  auto do_sample = [&](int s, bool valid, int &i, int &k, bool &blocked, double &term) {
-    blocked = false;
-    term = 0.0;
+  // prep: owner/time/coefficients -> cell index (or -1 outside, -2 nothing to do);
+  // then the voxel loads of both samples are issued before either is consumed.
+  struct Prep {
+    int i, k, idx;
+    double t;
+  };
+  auto prep = [&](int s, bool valid) {
+    Prep r;
     const unsigned ow = valid ? (unsigned)w_owner[s] : 0u;
-    i = (int)(ow >> 8);
-    k = (int)(ow & 255u);
+    r.i = (int)(ow >> 8);
+    r.k = (int)(ow & 255u);
+    r.idx = -2;
+    r.t = 0.0;
     // an earlier sample of this primitive already blocks: the result is inf whatever this one says
-    if (!valid || *(volatile int *)(w_first + i) < k) return;
-    const double t = __ldg(P.ttab + w_n[i] * kTStride + k);
-    const double *cf = w_coef + i * NC;
+    if (!valid || *(volatile int *)(w_first + r.i) < r.k) return r;
+    r.t = __ldg(P.ttab + w_n[r.i] * kTStride + r.k);
     double pk[DIM];
-    eval_pos<DIM, ORD>(cf, t, pk);
-    const int idx = sample_index<DIM>(P, pk);
-    if (idx < 0) {
-      blocked = true;
+    eval_pos<DIM, ORD>(w_coef + r.i * NC, r.t, pk);
+    r.idx = sample_index<DIM>(P, pk);
+    return r;
+  };
+  auto finish = [&](const Prep &r, const VoxelRaw &raw) {
+    if (r.idx == -2) return;
+    if (r.idx < 0) {
+      atomicMin(w_first + r.i, r.k);
       return;
     }
+    const double *cf = w_coef + r.i * NC;
     double vel[DIM];
     double gterm = 0.0;
     if (need_vel) {
-      eval_vel<DIM, ORD>(cf + L::NCP, t, vel);
+      eval_vel<DIM, ORD>(cf + L::NCP, r.t, vel);
       gterm = grad_term<DIM>(P, vel);
     }
-    const double dt = w_dt[i];
-    if (voxel_blocks(P, idx, dt, gterm, term)) {
-      blocked = true;
+    const double dt = w_dt[r.i];
+    double term = 0.0;
+    if (voxel_classify(P, raw, r.idx, dt, gterm, term)) {
+      atomicMin(w_first + r.i, r.k);
       return;
     }
     if (YAW) {
-      if (P.wyaw > 0) term += yaw_term(P, vel[0], vel[1], normalize_angle(cf[NC - 2] * t + cf[NC - 1]), dt);
+      if (P.wyaw > 0) term += yaw_term(P, vel[0], vel[1], normalize_angle(cf[NC - 2] * r.t + cf[NC - 1]), dt);
     }
+    if (term != 0.0) atomicAdd(w_cost + r.i, term);
   };
   for (int s = lane; s < S; s += 64) {
-    int iA, kA, iB, kB;
-    bool bA, bB;
-    double tA, tB;
-    do_sample(s, true, iA, kA, bA, tA);
-    do_sample(s + 32, s + 32 < S, iB, kB, bB, tB);
-    if (bA) atomicMin(w_first + iA, kA);
-    if (bB) atomicMin(w_first + iB, kB);
-    if (tA != 0.0) atomicAdd(w_cost + iA, tA);
-    if (tB != 0.0) atomicAdd(w_cost + iB, tB);
+    const Prep a = prep(s, true);
+    const Prep b = prep(s + 32, s + 32 < S);
+    VoxelRaw ra, rb;
+    ra.region_word = rb.region_word = 0xffffffffu;
+    ra.occ_word = rb.occ_word = 0;
+    ra.pot = rb.pot = 0;
+    if (a.idx >= 0) ra = voxel_fetch(P, a.idx);
+    if (b.idx >= 0) rb = voxel_fetch(P, b.idx);
+    finish(a, ra);
+    finish(b, rb);
   }
   __syncwarp();
 
@@ -582,10 +717,171 @@ static cudaError_t launch_t(const EnvParams &P, const mplx_waypoint *d_nodes, in
   const OutPtrs o{so.count, so.succ, so.cost, so.action, so.key, so.lattice};
   const int npb = P.nU >= kThreads ? 1 : kThreads / P.nU;
   const int grid = (n_nodes + npb - 1) / npb;
-  if (P.nU > kThreads || force_seq) {
+  if (P.nU > kThreads || force_seq == 1) {
     expand_seq_kernel<DIM, ORD, YAW><<<grid, kThreads, 0, st>>>(P, d_nodes, n_nodes, npb, o);
     return cudaGetLastError();
   }
+  if (force_seq != 3) {
+    expand_reg_kernel<DIM, ORD, YAW, 4, 4><<<grid, kThreads, 0, st>>>(P, d_nodes, n_nodes, npb, o);
+    return cudaGetLastError();
+  }
+  using L = FlatLayout<DIM, ORD, YAW>;
+  const bool need_vel = need_vel_i != 0;
+  const int NC = L::ncoef(need_vel);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  unsigned char *wb = smem + (size_t)warp * L::warp_bytes(need_vel, maxns);
+  double *w_coef = reinterpret_cast<double *>(wb);
+  double *w_cost = w_coef + 32 * NC;
+  double *w_dt = w_cost + 32;
+  int *w_n = reinterpret_cast<int *>(w_dt + 32);
+  int *w_first = w_n + 32;
+  unsigned short *w_owner = reinterpret_cast<unsigned short *>(w_first + 32);
+
+  const int nU = P.nU;
+  const int items = npb * nU;  // <= 256
+  const int node0 = blockIdx.x * npb;
+  const int words = (items + 31) >> 5;
+  if (threadIdx.x < 2) s_stats[threadIdx.x] = 0;
+
+  PrimState<DIM, ORD, YAW> pr;
+  bool emit, same;
+  double max_v;
+  size_t slot;
+  phase_ab<DIM, ORD, YAW>(P, nodes, n_nodes, threadIdx.x, items, nU, node0, vbits, words, o, pr, emit, same,
+                          max_v, slot);
+
+  // ---- phase C set-up: coefficient slot, n, sample count ----
+  const double T = P.T;
+  fill_coef<DIM, ORD, YAW>(pr, need_vel, w_coef + lane * NC);
+  int n = 0, ns = 0;
+  bool seq = false;
+  double cost_seq = 0.0;
+  unsigned seq_samples = 0;
+  if (emit && !same) {
+    // n = max(5, (int)ceil(max_v*T/res))  (env_map.h:95), exact quotient and ceiling
+    const double nd = ceil_exact(div_exact(max_v * T, P.res, P.rinv));
+    if (nd <= (double)P.maxn) {
+      n = max(5, (int)nd);
+      ns = __ldg(P.tcount + n);
+    } else {
+      seq = true;  // beyond the table: literal loop in this lane, coefficients from its smem slot
+      cost_seq = traverse_loop_cold<DIM, ORD, YAW>(&P, w_coef + lane * NC, need_vel, max_v, &seq_samples);
+    }
+  }
+  int incl = ns;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const int v = __shfl_up_sync(0xffffffffu, incl, d);
+    if (lane >= d) incl += v;
+  }
+  const int start = incl - ns;
+  const int S = __shfl_sync(0xffffffffu, incl, 31);
+  w_cost[lane] = 0.0;
+  w_dt[lane] = __ldg(P.tdt + n);  // T/n, env_map.h:98
+  w_n[lane] = n;
+  w_first[lane] = kNoBlock;
+  for (int k = 0; k < ns; k++) w_owner[start + k] = (unsigned short)((lane << 8) | k);
+  __syncwarp();
+
+  // ---- phase C: the warp's samples, dealt round-robin to its lanes, two per lane per trip ----
+  // prep: owner/time/coefficients -> cell index (or -1 outside, -2 nothing to do);
+  // then the voxel loads of both samples are issued before either is consumed.
+  struct Prep {
+    int i, k, idx;
+    double t;
+  };
+  auto prep = [&](int s, bool valid) {
+    Prep r;
+    const unsigned ow = valid ? (unsigned)w_owner[s] : 0u;
+    r.i = (int)(ow >> 8);
+    r.k = (int)(ow & 255u);
+    r.idx = -2;
+    r.t = 0.0;
+    // an earlier sample of this primitive already blocks: the result is inf whatever this one says
+    if (!valid || *(volatile int *)(w_first + r.i) < r.k) return r;
+    r.t = __ldg(P.ttab + w_n[r.i] * kTStride + r.k);
+    double pk[DIM];
+    eval_pos<DIM, ORD>(w_coef + r.i * NC, r.t, pk);
+    r.idx = sample_index<DIM>(P, pk);
+    return r;
+  };
+  auto finish = [&](const Prep &r, const VoxelRaw &raw) {
+    if (r.idx == -2) return;
+    if (r.idx < 0) {
+      atomicMin(w_first + r.i, r.k);
+      return;
+    }
+    const double *cf = w_coef + r.i * NC;
+    double vel[DIM];
+    double gterm = 0.0;
+    if (need_vel) {
+      eval_vel<DIM, ORD>(cf + L::NCP, r.t, vel);
+      gterm = grad_term<DIM>(P, vel);
+    }
+    const double dt = w_dt[r.i];
+    double term = 0.0;
+    if (voxel_classify(P, raw, r.idx, dt, gterm, term)) {
+      atomicMin(w_first + r.i, r.k);
+      return;
+    }
+    if (YAW) {
+      if (P.wyaw > 0) term += yaw_term(P, vel[0], vel[1], normalize_angle(cf[NC - 2] * r.t + cf[NC - 1]), dt);
+    }
+    if (term != 0.0) atomicAdd(w_cost + r.i, term);
+  };
+  for (int s = lane; s < S; s += 64) {
+    const Prep a = prep(s, true);
+    const Prep b = prep(s + 32, s + 32 < S);
+    VoxelRaw ra, rb;
+    ra.region_word = rb.region_word = 0xffffffffu;
+    ra.occ_word = rb.occ_word = 0;
+    ra.pot = rb.pot = 0;
+    if (a.idx >= 0) ra = voxel_fetch(P, a.idx);
+    if (b.idx >= 0) rb = voxel_fetch(P, b.idx);
+    finish(a, ra);
+    finish(b, rb);
+  }
+  __syncwarp();
+
+  if (emit) {
+    const int fb = w_first[lane];
+    double cost = same ? 0.0 : seq ? cost_seq : (fb != kNoBlock ? (double)INFINITY : w_cost[lane]);
+    if (!isinf(cost)) cost += intrinsic_cost<DIM, ORD, YAW>(P, pr);
+    if (o.cost) o.cost[slot] = cost;
+    if (P.stats) {
+      // samples the reference loop visits: up to and including the first blocking one
+      const unsigned visited = seq ? seq_samples : (fb != kNoBlock ? (unsigned)fb + 1u : (unsigned)ns);
+      atomicAdd(&s_stats[0], (unsigned long long)visited);
+      atomicAdd(&s_stats[1], 1ull);
+    }
+  }
+  if (P.stats) {
+    __syncthreads();
+    if (threadIdx.x < 2) atomicAdd(&P.stats[threadIdx.x], s_stats[threadIdx.x]);
+  }
+}
+
+template <int DIM, int ORD, bool YAW>
+static cudaError_t launch_t(const EnvParams &P, const mplx_waypoint *d_nodes, int n_nodes,
+                            const mplx_succ_out &so, cudaStream_t st, int force_seq) {
+  const OutPtrs o{so.count, so.succ, so.cost, so.action, so.key, so.lattice};
+  const int npb = P.nU >= kThreads ? 1 : kThreads / P.nU;
+  const int grid = (n_nodes + npb - 1) / npb;
+  if (P.nU > kThreads || force_seq == 1) {
+    expand_seq_kernel<DIM, ORD, YAW><<<grid, kThreads, 0, st>>>(P, d_nodes, n_nodes, npb, o);
+    return cudaGetLastError();
+  }
+  if (force_seq != 3 && !(force_seq >= 4)) {
+    expand_reg_kernel<DIM, ORD, YAW, 4, 4><<<grid, kThreads, 0, st>>>(P, d_nodes, n_nodes, npb, o);
+    return cudaGetLastError();
+  }
+#ifdef MPLX_TUNING_VARIANTS
+  if (force_seq == 4) { expand_reg_kernel<DIM, ORD, YAW, 2, 4><<<grid, kThreads, 0, st>>>(P, d_nodes, n_nodes, npb, o); return cudaGetLastError(); }
+  if (force_seq == 5) { expand_reg_kernel<DIM, ORD, YAW, 8, 4><<<grid, kThreads, 0, st>>>(P, d_nodes, n_nodes, npb, o); return cudaGetLastError(); }
+  if (force_seq == 6) { expand_reg_kernel<DIM, ORD, YAW, 4, 5><<<grid, kThreads, 0, st>>>(P, d_nodes, n_nodes, npb, o); return cudaGetLastError(); }
+  if (force_seq == 7) { expand_reg_kernel<DIM, ORD, YAW, 2, 5><<<grid, kThreads, 0, st>>>(P, d_nodes, n_nodes, npb, o); return cudaGetLastError(); }
+  if (force_seq == 8) { expand_reg_kernel<DIM, ORD, YAW, 3, 4><<<grid, kThreads, 0, st>>>(P, d_nodes, n_nodes, npb, o); return cudaGetLastError(); }
+#endif
   using L = FlatLayout<DIM, ORD, YAW>;
   const bool need_vel = YAW || (P.pot != nullptr && P.grad_w != 0.0);
   const int maxns = P.maxn + 1;

@@ -260,7 +260,7 @@ class env_map:
         return e.node(0)
 
     def set_kernel(self, which: int):
-        """0 = auto (flat sample-parallel kernel), 1 = sequential per-primitive loop."""
+        """0 = auto (register kernel), 1 = literal sequential loop, 2 = register kernel, 3 = flat kernel."""
         abi.check(self._lib.mplx_set_kernel(self._h, int(which)))
 
     def enable_stats(self, on=True):
