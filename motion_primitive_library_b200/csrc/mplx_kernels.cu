@@ -726,163 +726,6 @@ static cudaError_t launch_t(const EnvParams &P, const mplx_waypoint *d_nodes, in
     return cudaGetLastError();
   }
   using L = FlatLayout<DIM, ORD, YAW>;
-  const bool need_vel = need_vel_i != 0;
-  const int NC = L::ncoef(need_vel);
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  unsigned char *wb = smem + (size_t)warp * L::warp_bytes(need_vel, maxns);
-  double *w_coef = reinterpret_cast<double *>(wb);
-  double *w_cost = w_coef + 32 * NC;
-  double *w_dt = w_cost + 32;
-  int *w_n = reinterpret_cast<int *>(w_dt + 32);
-  int *w_first = w_n + 32;
-  unsigned short *w_owner = reinterpret_cast<unsigned short *>(w_first + 32);
-
-  const int nU = P.nU;
-  const int items = npb * nU;  // <= 256
-  const int node0 = blockIdx.x * npb;
-  const int words = (items + 31) >> 5;
-  if (threadIdx.x < 2) s_stats[threadIdx.x] = 0;
-
-  PrimState<DIM, ORD, YAW> pr;
-  bool emit, same;
-  double max_v;
-  size_t slot;
-  phase_ab<DIM, ORD, YAW>(P, nodes, n_nodes, threadIdx.x, items, nU, node0, vbits, words, o, pr, emit, same,
-                          max_v, slot);
-
-  // ---- phase C set-up: coefficient slot, n, sample count ----
-  const double T = P.T;
-  fill_coef<DIM, ORD, YAW>(pr, need_vel, w_coef + lane * NC);
-  int n = 0, ns = 0;
-  bool seq = false;
-  double cost_seq = 0.0;
-  unsigned seq_samples = 0;
-  if (emit && !same) {
-    // n = max(5, (int)ceil(max_v*T/res))  (env_map.h:95), exact quotient and ceiling
-    const double nd = ceil_exact(div_exact(max_v * T, P.res, P.rinv));
-    if (nd <= (double)P.maxn) {
-      n = max(5, (int)nd);
-      ns = __ldg(P.tcount + n);
-    } else {
-      seq = true;  // beyond the table: literal loop in this lane, coefficients from its smem slot
-      cost_seq = traverse_loop_cold<DIM, ORD, YAW>(&P, w_coef + lane * NC, need_vel, max_v, &seq_samples);
-    }
-  }
-  int incl = ns;
-#pragma unroll
-  for (int d = 1; d < 32; d <<= 1) {
-    const int v = __shfl_up_sync(0xffffffffu, incl, d);
-    if (lane >= d) incl += v;
-  }
-  const int start = incl - ns;
-  const int S = __shfl_sync(0xffffffffu, incl, 31);
-  w_cost[lane] = 0.0;
-  w_dt[lane] = __ldg(P.tdt + n);  // T/n, env_map.h:98
-  w_n[lane] = n;
-  w_first[lane] = kNoBlock;
-  for (int k = 0; k < ns; k++) w_owner[start + k] = (unsigned short)((lane << 8) | k);
-  __syncwarp();
-
-  // ---- phase C: the warp's samples, dealt round-robin to its lanes, two per lane per trip ----
-  // prep: owner/time/coefficients -> cell index (or -1 outside, -2 nothing to do);
-  // then the voxel loads of both samples are issued before either is consumed.
-  struct Prep {
-    int i, k, idx;
-    double t;
-  };
-  auto prep = [&](int s, bool valid) {
-    Prep r;
-    const unsigned ow = valid ? (unsigned)w_owner[s] : 0u;
-    r.i = (int)(ow >> 8);
-    r.k = (int)(ow & 255u);
-    r.idx = -2;
-    r.t = 0.0;
-    // an earlier sample of this primitive already blocks: the result is inf whatever this one says
-    if (!valid || *(volatile int *)(w_first + r.i) < r.k) return r;
-    r.t = __ldg(P.ttab + w_n[r.i] * kTStride + r.k);
-    double pk[DIM];
-    eval_pos<DIM, ORD>(w_coef + r.i * NC, r.t, pk);
-    r.idx = sample_index<DIM>(P, pk);
-    return r;
-  };
-  auto finish = [&](const Prep &r, const VoxelRaw &raw) {
-    if (r.idx == -2) return;
-    if (r.idx < 0) {
-      atomicMin(w_first + r.i, r.k);
-      return;
-    }
-    const double *cf = w_coef + r.i * NC;
-    double vel[DIM];
-    double gterm = 0.0;
-    if (need_vel) {
-      eval_vel<DIM, ORD>(cf + L::NCP, r.t, vel);
-      gterm = grad_term<DIM>(P, vel);
-    }
-    const double dt = w_dt[r.i];
-    double term = 0.0;
-    if (voxel_classify(P, raw, r.idx, dt, gterm, term)) {
-      atomicMin(w_first + r.i, r.k);
-      return;
-    }
-    if (YAW) {
-      if (P.wyaw > 0) term += yaw_term(P, vel[0], vel[1], normalize_angle(cf[NC - 2] * r.t + cf[NC - 1]), dt);
-    }
-    if (term != 0.0) atomicAdd(w_cost + r.i, term);
-  };
-  for (int s = lane; s < S; s += 64) {
-    const Prep a = prep(s, true);
-    const Prep b = prep(s + 32, s + 32 < S);
-    VoxelRaw ra, rb;
-    ra.region_word = rb.region_word = 0xffffffffu;
-    ra.occ_word = rb.occ_word = 0;
-    ra.pot = rb.pot = 0;
-    if (a.idx >= 0) ra = voxel_fetch(P, a.idx);
-    if (b.idx >= 0) rb = voxel_fetch(P, b.idx);
-    finish(a, ra);
-    finish(b, rb);
-  }
-  __syncwarp();
-
-  if (emit) {
-    const int fb = w_first[lane];
-    double cost = same ? 0.0 : seq ? cost_seq : (fb != kNoBlock ? (double)INFINITY : w_cost[lane]);
-    if (!isinf(cost)) cost += intrinsic_cost<DIM, ORD, YAW>(P, pr);
-    if (o.cost) o.cost[slot] = cost;
-    if (P.stats) {
-      // samples the reference loop visits: up to and including the first blocking one
-      const unsigned visited = seq ? seq_samples : (fb != kNoBlock ? (unsigned)fb + 1u : (unsigned)ns);
-      atomicAdd(&s_stats[0], (unsigned long long)visited);
-      atomicAdd(&s_stats[1], 1ull);
-    }
-  }
-  if (P.stats) {
-    __syncthreads();
-    if (threadIdx.x < 2) atomicAdd(&P.stats[threadIdx.x], s_stats[threadIdx.x]);
-  }
-}
-
-template <int DIM, int ORD, bool YAW>
-static cudaError_t launch_t(const EnvParams &P, const mplx_waypoint *d_nodes, int n_nodes,
-                            const mplx_succ_out &so, cudaStream_t st, int force_seq) {
-  const OutPtrs o{so.count, so.succ, so.cost, so.action, so.key, so.lattice};
-  const int npb = P.nU >= kThreads ? 1 : kThreads / P.nU;
-  const int grid = (n_nodes + npb - 1) / npb;
-  if (P.nU > kThreads || force_seq == 1) {
-    expand_seq_kernel<DIM, ORD, YAW><<<grid, kThreads, 0, st>>>(P, d_nodes, n_nodes, npb, o);
-    return cudaGetLastError();
-  }
-  if (force_seq != 3 && !(force_seq >= 4)) {
-    expand_reg_kernel<DIM, ORD, YAW, 4, 4><<<grid, kThreads, 0, st>>>(P, d_nodes, n_nodes, npb, o);
-    return cudaGetLastError();
-  }
-#ifdef MPLX_TUNING_VARIANTS
-  if (force_seq == 4) { expand_reg_kernel<DIM, ORD, YAW, 2, 4><<<grid, kThreads, 0, st>>>(P, d_nodes, n_nodes, npb, o); return cudaGetLastError(); }
-  if (force_seq == 5) { expand_reg_kernel<DIM, ORD, YAW, 8, 4><<<grid, kThreads, 0, st>>>(P, d_nodes, n_nodes, npb, o); return cudaGetLastError(); }
-  if (force_seq == 6) { expand_reg_kernel<DIM, ORD, YAW, 4, 5><<<grid, kThreads, 0, st>>>(P, d_nodes, n_nodes, npb, o); return cudaGetLastError(); }
-  if (force_seq == 7) { expand_reg_kernel<DIM, ORD, YAW, 2, 5><<<grid, kThreads, 0, st>>>(P, d_nodes, n_nodes, npb, o); return cudaGetLastError(); }
-  if (force_seq == 8) { expand_reg_kernel<DIM, ORD, YAW, 3, 4><<<grid, kThreads, 0, st>>>(P, d_nodes, n_nodes, npb, o); return cudaGetLastError(); }
-#endif
-  using L = FlatLayout<DIM, ORD, YAW>;
   const bool need_vel = YAW || (P.pot != nullptr && P.grad_w != 0.0);
   const int maxns = P.maxn + 1;
   const size_t smem = kWarps * L::warp_bytes(need_vel, maxns);
