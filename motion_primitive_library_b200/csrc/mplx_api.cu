@@ -134,6 +134,7 @@ int mplx_set_map(mplx_ctx *c, const int8_t *data, const int32_t *dim, const doub
   for (int k = 0; k < 3; k++) {
     c->P.mdim[k] = k < c->dim ? dim[k] : 1;
     c->P.origin[k] = k < c->dim ? origin[k] : 0.0;
+    c->P.dimd[k] = (double)c->P.mdim[k];
   }
   c->P.res = res;
   c->P.rinv = 1.0 / res;

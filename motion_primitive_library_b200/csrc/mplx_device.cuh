@@ -20,7 +20,8 @@ struct EnvParams {
   int mdim[3];
   double origin[3];
   double res;
-  double rinv;  // RN(1/res), host-computed (fast path of floatToInt)
+  double rinv;     // RN(1/res), host-computed (exact-quotient correction, see div_exact)
+  double dimd[3];  // (double)mdim[k]
   double pot_w, grad_w;
   const int8_t *map;           // x-fastest int8 grid in HBM
   const int8_t *pot;           // potential grid or nullptr

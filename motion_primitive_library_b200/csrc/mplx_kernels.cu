@@ -96,10 +96,10 @@ __device__ __forceinline__ int sample_index(const EnvParams &P, const double (&p
 #pragma unroll
   for (int k = 0; k < DIM; k++) {
     const double y = div_exact(pk[k] - P.origin[k], P.res, P.rinv);
-    inside = inside && (y > 0x1p-55) && (y < (double)P.mdim[k]);
-    const double m = y + MPLX_MAGIC;      // nearest integer in the low mantissa bits
-    const double kd = m - MPLX_MAGIC;
-    pn[k] = __double2loint(m) - (kd > y ? 1 : 0);  // floor(y)
+    // floor(y) on the (otherwise idle) conversion pipe: saturates for |y| >= 2^31 and gives 0
+    // for NaN, both of which the two tests below classify as outside
+    pn[k] = __double2int_rd(y);
+    inside = inside && (y > 0x1p-55) && ((unsigned)pn[k] < (unsigned)P.mdim[k]);
   }
   if (!inside) return -1;
   int idx = pn[0] + P.mdim[0] * pn[1];
@@ -533,6 +533,7 @@ expand_reg_kernel(const __grid_constant__ EnvParams P, const mplx_waypoint *__re
   unsigned n_samples = 0;
   if (emit) {
     double cost = 0.0;
+    const double intrinsic = intrinsic_cost<DIM, ORD, YAW>(P, pr);  // before the loop: pr dies here
     if (!same) {
       double cf[CoefLayout<DIM, ORD, YAW>::NCMAX];
       fill_coef<DIM, ORD, YAW>(pr, need_vel, cf);
@@ -543,7 +544,7 @@ expand_reg_kernel(const __grid_constant__ EnvParams P, const mplx_waypoint *__re
       const double dt = n <= kNMax ? __ldg(P.tdt + n) : P.T / n;
       cost = traverse_regs<DIM, ORD, YAW, UNR>(P, cf, need_vel, dt, n_samples);
     }
-    if (!isinf(cost)) cost += intrinsic_cost<DIM, ORD, YAW>(P, pr);
+    if (!isinf(cost)) cost += intrinsic;
     if (o.cost) o.cost[slot] = cost;
   }
   if (P.stats) {

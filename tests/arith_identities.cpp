@@ -43,6 +43,15 @@ static long check_cell_rule() {
       const bool in_ref = rr >= 0 && rr < dim;
       const bool in_k = (y > 0x1p-55) && (y < (double)dim);
       if (in_ref != in_k) { bad++; continue; }
+      // device form: pn = cvt.rmi.s32.f64(y) (saturating, NaN -> 0); inside <=> y > 2^-55 && (unsigned)pn < dim
+      int pn_dev;
+      if (y != y) pn_dev = 0;
+      else if (y >= 2147483648.0) pn_dev = 2147483647;
+      else if (y < -2147483648.0) pn_dev = (-2147483647 - 1);
+      else pn_dev = (int)std::floor(y);
+      const bool in_dev = (y > 0x1p-55) && ((unsigned)pn_dev < (unsigned)dim);
+      if (in_dev != in_ref) { bad++; continue; }
+      if (in_ref && pn_dev != (int)rr) bad++;
       if (in_ref) {
         const double m = y + MAGIC, kd = m - MAGIC;
         uint64_t bits;
