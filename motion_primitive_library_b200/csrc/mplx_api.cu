@@ -199,9 +199,10 @@ int mplx_set_params(mplx_ctx *c, int control, double T, double w, double wyaw, d
   CU(cudaStreamSynchronize(c->stream));
   CU(c->U.reserve((size_t)nU * udim));
   CU(cudaMemcpyAsync(c->U.p, U, sizeof(double) * nU * udim, cudaMemcpyHostToDevice, c->stream));
-  CU(c->ttab.reserve((size_t)(mplx::kNMax + 1) * mplx::kTStride));
+  CU(c->ttab.reserve((size_t)(mplx::kNMax + 1) * mplx::kTStride + 8));  // + padding: units read 4 times at once
   CU(c->tcount.reserve(mplx::kNMax + 1));
   CU(c->tdt.reserve(mplx::kNMax + 1));
+  CU(cudaMemsetAsync(c->ttab.p, 0, sizeof(double) * ((size_t)(mplx::kNMax + 1) * mplx::kTStride + 8), c->stream));
   CU(mplx::launch_build_ttab(T, c->ttab.p, c->tcount.p, c->tdt.p, c->stream));
   c->launches++;
   CU(cudaStreamSynchronize(c->stream));
@@ -339,7 +340,7 @@ int mplx_expand(mplx_ctx *c, const mplx_waypoint *nodes, int n_nodes, const mplx
 
 int mplx_set_kernel(mplx_ctx *c, int which) {
   if (!c) return fail(MPLX_ERR_ARG, "null ctx");
-  if (which < 0 || which > 3) return fail(MPLX_ERR_ARG, "which must be 0 (auto: register), 1 (sequential), 2 (register) or 3 (flat)");
+  if (which < 0 || which > 5) return fail(MPLX_ERR_ARG, "which must be 0 (auto: register), 1 (sequential), 2 (register) or 3 (flat)");
   c->force_seq = which;
   return MPLX_OK;
 }
