@@ -301,6 +301,50 @@ class env_map_gpu : public env_map_host<Dim> {
   }
   void prefetch(const vec_E<Waypoint<Dim>> &cands) const override { pending_ = cands; }
 
+  /// Packed batched expansion for lock-step drivers (mplx_expand_packed, +inf successors dropped
+  /// on the device: A* skips them, graph_search.h:81).  Results stay in the env's buffers until the
+  /// next call: record r of node i is r in [p_offset[i], p_offset[i] + p_count[i]).
+  void expand_packed(const std::vector<mplx_waypoint> &nodes) const {
+    sync();
+    const int n = (int)nodes.size(), nU = (int)this->U_.size();
+    const std::size_t cap = (std::size_t)n * nU;
+    const int nstate = Dim * __builtin_popcount(control_ & 15) + ((control_ & 16) ? 1 : 0);
+    p_count.resize(n); p_offset.resize(n); p_state.resize(cap * nstate); p_cost.resize(cap); p_action.resize(cap); p_key.resize(cap);
+    mplx_packed_out out{p_count.data(), (int64_t *)p_offset.data(), p_state.data(), p_cost.data(), p_action.data(),
+                        p_key.data(), (int64_t)cap, 0, 0};
+    check(mplx_expand_packed(ctx_, nodes.data(), n, MPLX_PACK_DROP_INF, &out));
+    p_nstate = out.nstate;
+    stats_nodes_ += n;
+    stats_calls_++;
+  }
+  /// Rebuild the successor Waypoint of packed record r (parent `curr`): the state fields come from
+  /// the record; the rest are copies, not results (include/mplx.h, mplx_packed_out): the first
+  /// derivative above the state order is 0 + U[action] (Primitive1D::v/a/j at T with literal-zero
+  /// higher coefficients, primitive.h:134-145), higher ones 0, yaw 0 without a yaw control,
+  /// t = curr.t + dt (env_map.h:161).
+  Waypoint<Dim> packed_waypoint(std::size_t r, const mplx_waypoint &curr) const {
+    Waypoint<Dim> w(control_);
+    const double *st = p_state.data() + r * p_nstate;
+    const int nf = __builtin_popcount(control_ & 15);
+    const VecDf &u = this->U_[p_action[r]];
+    int c = 0;
+    for (int d = 0; d < Dim; d++) w.pos(d) = st[c++];
+    for (int d = 0; d < Dim; d++) w.vel(d) = nf >= 2 ? st[c++] : 0.0 + u[d];
+    for (int d = 0; d < Dim; d++) w.acc(d) = nf >= 3 ? st[c++] : (nf == 2 ? 0.0 + u[d] : 0.0);
+    for (int d = 0; d < Dim; d++) w.jrk(d) = nf >= 4 ? st[c++] : (nf == 3 ? 0.0 + u[d] : 0.0);
+    w.yaw = (control_ & 16) ? st[c++] : 0.0;
+    w.t = curr.t + this->dt_;
+    return w;
+  }
+  mutable std::vector<int32_t> p_count;
+  mutable std::vector<long long> p_offset;
+  mutable std::vector<double> p_state, p_cost;
+  mutable std::vector<uint16_t> p_action;
+  mutable std::vector<uint64_t> p_key;
+  mutable int p_nstate = 0;
+  static mplx_waypoint pod(const Waypoint<Dim> &w) { return to_pod(w); }
+  int control() const { return control_; }
+
   long stats_nodes() const { return stats_nodes_; }
   long stats_calls() const { return stats_calls_; }
   long stats_hits() const { return stats_hits_; }
@@ -459,98 +503,103 @@ struct StateSpace {
 template <int Dim>
 struct Edge { Waypoint<Dim> from; int action_id; };
 
-/// GraphSearch::Astar: include/mpl_planner/common/graph_search.h:39-182
+/// The A* loop of include/mpl_planner/common/graph_search.h:39-182 cut at the get_succ call, so
+/// that a driver can either run it to completion for one query (GraphSearch::Astar below) or
+/// advance many queries in lock-step and expand their current nodes in ONE device launch
+/// (MultiQueryPlanner).  The order of operations inside an iteration is the reference's:
+/// pop + close (:66-68) -> get_succ (:75) -> relax successors (:79-143) -> goal test (:146) ->
+/// max_expand (:149-155) -> empty queue (:157-161).
 template <int Dim>
-class GraphSearch {
+class AstarStepper {
  public:
-  explicit GraphSearch(bool verbose = false, int lookahead = 0) : verbose_(verbose), lookahead_(lookahead) {}
+  using S = State<Dim>;
+  AstarStepper(const env_base<Dim> *env, std::shared_ptr<StateSpace<Dim>> ss, int max_expand)
+      : ENV(env), ss_ptr(ss), max_expand_(max_expand) {}
 
-  decimal_t Astar(const Waypoint<Dim> &start_coord, const std::shared_ptr<env_base<Dim>> &ENV,
-                  std::shared_ptr<StateSpace<Dim>> &ss_ptr, std::vector<Edge<Dim>> &traj, int max_expand = -1) {
-    using S = State<Dim>;
+  /// graph_search.h:43-61
+  void start(const Waypoint<Dim> &start_coord) {
+    start_key_ = hash_value(start_coord);
+    if (ENV->is_goal(start_coord)) {
+      status_ = DONE_TRIVIAL;
+      return;
+    }
+    if (ss_ptr->pq_.empty()) {
+      auto &slot = ss_ptr->hm_[start_key_];
+      slot.reset(new S(start_coord, start_key_));
+      S *n = slot.get();
+      n->g = 0;
+      n->h = ss_ptr->eps_ == 0 ? 0 : ENV->get_heur(start_coord);
+      n->fval = n->g + ss_ptr->eps_ * n->h;
+      ss_ptr->pq_.push(n);
+      n->iterationopened = true;
+      n->iterationclosed = false;
+    }
+    status_ = RUNNING;
+  }
+  bool active() const { return status_ == RUNNING; }
+  const std::vector<S *> &open_heap() const { return ss_ptr->pq_.raw(); }
+
+  /// graph_search.h:64-68: the node this iteration expands
+  const Waypoint<Dim> &pop() {
+    expand_iteration_++;
+    curr_ = ss_ptr->pq_.top();
+    ss_ptr->pq_.pop();
+    curr_->iterationclosed = true;
+    return curr_->coord;
+  }
+
+  /// graph_search.h:79-161 with the successors of the node returned by pop()
+  template <typename SuccAt, typename KeyAt>
+  void consume(int n_succ, SuccAt succ_at, const decimal_t *succ_cost, const int *succ_act_id, KeyAt key_at) {
+    for (int s = 0; s < n_succ; ++s) {
+      if (std::isinf(succ_cost[s])) continue;  // graph_search.h:81
+      const std::size_t skey = key_at(s);
+      auto &slot = ss_ptr->hm_[skey];
+      if (!slot) {
+        slot.reset(new S(succ_at(s), skey));
+        slot->h = ss_ptr->eps_ == 0 ? 0 : ENV->get_heur(slot->coord);
+      }
+      S *succNode_ptr = slot.get();
+      succNode_ptr->pred_key.push_back(curr_->key);
+      succNode_ptr->pred_action_cost.push_back(succ_cost[s]);
+      succNode_ptr->pred_action_id.push_back(succ_act_id[s]);
+      const decimal_t tentative_gval = curr_->g + succ_cost[s];
+      if (tentative_gval < succNode_ptr->g) {
+        succNode_ptr->g = tentative_gval;
+        const decimal_t fval = succNode_ptr->g + (ss_ptr->eps_) * succNode_ptr->h;
+        succNode_ptr->fval = fval;
+        if (succNode_ptr->iterationopened && !succNode_ptr->iterationclosed) {
+          ss_ptr->pq_.increase(succNode_ptr);
+        } else {
+          ss_ptr->pq_.push(succNode_ptr);
+          succNode_ptr->iterationopened = true;
+        }
+      }
+    }
+    if (ENV->is_goal(curr_->coord)) {
+      status_ = DONE_GOAL;
+    } else if (max_expand_ > 0 && expand_iteration_ >= max_expand_) {
+      status_ = FAILED;
+    } else if (ss_ptr->pq_.empty()) {
+      status_ = FAILED;
+    }
+    if (status_ != RUNNING) ss_ptr->expand_iteration_ = expand_iteration_;
+  }
+
+  /// graph_search.h:163-181: cost + recovered trajectory
+  decimal_t finish(std::vector<Edge<Dim>> &traj) {
     const decimal_t inf = std::numeric_limits<decimal_t>::infinity();
     traj.clear();
-    if (ENV->is_goal(start_coord)) return 0;
-    const std::size_t start_key = hash_value(start_coord);
-    S *currNode_ptr = nullptr;
-    if (ss_ptr->pq_.empty()) {
-      auto &slot = ss_ptr->hm_[start_key];
-      slot.reset(new S(start_coord, start_key));
-      currNode_ptr = slot.get();
-      currNode_ptr->g = 0;
-      currNode_ptr->h = ss_ptr->eps_ == 0 ? 0 : ENV->get_heur(start_coord);
-      currNode_ptr->fval = currNode_ptr->g + ss_ptr->eps_ * currNode_ptr->h;
-      ss_ptr->pq_.push(currNode_ptr);
-      currNode_ptr->iterationopened = true;
-      currNode_ptr->iterationclosed = false;
-    }
-    int expand_iteration = 0;
-    vec_E<Waypoint<Dim>> succ_coord;
-    std::vector<decimal_t> succ_cost;
-    std::vector<int> succ_act_id;
-    vec_E<Waypoint<Dim>> cands;
-    while (true) {
-      expand_iteration++;
-      currNode_ptr = ss_ptr->pq_.top();
-      if (lookahead_ > 0) {
-        // hint: the open nodes nearest the root of the heap are the likeliest next pops
-        cands.clear();
-        const auto &raw = ss_ptr->pq_.raw();
-        for (std::size_t i = 1; i < raw.size() && (int)cands.size() < lookahead_; i++) cands.push_back(raw[i]->coord);
-        ENV->prefetch(cands);
-      }
-      ss_ptr->pq_.pop();
-      currNode_ptr->iterationclosed = true;
-
-      ENV->get_succ(currNode_ptr->coord, succ_coord, succ_cost, succ_act_id);
-
-      for (unsigned s = 0; s < succ_coord.size(); ++s) {
-        if (std::isinf(succ_cost[s])) continue;  // graph_search.h:81
-        const std::size_t skey = hash_value(succ_coord[s]);
-        auto &slot = ss_ptr->hm_[skey];
-        if (!slot) {
-          slot.reset(new S(succ_coord[s], skey));
-          slot->h = ss_ptr->eps_ == 0 ? 0 : ENV->get_heur(slot->coord);
-        }
-        S *succNode_ptr = slot.get();
-        succNode_ptr->pred_key.push_back(currNode_ptr->key);
-        succNode_ptr->pred_action_cost.push_back(succ_cost[s]);
-        succNode_ptr->pred_action_id.push_back(succ_act_id[s]);
-        decimal_t tentative_gval = currNode_ptr->g + succ_cost[s];
-        if (tentative_gval < succNode_ptr->g) {
-          succNode_ptr->g = tentative_gval;
-          decimal_t fval = succNode_ptr->g + (ss_ptr->eps_) * succNode_ptr->h;
-          if (succNode_ptr->iterationopened && !succNode_ptr->iterationclosed) {
-            succNode_ptr->fval = fval;
-            ss_ptr->pq_.increase(succNode_ptr);
-          } else {
-            succNode_ptr->fval = fval;
-            ss_ptr->pq_.push(succNode_ptr);
-            succNode_ptr->iterationopened = true;
-          }
-        }
-      }
-      if (ENV->is_goal(currNode_ptr->coord)) break;
-      if (max_expand > 0 && expand_iteration >= max_expand) {
-        if (verbose_) printf("MaxExpandStep [%d] Reached!!!!!!\n\n", max_expand);
-        ss_ptr->expand_iteration_ = expand_iteration;
-        return inf;
-      }
-      if (ss_ptr->pq_.empty()) {
-        if (verbose_) printf("Priority queue is empty!!!!!!\n\n");
-        ss_ptr->expand_iteration_ = expand_iteration;
-        return inf;
-      }
-    }
-    ss_ptr->expand_iteration_ = expand_iteration;
-    if (recoverTraj(currNode_ptr, ss_ptr, start_key, traj)) return currNode_ptr->g;
+    if (status_ == DONE_TRIVIAL) return 0;
+    if (status_ != DONE_GOAL) return inf;
+    if (recoverTraj(curr_, traj)) return curr_->g;
     return inf;
   }
+  int expanded() const { return expand_iteration_; }
 
  private:
   /// recoverTraj: graph_search.h:369-455
-  bool recoverTraj(State<Dim> *currNode_ptr, std::shared_ptr<StateSpace<Dim>> ss_ptr, std::size_t start_key,
-                   std::vector<Edge<Dim>> &traj) {
+  bool recoverTraj(S *currNode_ptr, std::vector<Edge<Dim>> &traj) {
     const decimal_t inf = std::numeric_limits<decimal_t>::infinity();
     ss_ptr->best_child_.clear();
     bool find_traj = false;
@@ -560,7 +609,7 @@ class GraphSearch {
       int min_id = -1;
       decimal_t min_rhs = inf, min_g = inf;
       for (unsigned int i = 0; i < currNode_ptr->pred_key.size(); i++) {
-        State<Dim> *pred = ss_ptr->hm_[currNode_ptr->pred_key[i]].get();
+        S *pred = ss_ptr->hm_[currNode_ptr->pred_key[i]].get();
         if (min_rhs > pred->g + currNode_ptr->pred_action_cost[i]) {
           min_rhs = pred->g + currNode_ptr->pred_action_cost[i];
           min_g = pred->g;
@@ -579,7 +628,7 @@ class GraphSearch {
         prs.push_back(Edge<Dim>{currNode_ptr->coord, action_idx});  // forward_action(coord, action): env_base.h:228-231
       } else
         break;
-      if (currNode_ptr->key == start_key) {
+      if (currNode_ptr->key == start_key_) {
         ss_ptr->best_child_.push_back(currNode_ptr);
         find_traj = true;
         break;
@@ -590,6 +639,49 @@ class GraphSearch {
     traj = find_traj ? prs : std::vector<Edge<Dim>>();
     return find_traj;
   }
+
+  enum Status { IDLE, RUNNING, DONE_TRIVIAL, DONE_GOAL, FAILED };
+  const env_base<Dim> *ENV;
+  std::shared_ptr<StateSpace<Dim>> ss_ptr;
+  int max_expand_;
+  Status status_ = IDLE;
+  int expand_iteration_ = 0;
+  std::size_t start_key_ = 0;
+  S *curr_ = nullptr;
+};
+
+/// GraphSearch::Astar: include/mpl_planner/common/graph_search.h:39-182
+template <int Dim>
+class GraphSearch {
+ public:
+  explicit GraphSearch(bool verbose = false, int lookahead = 0) : verbose_(verbose), lookahead_(lookahead) {}
+
+  decimal_t Astar(const Waypoint<Dim> &start_coord, const std::shared_ptr<env_base<Dim>> &ENV,
+                  std::shared_ptr<StateSpace<Dim>> &ss_ptr, std::vector<Edge<Dim>> &traj, int max_expand = -1) {
+    AstarStepper<Dim> st(ENV.get(), ss_ptr, max_expand);
+    st.start(start_coord);
+    vec_E<Waypoint<Dim>> succ_coord;
+    std::vector<decimal_t> succ_cost;
+    std::vector<int> succ_act_id;
+    vec_E<Waypoint<Dim>> cands;
+    while (st.active()) {
+      if (lookahead_ > 0) {
+        // hint: the open nodes nearest the root of the heap are the likeliest next pops
+        cands.clear();
+        const auto &raw = st.open_heap();
+        for (std::size_t i = 1; i < raw.size() && (int)cands.size() < lookahead_; i++) cands.push_back(raw[i]->coord);
+        ENV->prefetch(cands);
+      }
+      const Waypoint<Dim> &curr = st.pop();
+      ENV->get_succ(curr, succ_coord, succ_cost, succ_act_id);
+      st.consume((int)succ_coord.size(), [&](int s) -> const Waypoint<Dim> & { return succ_coord[s]; },
+                 succ_cost.data(), succ_act_id.data(), [&](int s) { return hash_value(succ_coord[s]); });
+    }
+    if (verbose_ && std::isinf(st.finish(traj))) printf("[GraphSearch] no trajectory (max expansions or empty queue)\n");
+    return st.finish(traj);
+  }
+
+ private:
   bool verbose_;
   int lookahead_;
 };
@@ -684,4 +776,91 @@ class MapPlanner : public PlannerBase<Dim> {
 };
 typedef MapPlanner<2> OccMapPlanner;
 typedef MapPlanner<3> VoxelMapPlanner;
+
+/// Lock-step batched A* over many independent (start, goal) queries on one map — BASELINE.json
+/// config 5.  Every iteration pops the best open node of each live query (AstarStepper::pop) and
+/// expands all of them in ONE device launch (env_map_gpu::expand_packed); each query then relaxes
+/// its own successors.  Per query the sequence of expanded nodes is exactly the one
+/// MapPlanner::plan() produces for that query alone.
+template <int Dim>
+class MultiQueryPlanner {
+ public:
+  struct Result {
+    bool valid = false;
+    decimal_t cost = std::numeric_limits<decimal_t>::infinity();
+    int expanded = 0;
+    std::size_t n_closed = 0;
+    std::vector<int> actions;
+  };
+  explicit MultiQueryPlanner(const std::shared_ptr<MapUtil<Dim>> &map_util, int device = 0)
+      : map_util_(map_util), gpu_(new env_map_gpu<Dim>(map_util, device)) {}
+  /// the shared env: set U, limits, weights, control, tolerances on it
+  env_map_gpu<Dim> &env() { return *gpu_; }
+  long iterations() const { return iterations_; }
+  long nodes_expanded() const { return nodes_; }
+
+  std::vector<Result> plan(const vec_E<Waypoint<Dim>> &starts, const vec_E<Waypoint<Dim>> &goals, decimal_t eps,
+                           int max_expand) {
+    // per-query host env: goal test + heuristic only (its get_succ is never called)
+    struct QueryEnv : env_map_host<Dim> {
+      using env_map_host<Dim>::env_map_host;
+      void get_succ(const Waypoint<Dim> &, vec_E<Waypoint<Dim>> &, std::vector<decimal_t> &, std::vector<int> &) const override {}
+    };
+    const std::size_t Q = starts.size();
+    std::vector<std::unique_ptr<QueryEnv>> envs(Q);
+    std::vector<std::shared_ptr<StateSpace<Dim>>> ss(Q);
+    std::vector<std::unique_ptr<AstarStepper<Dim>>> st(Q);
+    std::vector<Result> res(Q);
+    for (std::size_t q = 0; q < Q; q++) {
+      envs[q].reset(new QueryEnv(map_util_));
+      QueryEnv &e = *envs[q];
+      e.w_ = gpu_->w_; e.v_max_ = gpu_->v_max_; e.dt_ = gpu_->dt_; e.t_max_ = gpu_->t_max_;
+      e.tol_pos_ = gpu_->tol_pos_; e.tol_vel_ = gpu_->tol_vel_; e.tol_acc_ = gpu_->tol_acc_; e.tol_yaw_ = gpu_->tol_yaw_;
+      e.set_goal(goals[q]);
+      ss[q].reset(new StateSpace<Dim>(eps));
+      st[q].reset(new AstarStepper<Dim>(&e, ss[q], max_expand));
+      if (e.is_free(starts[q].pos)) st[q]->start(starts[q]);  // planner_base.h:283-287
+    }
+    std::vector<mplx_waypoint> batch;
+    std::vector<std::size_t> who;
+    std::vector<int> act;
+    iterations_ = nodes_ = 0;
+    for (;;) {
+      batch.clear();
+      who.clear();
+      for (std::size_t q = 0; q < Q; q++)
+        if (st[q]->active()) {
+          batch.push_back(env_map_gpu<Dim>::pod(st[q]->pop()));
+          who.push_back(q);
+        }
+      if (batch.empty()) break;
+      gpu_->expand_packed(batch);
+      iterations_++;
+      nodes_ += (long)batch.size();
+      for (std::size_t b = 0; b < who.size(); b++) {
+        const std::size_t r0 = (std::size_t)gpu_->p_offset[b];
+        const int cnt = gpu_->p_count[b];
+        act.resize(cnt);
+        for (int j = 0; j < cnt; j++) act[j] = gpu_->p_action[r0 + j];
+        st[who[b]]->consume(cnt, [&](int s) { return gpu_->packed_waypoint(r0 + s, batch[b]); },
+                            gpu_->p_cost.data() + r0, act.data(),
+                            [&](int s) { return (std::size_t)gpu_->p_key[r0 + s]; });
+      }
+    }
+    for (std::size_t q = 0; q < Q; q++) {
+      std::vector<Edge<Dim>> traj;
+      res[q].cost = st[q]->finish(traj);
+      res[q].valid = !std::isinf(res[q].cost);
+      res[q].expanded = st[q]->expanded();
+      for (const auto &e : traj) res[q].actions.push_back(e.action_id);
+      for (const auto &it : ss[q]->hm_) if (it.second && it.second->iterationclosed) res[q].n_closed++;
+    }
+    return res;
+  }
+
+ private:
+  std::shared_ptr<MapUtil<Dim>> map_util_;
+  std::unique_ptr<env_map_gpu<Dim>> gpu_;
+  long iterations_ = 0, nodes_ = 0;
+};
 }  // namespace MPL

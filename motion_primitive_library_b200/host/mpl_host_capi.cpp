@@ -38,4 +38,54 @@ int mplh_plan(const mplh_plan_args *a, mplh_plan_result *r, uint64_t *closed_key
     return 2;
   }
 }
+
+/* Lock-step batched A* over n_q (start, goal) pairs on the map/params of `a` (a->start/goal are
+ * ignored).  totals[0] = lock-step iterations (= device launches of the expansion kernel),
+ * totals[1] = nodes expanded over all queries, totals[2] = wall seconds of the search. */
+int mplh_plan_batch(const mplh_plan_args *a, const mplx_waypoint *starts, const mplx_waypoint *goals, int n_q,
+                    mplh_query_result *out, double *totals) {
+  try {
+    auto go = [&](auto dimtag) {
+      constexpr int Dim = decltype(dimtag)::value;
+      MPL::MultiQueryPlanner<Dim> mq(mplh::make_map<Dim>(a), a->device);
+      auto &e = mq.env();
+      vec_E<VecDf> U;
+      for (int i = 0; i < a->nU; i++) U.push_back(VecDf(a->U + (size_t)i * a->udim, a->U + (size_t)(i + 1) * a->udim));
+      e.set_u(U); e.set_control(a->control);
+      e.set_v_max(a->v_max); e.set_a_max(a->a_max); e.set_j_max(a->j_max); e.set_yaw_max(a->yaw_max);
+      e.set_dt(a->T); e.set_w(a->w); e.set_wyaw(a->wyaw);
+      e.set_tol_pos(a->tol_pos); e.set_tol_vel(a->tol_vel); e.set_tol_acc(a->tol_acc);
+      if (a->potential) {
+        size_t n = 1;
+        for (int k = 0; k < Dim; k++) n *= (size_t)a->mdim[k];
+        e.set_potential_map(std::vector<int8_t>(a->potential, a->potential + n));
+        e.set_potential_weight(a->potential_weight);
+        e.set_gradient_weight(a->gradient_weight);
+      }
+      vec_E<Waypoint<Dim>> S, G;
+      for (int q = 0; q < n_q; q++) {
+        S.push_back(mplh::wp_from<Dim>(starts[q], a->control));
+        G.push_back(mplh::wp_from<Dim>(goals[q], a->control));
+      }
+      auto t0 = std::chrono::steady_clock::now();
+      auto res = mq.plan(S, G, a->eps, a->max_num);
+      const double secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+      for (int q = 0; q < n_q; q++) {
+        out[q].valid = res[q].valid ? 1 : 0;
+        out[q].cost = res[q].cost;
+        out[q].expanded = res[q].expanded;
+        out[q].n_closed = (int)res[q].n_closed;
+        out[q].n_actions = (int)res[q].actions.size();
+      }
+      if (totals) { totals[0] = (double)mq.iterations(); totals[1] = (double)mq.nodes_expanded(); totals[2] = secs; }
+    };
+    if (a->dim == 2) go(std::integral_constant<int, 2>());
+    else if (a->dim == 3) go(std::integral_constant<int, 3>());
+    else { g_err = "dim must be 2 or 3"; return 1; }
+    return 0;
+  } catch (const std::exception &e) {
+    g_err = e.what();
+    return 2;
+  }
+}
 }

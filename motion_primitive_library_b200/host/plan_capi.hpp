@@ -37,6 +37,17 @@ typedef struct {
 } mplh_plan_result;
 }
 
+extern "C" {
+/* Batched queries (config 5): shares every field of mplh_plan_args except start/goal. */
+typedef struct {
+  int32_t valid;
+  double cost;
+  int32_t expanded;
+  int32_t n_closed;
+  int32_t n_actions;
+} mplh_query_result;
+}
+
 namespace mplh {
 template <int Dim>
 Waypoint<Dim> wp_from(const mplx_waypoint &p, int control) {

@@ -1,0 +1,130 @@
+"""ctypes binding of libmpl_host.so: the C++ host planner (MPL::MapPlanner with the GPU env,
+MPL::MultiQueryPlanner) behind flat C structs.  See host/plan_capi.hpp."""
+import ctypes as C
+from pathlib import Path
+
+import numpy as np
+
+PKG = Path(__file__).resolve().parent
+LIB = PKG / "lib" / "libmpl_host.so"
+
+class Waypoint(C.Structure):
+    _fields_ = [("pos", C.c_double * 3), ("vel", C.c_double * 3), ("acc", C.c_double * 3), ("jrk", C.c_double * 3),
+                ("yaw", C.c_double), ("t", C.c_double)]
+
+
+class PlanArgs(C.Structure):
+    _fields_ = [
+        ("dim", C.c_int32), ("control", C.c_int32), ("map", C.c_void_p), ("mdim", C.c_int32 * 3),
+        ("origin", C.c_double * 3), ("res", C.c_double), ("U", C.c_void_p), ("nU", C.c_int32), ("udim", C.c_int32),
+        ("T", C.c_double), ("w", C.c_double), ("wyaw", C.c_double), ("eps", C.c_double),
+        ("v_max", C.c_double), ("a_max", C.c_double), ("j_max", C.c_double), ("yaw_max", C.c_double),
+        ("tol_pos", C.c_double), ("tol_vel", C.c_double), ("tol_acc", C.c_double),
+        ("start", Waypoint), ("goal", Waypoint), ("max_num", C.c_int32), ("speculate", C.c_int32),
+        ("device", C.c_int32), ("potential", C.c_void_p), ("potential_weight", C.c_double),
+        ("gradient_weight", C.c_double),
+    ]
+
+
+class PlanResult(C.Structure):
+    _fields_ = [("valid", C.c_int32), ("cost", C.c_double), ("expanded", C.c_int32), ("n_closed", C.c_int32),
+                ("n_open", C.c_int32), ("n_actions", C.c_int32), ("gpu_nodes", C.c_int64), ("gpu_calls", C.c_int64),
+                ("gpu_launches", C.c_int64), ("seconds", C.c_double)]
+
+
+class QueryResult(C.Structure):
+    _fields_ = [("valid", C.c_int32), ("cost", C.c_double), ("expanded", C.c_int32), ("n_closed", C.c_int32),
+                ("n_actions", C.c_int32)]
+
+
+WAYPOINT_DTYPE = np.dtype(
+    [("pos", "<f8", 3), ("vel", "<f8", 3), ("acc", "<f8", 3), ("jrk", "<f8", 3), ("yaw", "<f8"), ("t", "<f8")]
+)
+
+
+def load_fn(path, fn):
+    L = C.CDLL(str(path))
+    f = getattr(L, fn)
+    f.argtypes = [C.POINTER(PlanArgs), C.POINTER(PlanResult), C.c_void_p, C.c_int, C.c_void_p, C.c_int]
+    f.restype = C.c_int
+    return L, f
+
+
+def make_args(dim, control, grid, mdim, origin, res, U, start, goal, T=1.0, w=10.0, wyaw=1.0, eps=1.0, v_max=-1.0,
+              a_max=-1.0, j_max=-1.0, yaw_max=-1.0, tol_pos=0.5, tol_vel=-1.0, tol_acc=-1.0, max_num=-1, speculate=1,
+              potential=None, potential_weight=0.1, gradient_weight=0.0):
+    keep = dict(grid=np.ascontiguousarray(grid, dtype=np.int8), U=np.ascontiguousarray(U, dtype=np.float64))
+    a = PlanArgs()
+    a.dim, a.control = dim, control
+    a.map = keep["grid"].ctypes.data
+    for k in range(3):
+        a.mdim[k] = int(mdim[k]) if k < dim else 1
+        a.origin[k] = float(origin[k]) if k < dim else 0.0
+    a.res = res
+    a.U = keep["U"].ctypes.data
+    a.nU, a.udim = keep["U"].shape
+    a.T, a.w, a.wyaw, a.eps = T, w, wyaw, eps
+    a.v_max, a.a_max, a.j_max, a.yaw_max = v_max, a_max, j_max, yaw_max
+    a.tol_pos, a.tol_vel, a.tol_acc = tol_pos, tol_vel, tol_acc
+    for name, src in (("start", start), ("goal", goal)):
+        w_ = getattr(a, name)
+        for f in ("pos", "vel", "acc", "jrk"):
+            v = src.get(f, ())
+            for k in range(len(v)):
+                getattr(w_, f)[k] = float(v[k])
+        w_.yaw = float(src.get("yaw", 0.0))
+    a.max_num, a.speculate, a.device = max_num, speculate, 0
+    if potential is not None:
+        keep["pot"] = np.ascontiguousarray(potential, dtype=np.int8)
+        a.potential = keep["pot"].ctypes.data
+    a.potential_weight, a.gradient_weight = potential_weight, gradient_weight
+    a._keep = keep
+    return a
+
+
+def run_plan(fn, lib, args, cap=1 << 21):
+    r = PlanResult()
+    closed = np.zeros(cap, dtype=np.uint64)
+    actions = np.zeros(65536, dtype=np.int32)
+    rc = fn(C.byref(args), C.byref(r), closed.ctypes.data, cap, actions.ctypes.data, actions.size)
+    if rc != 0:
+        err = getattr(lib, "mplh_last_error", None)
+        raise RuntimeError(err().decode() if err else f"plan failed rc={rc}")
+    out = {k: getattr(r, k) for k, _ in PlanResult._fields_}
+    out["closed"] = closed[: min(r.n_closed, cap)].copy()
+    out["actions"] = actions[: r.n_actions].copy()
+    return out
+
+
+def _host():
+    if not LIB.exists():
+        raise ImportError(f"{LIB} not built (python -c 'import __graft_entry__ as g; g.build()')")
+    lib, fn = load_fn(LIB, "mplh_plan")
+    lib.mplh_last_error.restype = C.c_char_p
+    lib.mplh_plan_batch.argtypes = [C.POINTER(PlanArgs), C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+    lib.mplh_plan_batch.restype = C.c_int
+    return lib, fn
+
+
+def plan(args):
+    """MPL::MapPlanner<Dim>::plan() with the GPU env (one query)."""
+    lib, fn = _host()
+    return run_plan(fn, lib, args)
+
+
+def plan_batch(args, starts, goals):
+    """MPL::MultiQueryPlanner: lock-step A* over many (start, goal) pairs; one device launch per
+    iteration expands the current node of every live query.  starts/goals: WAYPOINT_DTYPE arrays."""
+    lib, _ = _host()
+    starts = np.ascontiguousarray(starts, dtype=WAYPOINT_DTYPE)
+    goals = np.ascontiguousarray(goals, dtype=WAYPOINT_DTYPE)
+    nq = len(starts)
+    out = (QueryResult * max(nq, 1))()
+    totals = np.zeros(3)
+    rc = lib.mplh_plan_batch(C.byref(args), starts.ctypes.data, goals.ctypes.data, nq, out, totals.ctypes.data)
+    if rc != 0:
+        raise RuntimeError(lib.mplh_last_error().decode())
+    res = np.zeros(nq, dtype=[("valid", "i4"), ("cost", "f8"), ("expanded", "i4"), ("n_closed", "i4"), ("n_actions", "i4")])
+    for q in range(nq):
+        res[q] = (out[q].valid, out[q].cost, out[q].expanded, out[q].n_closed, out[q].n_actions)
+    return res, dict(iterations=int(totals[0]), nodes=int(totals[1]), seconds=float(totals[2]))

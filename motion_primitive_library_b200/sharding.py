@@ -1,0 +1,66 @@
+"""Multi-GPU: the path shards over independent units (frontier batches, or whole start/goal queries
+— BASELINE.json config 5), one process per GPU, every rank holding a replica of the map.  There is
+no data-path collective: ranks exchange only the per-query results and the counters at the end
+(torch.distributed: NCCL on GPUs, gloo in the CPU tests)."""
+from __future__ import annotations
+
+import numpy as np
+
+
+def shard_slice(n_items: int, rank: int, world: int) -> slice:
+    """Contiguous, balanced partition: rank r owns [n*r/world, n*(r+1)/world)."""
+    if not (0 <= rank < world):
+        raise ValueError("rank out of range")
+    return slice(n_items * rank // world, n_items * (rank + 1) // world)
+
+
+def run_sharded(items: np.ndarray, fn, group=None, device=None):
+    """Run fn(my_items) -> (structured result array of len(my_items), counters dict) on this rank's
+    slice and return (all results in the original order, counters reduced over ranks).
+    Counter reduction: keys ending in '_max' are max-reduced (e.g. device seconds), the rest summed.
+    Works without torch.distributed (world 1)."""
+    import torch
+    import torch.distributed as dist
+
+    on = dist.is_available() and dist.is_initialized()
+    rank = dist.get_rank(group) if on else 0
+    world = dist.get_world_size(group) if on else 1
+    sl = shard_slice(len(items), rank, world)
+    mine, counters = fn(items[sl])
+    mine = np.ascontiguousarray(mine)
+    if len(mine) != sl.stop - sl.start:
+        raise ValueError("fn must return one result per item")
+    if not on or world == 1:
+        return mine, dict(counters)
+    dev = device if device is not None else (torch.device("cuda", torch.cuda.current_device())
+                                             if dist.get_backend(group) == "nccl" else torch.device("cpu"))
+    # results: pad each rank's bytes to the largest shard, all_gather, strip
+    per = mine.dtype.itemsize
+    longest = max(shard_slice(len(items), r, world).stop - shard_slice(len(items), r, world).start for r in range(world))
+    buf = np.zeros(longest * per, dtype=np.uint8)
+    buf[: mine.nbytes] = mine.view(np.uint8).reshape(-1)
+    send = torch.from_numpy(buf).to(dev)
+    recv = [torch.empty_like(send) for _ in range(world)]
+    dist.all_gather(recv, send, group=group)
+    parts = []
+    for r in range(world):
+        s = shard_slice(len(items), r, world)
+        nbytes = (s.stop - s.start) * per
+        parts.append(recv[r].cpu().numpy()[:nbytes].view(mine.dtype))
+    allres = np.concatenate(parts) if parts else mine
+    keys = sorted(counters)
+    sums = torch.tensor([float(counters[k]) for k in keys if not k.endswith("_max")], dtype=torch.float64, device=dev)
+    maxs = torch.tensor([float(counters[k]) for k in keys if k.endswith("_max")], dtype=torch.float64, device=dev)
+    if sums.numel():
+        dist.all_reduce(sums, op=dist.ReduceOp.SUM, group=group)
+    if maxs.numel():
+        dist.all_reduce(maxs, op=dist.ReduceOp.MAX, group=group)
+    out, si, mi = {}, 0, 0
+    for k in keys:
+        if k.endswith("_max"):
+            out[k] = float(maxs[mi])
+            mi += 1
+        else:
+            out[k] = float(sums[si])
+            si += 1
+    return allres, out
