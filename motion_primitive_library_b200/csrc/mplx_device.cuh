@@ -90,8 +90,10 @@ __device__ __forceinline__ double round_haz(double x, int &k) {
   double kd = m - MPLX_MAGIC;
   const double f = x - kd;  // exact, in [-0.5, 0.5]
   k = __double2loint(m);
-  if (f == 0.5 && x > 0.0) { kd += 1.0; k += 1; }    // tie rounded down to even: away from zero is up
-  if (f == -0.5 && x < 0.0) { kd -= 1.0; k -= 1; }   // tie rounded up to even: away from zero is down
+  if (fabs(f) == 0.5) {  // an exact tie (uncommon): RN-even may have gone toward zero
+    if (f > 0.0 && x > 0.0) { kd += 1.0; k += 1; }  // rounded down to even: away from zero is up
+    if (f < 0.0 && x < 0.0) { kd -= 1.0; k -= 1; }  // rounded up to even: away from zero is down
+  }
   return kd;
 }
 

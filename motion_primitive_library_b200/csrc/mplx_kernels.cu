@@ -332,26 +332,16 @@ __device__ __forceinline__ void phase_ab(const EnvParams &P, const mplx_waypoint
   if (active) {
     const mplx_waypoint *cp = nodes + ni;
     const double *u = P.U + (size_t)ci * P.udim;
-    uint64_t hcurr = 0;
-    // Primitive(curr, U[i], dt): primitive.h:220-256 ; hash_value(curr): waypoint.h:93-125
+    // Primitive(curr, U[i], dt): primitive.h:220-256
 #pragma unroll
-    for (int k = 0; k < DIM; k++) {
-      const double p = cp->pos[k], v = cp->vel[k], a = cp->acc[k], j = cp->jrk[k];
-      pr.ax[k].build(__ldg(u + k), p, v, a, j);
-      hash_combine(hcurr, lattice_id(p, 0.01, 100.0));
-      if (ORD >= 2) hash_combine(hcurr, lattice_id(v, 0.1, 10.0));
-      if (ORD >= 3) hash_combine(hcurr, lattice_id(a, 0.1, 10.0));
-      if (ORD >= 4) hash_combine(hcurr, lattice_id(j, 0.1, 10.0));
-    }
+    for (int k = 0; k < DIM; k++) pr.ax[k].build(__ldg(u + k), cp->pos[k], cp->vel[k], cp->acc[k], cp->jrk[k]);
     if (YAW) {
       pr.yaw_u = __ldg(u + DIM);
       pr.yaw0 = cp->yaw;
-      hash_combine(hcurr, lattice_id(cp->yaw, 0.1, 10.0));
     }
     // tn = pr.evaluate(dt): primitive.h:321-331 (all four derivative vectors are filled)
     const double T = P.T;
     const double pw3T = (T * T) * T, pw4T = pw3T * T;
-    int nl_ = 0;
 #pragma unroll
     for (int k = 0; k < 3; k++) {
       if (k < DIM) {
@@ -359,33 +349,20 @@ __device__ __forceinline__ void phase_ab(const EnvParams &P, const mplx_waypoint
         tn.vel[k] = pr.ax[k].v(T, pw3T);
         tn.acc[k] = pr.ax[k].a(T);
         tn.jrk[k] = pr.ax[k].j(T);
-        int id = lattice_id(tn.pos[k], 0.01, 100.0);
-        hash_combine(key, id);
-        lat[nl_++] = id;
-        if (ORD >= 2) { id = lattice_id(tn.vel[k], 0.1, 10.0); hash_combine(key, id); lat[nl_++] = id; }
-        if (ORD >= 3) { id = lattice_id(tn.acc[k], 0.1, 10.0); hash_combine(key, id); lat[nl_++] = id; }
-        if (ORD >= 4) { id = lattice_id(tn.jrk[k], 0.1, 10.0); hash_combine(key, id); lat[nl_++] = id; }
         same = same && (pr.ax[k].c5 == tn.pos[k]);  // curr.pos == tn.pos (env_map.h:163)
       } else {
         tn.pos[k] = tn.vel[k] = tn.acc[k] = tn.jrk[k] = 0.0;
       }
     }
     tn.yaw = 0.0;
-    if (YAW) {
-      // pr_yaw_.p(t) = 0/120*.. + c4*t + c5 with the leading +0 sum (primitive.h:128-131,328)
-      tn.yaw = normalize_angle(0.0 + pr.yaw_u * T + pr.yaw0);
-      int id = lattice_id(tn.yaw, 0.1, 10.0);
-      hash_combine(key, id);
-      lat[nl_++] = id;
-    }
-#pragma unroll
-    for (int q = 0; q < MPLX_LATTICE_MAX; q++)
-      if (q >= nl_) lat[q] = 0;
+    // pr_yaw_.p(t) = 0/120*.. + c4*t + c5 with the leading +0 sum (primitive.h:128-131,328)
+    if (YAW) tn.yaw = normalize_angle(0.0 + pr.yaw_u * T + pr.yaw0);
     tn.t = cp->t + T;  // env_map.h:161
 
-    // tn == curr (hash equality, waypoint.h:133-135) || !validate_primitive (primitive.h:449-475)
-    bool ok = key != hcurr;
-    if (ok && YAW) ok = validate_yaw<DIM, ORD, YAW>(P, pr);
+    // !validate_primitive (primitive.h:449-475) first: the test is pure, and a primitive that fails
+    // it is dropped whatever its key, so the lattice key is only computed for the survivors
+    bool ok = true;
+    if (YAW) ok = validate_yaw<DIM, ORD, YAW>(P, pr);
     // max_vel per axis serves validate_xxx(VEL) (primitive.h:482-496) and traverse (env_map.h:91-94)
 #pragma unroll
     for (int k = 0; k < DIM; k++) {
@@ -400,6 +377,34 @@ __device__ __forceinline__ void phase_ab(const EnvParams &P, const mplx_waypoint
     if (ok && ORD >= 4 && P.j_max > 0) {
 #pragma unroll
       for (int k = 0; k < DIM; k++) ok = ok && !(pr.ax[k].max_jrk(T) > P.j_max);
+    }
+    if (ok) {
+      // tn == curr  <=>  hash_value(tn) == hash_value(curr)  (waypoint.h:133-135, 93-125)
+      uint64_t hcurr = 0;
+      int nl_ = 0;
+#pragma unroll
+      for (int k = 0; k < DIM; k++) {
+        hash_combine(hcurr, lattice_id(cp->pos[k], 0.01, 100.0));
+        if (ORD >= 2) hash_combine(hcurr, lattice_id(cp->vel[k], 0.1, 10.0));
+        if (ORD >= 3) hash_combine(hcurr, lattice_id(cp->acc[k], 0.1, 10.0));
+        if (ORD >= 4) hash_combine(hcurr, lattice_id(cp->jrk[k], 0.1, 10.0));
+        int id = lattice_id(tn.pos[k], 0.01, 100.0);
+        hash_combine(key, id);
+        lat[nl_++] = id;
+        if (ORD >= 2) { id = lattice_id(tn.vel[k], 0.1, 10.0); hash_combine(key, id); lat[nl_++] = id; }
+        if (ORD >= 3) { id = lattice_id(tn.acc[k], 0.1, 10.0); hash_combine(key, id); lat[nl_++] = id; }
+        if (ORD >= 4) { id = lattice_id(tn.jrk[k], 0.1, 10.0); hash_combine(key, id); lat[nl_++] = id; }
+      }
+      if (YAW) {
+        hash_combine(hcurr, lattice_id(cp->yaw, 0.1, 10.0));
+        const int id = lattice_id(tn.yaw, 0.1, 10.0);
+        hash_combine(key, id);
+        lat[nl_++] = id;
+      }
+#pragma unroll
+      for (int q = 0; q < MPLX_LATTICE_MAX; q++)
+        if (q >= nl_) lat[q] = 0;
+      ok = key != hcurr;
     }
     emit = ok;
   }
