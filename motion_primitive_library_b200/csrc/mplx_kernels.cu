@@ -491,56 +491,98 @@ expand_seq_kernel(const __grid_constant__ EnvParams P, const mplx_waypoint *__re
 // potential / yaw sums accumulate in the reference's order, and up to three samples past a block
 // are computed for nothing (they are bounds-checked like any other).  No shared-memory staging,
 // no atomics; lanes whose primitive is invalid or short idle while the longest one finishes.
+// Phase C of the register kernel: the reference's loop `for (t = 0; t < T; t += dt)`
+// (env_map.h:99) in groups of UNR samples with group-level control flow only.  All UNR samples of
+// a group are evaluated unconditionally (a sample past T or outside the map just gets no load),
+// their voxel loads are issued back to back, and two decisions close the group:
+//   some valid sample blocks  -> the primitive's cost is inf (the reference returns at the first
+//                                such sample; later ones cannot change an inf);
+//   the group reached t >= T  -> the loop has ended, return the accumulated cost;
+// otherwise the terms of the group are added in sample order and the next group starts.
+// n_samples counts what the reference's loop visits (up to and including the first blocking
+// sample) and is only maintained when the stats counters are on.
 template <int DIM, int ORD, bool YAW, int UNR>
 __device__ __forceinline__ double traverse_regs3(const EnvParams &P, const double (&cf)[CoefLayout<DIM, ORD, YAW>::NCMAX],
-                                                bool need_vel, double dt, unsigned &n_samples) {
+                                                 bool need_vel, double dt, unsigned &n_samples) {
   using CL = CoefLayout<DIM, ORD, YAW>;
   const double T = P.T;
   const int NC = CL::ncoef(need_vel);
+  const bool plain = P.pot == nullptr && P.region_bits == nullptr && !YAW;
   double c = 0;
   double t = 0;
-  while (t < T) {
+  for (;;) {
     double ts[UNR];
     int idx[UNR];
-    VoxelRaw3 raw[UNR];
+    bool valid[UNR];
 #pragma unroll
     for (int j = 0; j < UNR; j++) {
       ts[j] = t;
-      idx[j] = -2;
-      if (t < T) {
-        double pk[DIM];
-        eval_pos<DIM, ORD>(cf, t, pk);
-        idx[j] = sample_index<DIM>(P, pk);
-      }
-      t += dt;  // the reference's running sum; harmless past T
+      valid[j] = t < T;
+      double pk[DIM];
+      eval_pos<DIM, ORD>(cf, t, pk);
+      idx[j] = sample_index<DIM>(P, pk);  // -1 when outside the map
+      t += dt;                            // the reference's running sum
     }
+    bool blocked[UNR];
+    double term[UNR];
+    if (plain) {
+      // occupancy planning: the only question per sample is the voxel bit
+      unsigned word[UNR];
 #pragma unroll
-    for (int j = 0; j < UNR; j++) {
-      raw[j].region_word = 0xffffffffu;
-      raw[j].occ_word = 0;
-      raw[j].pot = 0;
-      if (idx[j] >= 0) raw[j] = voxel_fetch3(P, idx[j]);
-    }
+      for (int j = 0; j < UNR; j++) {
+        word[j] = 0;
+        if (valid[j] && idx[j] >= 0) word[j] = __ldg(P.occ_bits + (idx[j] >> 5));
+      }
 #pragma unroll
-    for (int j = 0; j < UNR; j++) {
-      if (idx[j] == -2) return c;  // t_j >= T: the loop has ended
-      n_samples++;
-      if (idx[j] < 0) return INFINITY;
-      double vel[DIM];
-      double gterm = 0.0;
-      if (need_vel) {
-        eval_vel<DIM, ORD>(cf + CL::NCP, ts[j], vel);
-        gterm = grad_term<DIM>(P, vel);
+      for (int j = 0; j < UNR; j++) {
+        blocked[j] = idx[j] < 0 || ((word[j] >> (idx[j] & 31)) & 1u);
+        term[j] = 0.0;
       }
-      double term = 0.0;
-      if (voxel_classify3(P, raw[j], idx[j], dt, gterm, term)) return INFINITY;
-      c += term;
-      if (YAW) {
-        if (P.wyaw > 0) c += yaw_term(P, vel[0], vel[1], normalize_angle(cf[NC - 2] * ts[j] + cf[NC - 1]), dt);
+    } else {
+      VoxelRaw raw[UNR];
+#pragma unroll
+      for (int j = 0; j < UNR; j++) {
+        raw[j] = kVoxelNone;
+        if (valid[j] && idx[j] >= 0) raw[j] = voxel_fetch(P, idx[j]);
+      }
+#pragma unroll
+      for (int j = 0; j < UNR; j++) {
+        term[j] = 0.0;
+        blocked[j] = idx[j] < 0;
+        if (valid[j] && !blocked[j]) {
+          double vel[DIM];
+          double gterm = 0.0;
+          if (need_vel) {
+            eval_vel<DIM, ORD>(cf + CL::NCP, ts[j], vel);
+            gterm = grad_term<DIM>(P, vel);
+          }
+          blocked[j] = voxel_classify(P, raw[j], dt, gterm, term[j]);
+          if (YAW) {
+            if (!blocked[j] && P.wyaw > 0)
+              term[j] += yaw_term(P, vel[0], vel[1], normalize_angle(cf[NC - 2] * ts[j] + cf[NC - 1]), dt);
+          }
+        }
       }
     }
+    bool any_blocked = false;
+#pragma unroll
+    for (int j = 0; j < UNR; j++) any_blocked = any_blocked || (valid[j] && blocked[j]);
+    if (P.stats) {
+      bool open = true;  // still before the first blocking sample
+#pragma unroll
+      for (int j = 0; j < UNR; j++) {
+        if (open && valid[j]) n_samples++;
+        open = open && !(valid[j] && blocked[j]);
+      }
+    }
+    if (any_blocked) return INFINITY;
+    if (!plain) {
+#pragma unroll
+      for (int j = 0; j < UNR; j++)
+        if (valid[j]) c += term[j];
+    }
+    if (!valid[UNR - 1]) return c;  // this group contained the end of the loop
   }
-  return c;
 }
 
 template <int DIM, int ORD, bool YAW, bool VEL, int UNR>
@@ -1098,11 +1140,21 @@ static cudaError_t launch_t(const EnvParams &P, const mplx_waypoint *d_nodes, in
     return nv ? launch_unit<DIM, ORD, YAW, true>(P, d_nodes, n_nodes, npb, grid, o, st)
               : launch_unit<DIM, ORD, YAW, YAW>(P, d_nodes, n_nodes, npb, grid, o, st);
   }
-  if (force_seq == 0 || force_seq == 2) {  // register kernel without the sort
-    if (nv)
-      expand_reg_kernel<DIM, ORD, YAW, true, 4, 4><<<grid, kThreads, 0, st>>>(P, d_nodes, n_nodes, npb, o);
-    else
-      expand_reg_kernel<DIM, ORD, YAW, YAW, 4, 4><<<grid, kThreads, 0, st>>>(P, d_nodes, n_nodes, npb, o);
+  if (force_seq == 0 || force_seq == 2) {  // register kernel (default)
+    // samples in flight per lane: 4, or 2 when every primitive of the plan has a short loop
+    // (n <= 15: a group of 4 would mostly run past the end of the loop)
+    const bool short_loops = P.maxn <= 15;
+    if (nv) {
+      if (short_loops)
+        expand_reg_kernel<DIM, ORD, YAW, true, 2, 4><<<grid, kThreads, 0, st>>>(P, d_nodes, n_nodes, npb, o);
+      else
+        expand_reg_kernel<DIM, ORD, YAW, true, 4, 4><<<grid, kThreads, 0, st>>>(P, d_nodes, n_nodes, npb, o);
+    } else {
+      if (short_loops)
+        expand_reg_kernel<DIM, ORD, YAW, YAW, 2, 4><<<grid, kThreads, 0, st>>>(P, d_nodes, n_nodes, npb, o);
+      else
+        expand_reg_kernel<DIM, ORD, YAW, YAW, 4, 4><<<grid, kThreads, 0, st>>>(P, d_nodes, n_nodes, npb, o);
+    }
     return cudaGetLastError();
   }
   if (force_seq == 5) {  // register kernel with the CTA-level sort by sample count

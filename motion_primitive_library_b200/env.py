@@ -96,6 +96,9 @@ class env_map:
 
     # -- lifecycle ------------------------------------------------------------------------
     def close(self):
+        for p in getattr(self, "_pins", []):
+            self._lib.mplx_host_free(p)  # numpy views handed out by _pinned_empty die with the env
+        self._pins = []
         if getattr(self, "_h", None) is not None and self._h:
             self._lib.mplx_destroy(self._h)
             self._h = None
