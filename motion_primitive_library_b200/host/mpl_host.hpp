@@ -203,9 +203,16 @@ class env_base {
   /// env_base.h:358-362
   virtual void get_succ(const Waypoint<Dim> &curr, vec_E<Waypoint<Dim>> &succ, std::vector<decimal_t> &succ_cost,
                         std::vector<int> &action_idx) const = 0;
-  /// Extension: candidates the search is likely to expand next (results are pure, so a batching
-  /// env may expand them together with the next get_succ call; default: ignore).
-  virtual void prefetch(const vec_E<Waypoint<Dim>> &) const {}
+  /// Extensions for batching envs (results of get_succ are pure, so none of this can change what
+  /// the search expands):
+  ///  - wants_candidates(key): true when the env would have to launch for this node and could take
+  ///    more nodes in the same launch;
+  ///  - prefetch(cands, keys): the open nodes the search is likely to pop next;
+  ///  - last_succ_keys(): lattice keys of the successors returned by the last get_succ call, if the
+  ///    env already has them (the device computes them); nullptr = hash on the host.
+  virtual bool wants_candidates(std::size_t) const { return false; }
+  virtual void prefetch(const vec_E<Waypoint<Dim>> &, const std::vector<std::size_t> &) const {}
+  virtual const std::size_t *last_succ_keys() const { return nullptr; }
   virtual void begin_plan() const {}
 
   bool heur_ignore_dynamics_{true};
@@ -279,27 +286,31 @@ class env_map_gpu : public env_map_host<Dim> {
     const std::size_t key = hash_value(curr);
     auto it = cache_.find(key);
     if (it == cache_.end()) {
-      vec_E<Waypoint<Dim>> batch{curr};
-      for (const auto &c : pending_) {
-        if ((int)batch.size() >= speculate_) break;
-        const std::size_t k = hash_value(c);
-        if (k != key && !cache_.count(k)) batch.push_back(c);
+      batch_.clear(); batch_keys_.clear();
+      batch_.push_back(curr); batch_keys_.push_back(key);
+      for (std::size_t c = 0; c < pending_.size() && (int)batch_.size() < speculate_; c++) {
+        const std::size_t k = pending_keys_[c];
+        if (k != key && !cache_.count(k)) { batch_.push_back(pending_[c]); batch_keys_.push_back(k); }
       }
-      pending_.clear();
-      expand_batch(batch);
+      pending_.clear(); pending_keys_.clear();
+      expand_batch();
       it = cache_.find(key);
     } else {
       stats_hits_++;
     }
-    const Entry &e = it->second;
-    for (std::size_t j = 0; j < e.cost.size(); j++) {
-      succ.push_back(from_pod(e.succ[j], curr.control));
-      succ_cost.push_back(e.cost[j]);
-      action_idx.push_back(e.action[j]);
-    }
+    Entry &e = it->second;
+    for (std::size_t j = 0; j < e.cost.size(); j++) succ.push_back(from_pod(e.succ[j], curr.control));
+    succ_cost.assign(e.cost.begin(), e.cost.end());
+    action_idx.assign(e.action.begin(), e.action.end());
+    last_keys_.swap(e.key);
     cache_.erase(it);  // A* expands a node once
   }
-  void prefetch(const vec_E<Waypoint<Dim>> &cands) const override { pending_ = cands; }
+  bool wants_candidates(std::size_t key) const override { return speculate_ > 1 && !cache_.count(key); }
+  void prefetch(const vec_E<Waypoint<Dim>> &cands, const std::vector<std::size_t> &keys) const override {
+    pending_ = cands;
+    pending_keys_ = keys;
+  }
+  const std::size_t *last_succ_keys() const override { return last_keys_.data(); }
 
   /// Packed batched expansion for lock-step drivers (mplx_expand_packed, +inf successors dropped
   /// on the device: A* skips them, graph_search.h:81).  Results stay in the env's buffers until the
@@ -351,7 +362,7 @@ class env_map_gpu : public env_map_host<Dim> {
   long launches() const { return (long)mplx_launch_count(ctx_); }
 
  private:
-  struct Entry { std::vector<mplx_waypoint> succ; std::vector<double> cost; std::vector<int> action; };
+  struct Entry { std::vector<mplx_waypoint> succ; std::vector<double> cost; std::vector<int> action; std::vector<std::size_t> key; };
   static void check(int rc) { if (rc != MPLX_OK) throw std::runtime_error(mplx_last_error()); }
   static mplx_waypoint to_pod(const Waypoint<Dim> &w) {
     mplx_waypoint p{};
@@ -390,21 +401,22 @@ class env_map_gpu : public env_map_host<Dim> {
       sent_version_ = this->params_version_;
     }
   }
-  void expand_batch(const vec_E<Waypoint<Dim>> &batch) const {
+  void expand_batch() const {
     sync();
-    const int n = (int)batch.size(), nU = (int)this->U_.size();
+    const int n = (int)batch_.size(), nU = (int)this->U_.size();
     in_.resize(n);
-    for (int i = 0; i < n; i++) in_[i] = to_pod(batch[i]);
-    count_.resize(n); succ_.resize((std::size_t)n * nU); cost_.resize((std::size_t)n * nU); action_.resize((std::size_t)n * nU);
-    mplx_succ_out out{count_.data(), succ_.data(), cost_.data(), action_.data(), nullptr, nullptr};
+    for (int i = 0; i < n; i++) in_[i] = to_pod(batch_[i]);
+    const std::size_t slots = (std::size_t)n * nU;
+    count_.resize(n); succ_.resize(slots); cost_.resize(slots); action_.resize(slots); key_.resize(slots);
+    mplx_succ_out out{count_.data(), succ_.data(), cost_.data(), action_.data(), key_.data(), nullptr};
     check(mplx_expand(ctx_, in_.data(), n, &out));
     for (int i = 0; i < n; i++) {
-      Entry e;
+      Entry &e = cache_[batch_keys_[i]];
       const std::size_t o = (std::size_t)i * nU;
       e.succ.assign(succ_.begin() + o, succ_.begin() + o + count_[i]);
       e.cost.assign(cost_.begin() + o, cost_.begin() + o + count_[i]);
       e.action.assign(action_.begin() + o, action_.begin() + o + count_[i]);
-      cache_[hash_value(batch[i])] = std::move(e);
+      e.key.assign(key_.begin() + o, key_.begin() + o + count_[i]);
     }
     stats_nodes_ += n;
     stats_calls_++;
@@ -416,7 +428,9 @@ class env_map_gpu : public env_map_host<Dim> {
   decimal_t potential_weight_{0.1}, gradient_weight_{0.0};
   mutable unsigned long map_version_ = ~0ul, sent_version_ = 0;
   mutable std::unordered_map<std::size_t, Entry> cache_;
-  mutable vec_E<Waypoint<Dim>> pending_;
+  mutable vec_E<Waypoint<Dim>> pending_, batch_;
+  mutable std::vector<std::size_t> pending_keys_, batch_keys_, last_keys_;
+  mutable std::vector<uint64_t> key_;
   mutable std::vector<mplx_waypoint> in_, succ_;
   mutable std::vector<int32_t> count_, action_;
   mutable std::vector<double> cost_;
@@ -664,18 +678,25 @@ class GraphSearch {
     std::vector<decimal_t> succ_cost;
     std::vector<int> succ_act_id;
     vec_E<Waypoint<Dim>> cands;
+    std::vector<std::size_t> cand_keys;
     while (st.active()) {
-      if (lookahead_ > 0) {
+      const auto &raw = st.open_heap();
+      if (lookahead_ > 0 && !raw.empty() && ENV->wants_candidates(raw[0]->key)) {
         // hint: the open nodes nearest the root of the heap are the likeliest next pops
         cands.clear();
-        const auto &raw = st.open_heap();
-        for (std::size_t i = 1; i < raw.size() && (int)cands.size() < lookahead_; i++) cands.push_back(raw[i]->coord);
-        ENV->prefetch(cands);
+        cand_keys.clear();
+        for (std::size_t i = 1; i < raw.size() && (int)cands.size() < lookahead_; i++) {
+          cands.push_back(raw[i]->coord);
+          cand_keys.push_back(raw[i]->key);
+        }
+        ENV->prefetch(cands, cand_keys);
       }
       const Waypoint<Dim> &curr = st.pop();
       ENV->get_succ(curr, succ_coord, succ_cost, succ_act_id);
+      const std::size_t *keys = ENV->last_succ_keys();
       st.consume((int)succ_coord.size(), [&](int s) -> const Waypoint<Dim> & { return succ_coord[s]; },
-                 succ_cost.data(), succ_act_id.data(), [&](int s) { return hash_value(succ_coord[s]); });
+                 succ_cost.data(), succ_act_id.data(),
+                 [&](int s) { return keys ? keys[s] : hash_value(succ_coord[s]); });
     }
     if (verbose_ && std::isinf(st.finish(traj))) printf("[GraphSearch] no trajectory (max expansions or empty queue)\n");
     return st.finish(traj);
