@@ -3,50 +3,7 @@
 #pragma once
 #include "mpl_host.hpp"
 
-extern "C" {
-typedef struct {
-  int32_t dim, control;
-  const int8_t *map;
-  int32_t mdim[3];
-  double origin[3];
-  double res;
-  const double *U;
-  int32_t nU, udim;
-  double T, w, wyaw, eps;
-  double v_max, a_max, j_max, yaw_max;
-  double tol_pos, tol_vel, tol_acc;
-  mplx_waypoint start, goal;
-  int32_t max_num;     /* PlannerBase::setMaxNum */
-  int32_t speculate;   /* nodes expanded per launch (GPU env); 1 = no speculation */
-  int32_t device;
-  const int8_t *potential; /* optional */
-  double potential_weight, gradient_weight;
-} mplh_plan_args;
-
-typedef struct {
-  int32_t valid;          /* plan() return value */
-  double cost;            /* getTrajCost() */
-  int32_t expanded;       /* expand iterations (get_succ calls made by A*) */
-  int32_t n_closed;       /* closed states */
-  int32_t n_open;
-  int32_t n_actions;      /* edges of the recovered trajectory */
-  int64_t gpu_nodes;      /* nodes sent to the device (>= expanded when speculating) */
-  int64_t gpu_calls;      /* mplx_expand calls */
-  int64_t gpu_launches;
-  double seconds;         /* wall time of plan() */
-} mplh_plan_result;
-}
-
-extern "C" {
-/* Batched queries (config 5): shares every field of mplh_plan_args except start/goal. */
-typedef struct {
-  int32_t valid;
-  double cost;
-  int32_t expanded;
-  int32_t n_closed;
-  int32_t n_actions;
-} mplh_query_result;
-}
+#include "plan_capi_types.h"
 
 namespace mplh {
 template <int Dim>

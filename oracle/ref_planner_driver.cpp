@@ -1,0 +1,161 @@
+// ref_planner_driver.cpp — the UNMODIFIED reference planner (include/mpl_planner/planner/map_planner.h,
+// src/mpl_planner/map_planner.cpp, graph_search.h, state_space.h, planner_base.h) compiled where it
+// lies, behind the same flat C interface as the product's host planner (host/plan_capi.hpp), plus
+// MapPlanner::updatePotentialMap / setSearchRegion for pinning the generators.  TEST INFRASTRUCTURE.
+#include <mpl_planner/planner/map_planner.h>
+
+#include <algorithm>
+#include <chrono>
+
+#include "../motion_primitive_library_b200/host/plan_capi_types.h"
+
+namespace {
+template <int Dim>
+std::shared_ptr<MPL::MapUtil<Dim>> make_map(const mplh_plan_args *a) {
+  std::shared_ptr<MPL::MapUtil<Dim>> mu(new MPL::MapUtil<Dim>);
+  Vecf<Dim> ori;
+  Veci<Dim> dim;
+  size_t n = 1;
+  for (int k = 0; k < Dim; k++) {
+    ori(k) = a->origin[k];
+    dim(k) = a->mdim[k];
+    n *= (size_t)a->mdim[k];
+  }
+  mu->setMap(ori, dim, MPL::Tmap(a->map, a->map + n), a->res);
+  return mu;
+}
+template <int Dim>
+Waypoint<Dim> wp_from(const mplx_waypoint &p, int control) {
+  Waypoint<Dim> w((Control::Control)control);
+  for (int d = 0; d < Dim; d++) {
+    w.pos(d) = p.pos[d];
+    w.vel(d) = p.vel[d];
+    w.acc(d) = p.acc[d];
+    w.jrk(d) = p.jrk[d];
+  }
+  w.yaw = p.yaw;
+  w.t = p.t;
+  return w;
+}
+
+// exposes the protected state space of PlannerBase for the closed-set export
+template <int Dim>
+struct Planner : MPL::MapPlanner<Dim> {
+  explicit Planner(bool v) : MPL::MapPlanner<Dim>(v) {}
+  using MPL::MapPlanner<Dim>::ss_ptr_;
+  using MPL::MapPlanner<Dim>::ENV_;
+};
+
+template <int Dim>
+int plan(const mplh_plan_args *a, mplh_plan_result *r, uint64_t *closed_keys, int cap_closed, int32_t *actions,
+         int cap_actions) {
+  Planner<Dim> planner(false);
+  planner.setMapUtil(make_map<Dim>(a));
+  vec_E<VecDf> U;
+  for (int i = 0; i < a->nU; i++) {
+    VecDf u(a->udim);
+    for (int k = 0; k < a->udim; k++) u(k) = a->U[(size_t)i * a->udim + k];
+    U.push_back(u);
+  }
+  planner.setU(U);
+  planner.setVmax(a->v_max);
+  planner.setAmax(a->a_max);
+  planner.setJmax(a->j_max);
+  planner.setYawmax(a->yaw_max);
+  planner.setDt(a->T);
+  planner.setW(a->w);
+  planner.setWyaw(a->wyaw);
+  planner.setEpsilon(a->eps);
+  planner.setTol(a->tol_pos, a->tol_vel, a->tol_acc);
+  planner.setMaxNum(a->max_num);
+  const Waypoint<Dim> start = wp_from<Dim>(a->start, a->control), goal = wp_from<Dim>(a->goal, a->control);
+  auto t0 = std::chrono::steady_clock::now();
+  r->valid = planner.plan(start, goal) ? 1 : 0;
+  r->seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+  r->cost = planner.getTrajCost();
+  r->expanded = planner.initialized() ? planner.getExpandedNum() : 0;
+  std::vector<uint64_t> keys;
+  int n_open = 0;
+  if (planner.initialized()) {
+    for (const auto &it : planner.ss_ptr_->hm_) {
+      if (!it.second) continue;
+      if (it.second->iterationclosed) keys.push_back((uint64_t)hash_value(it.second->coord));
+      else if (it.second->iterationopened) n_open++;
+    }
+  }
+  std::sort(keys.begin(), keys.end());
+  r->n_closed = (int)keys.size();
+  r->n_open = n_open;
+  for (int i = 0; i < (int)keys.size() && i < cap_closed; i++) closed_keys[i] = keys[i];
+  // action ids of the recovered trajectory: match each primitive's control against U
+  const auto prs = planner.getTraj().getPrimitives();
+  r->n_actions = (int)prs.size();
+  const int order = __builtin_popcount(a->control & 15);  // coefficient index of the control: 5 - order
+  for (int i = 0; i < (int)prs.size() && i < cap_actions; i++) {
+    int found = -1;
+    for (int u = 0; u < a->nU && found < 0; u++) {
+      bool same = true;
+      for (int d = 0; d < Dim; d++) same = same && prs[i].pr(d).coeff()(5 - order) == a->U[(size_t)u * a->udim + d];
+      if (same && (a->control & 16)) same = prs[i].pr_yaw().coeff()(4) == a->U[(size_t)u * a->udim + Dim];
+      if (same) found = u;
+    }
+    actions[i] = found;
+  }
+  return 0;
+}
+
+template <int Dim>
+int potential(const mplh_plan_args *a, const double *radius, const double *range, const double *pos, int8_t *out) {
+  Planner<Dim> planner(false);
+  auto mu = make_map<Dim>(a);
+  planner.setMapUtil(mu);
+  Vecf<Dim> rad, rng, p;
+  for (int k = 0; k < Dim; k++) {
+    rad(k) = radius[k];
+    rng(k) = range ? range[k] : 0;
+    p(k) = pos ? pos[k] : 0;
+  }
+  planner.setPotentialRadius(rad);
+  planner.setPotentialMapRange(rng);
+  planner.updatePotentialMap(p);
+  const MPL::Tmap m = mu->getMap();
+  std::copy(m.begin(), m.end(), out);
+  return 0;
+}
+
+template <int Dim>
+int region(const mplh_plan_args *a, const double *path, int n_path, const double *radius, int dense, uint8_t *out) {
+  Planner<Dim> planner(false);
+  planner.setMapUtil(make_map<Dim>(a));
+  Vecf<Dim> rad;
+  for (int k = 0; k < Dim; k++) rad(k) = radius[k];
+  planner.setSearchRadius(rad);
+  vec_Vecf<Dim> pts;
+  for (int i = 0; i < n_path; i++) {
+    Vecf<Dim> p;
+    for (int k = 0; k < Dim; k++) p(k) = path[(size_t)i * Dim + k];
+    pts.push_back(p);
+  }
+  planner.setSearchRegion(pts, dense != 0);
+  const std::vector<bool> reg = planner.ENV_->get_search_region();
+  for (size_t i = 0; i < reg.size(); i++) out[i] = reg[i] ? 1 : 0;
+  return 0;
+}
+}  // namespace
+
+extern "C" {
+int refp_plan(const mplh_plan_args *a, mplh_plan_result *r, uint64_t *closed_keys, int cap_closed, int32_t *actions,
+              int cap_actions) {
+  *r = mplh_plan_result{};
+  return a->dim == 2 ? plan<2>(a, r, closed_keys, cap_closed, actions, cap_actions)
+                     : plan<3>(a, r, closed_keys, cap_closed, actions, cap_actions);
+}
+int refp_update_potential_map(const mplh_plan_args *a, const double *radius, const double *range, const double *pos,
+                              int8_t *out) {
+  return a->dim == 2 ? potential<2>(a, radius, range, pos, out) : potential<3>(a, radius, range, pos, out);
+}
+int refp_set_search_region(const mplh_plan_args *a, const double *path, int n_path, const double *radius, int dense,
+                           uint8_t *out) {
+  return a->dim == 2 ? region<2>(a, path, n_path, radius, dense, out) : region<3>(a, path, n_path, radius, dense, out);
+}
+}

@@ -7,8 +7,12 @@
 #include <cstddef>
 #include <cstdint>
 namespace boost {
+// boost::hash<T> for a user type calls hash_value(v) found by argument-dependent lookup
+// (waypoint.h:93 defines hash_value(Waypoint<Dim>)).
 template <typename T>
-struct hash;
+struct hash {
+  std::size_t operator()(const T &v) const { return hash_value(v); }
+};
 template <>
 struct hash<int> {
   std::size_t operator()(int v) const { return static_cast<std::size_t>(v); }

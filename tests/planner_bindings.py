@@ -19,3 +19,49 @@ def plan_oracle(args):
         subprocess.check_call(["make", "-C", str(ROOT / "oracle"), "liboracle_planner.so"], stdout=subprocess.DEVNULL)
     lib, fn = load_fn(p, "orcp_plan")
     return run_plan(fn, lib, args)
+
+
+REF_PLANNER = ROOT / "oracle" / "_ref" / "libmplref_planner.so"
+
+
+def ref_planner_available():
+    return REF_PLANNER.exists()
+
+
+def plan_reference(args):
+    """The REFERENCE's MapPlanner<Dim>::plan() (unmodified sources + Eigen/Boost stand-ins)."""
+    lib, fn = load_fn(REF_PLANNER, "refp_plan")
+    return run_plan(fn, lib, args)
+
+
+def reference_potential_map(args, radius, n_cells, range_=None, pos=None):
+    """MapPlanner::updatePotentialMap (src/mpl_planner/map_planner.cpp:323-391) on args' map."""
+    import ctypes as C
+
+    import numpy as np
+
+    lib = C.CDLL(str(REF_PLANNER))
+    out = np.zeros(n_cells, dtype=np.int8)
+    rad = np.asarray(radius, dtype=np.float64)
+    rng = None if range_ is None else np.asarray(range_, dtype=np.float64)
+    p = None if pos is None else np.asarray(pos, dtype=np.float64)
+    lib.refp_update_potential_map.argtypes = [C.POINTER(PlanArgs), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.refp_update_potential_map(C.byref(args), rad.ctypes.data, None if rng is None else rng.ctypes.data,
+                                  None if p is None else p.ctypes.data, out.ctypes.data)
+    return out
+
+
+def reference_search_region(args, path, radius, n_cells, dense=False):
+    """MapPlanner::setSearchRegion (src/mpl_planner/map_planner.cpp:46-95)."""
+    import ctypes as C
+
+    import numpy as np
+
+    lib = C.CDLL(str(REF_PLANNER))
+    out = np.zeros(n_cells, dtype=np.uint8)
+    path = np.ascontiguousarray(path, dtype=np.float64)
+    rad = np.asarray(radius, dtype=np.float64)
+    lib.refp_set_search_region.argtypes = [C.POINTER(PlanArgs), C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p]
+    lib.refp_set_search_region(C.byref(args), path.ctypes.data, len(path), rad.ctypes.data, 1 if dense else 0,
+                               out.ctypes.data)
+    return out

@@ -14,6 +14,12 @@ ACC, JRK, ACCxYAW = 0x03, 0x07, 0x13
 
 def check_same(args_factory, speculations=(1, 16)):
     ref = pb.plan_oracle(args_factory(1))
+    if pb.ref_planner_available():
+        # ... and the REFERENCE's own MapPlanner::plan() (oracle/_ref, unmodified sources) agrees with both
+        r0 = pb.plan_reference(args_factory(1))
+        assert r0["valid"] == ref["valid"] and r0["n_closed"] == ref["n_closed"]
+        np.testing.assert_array_equal(r0["closed"], ref["closed"])
+        np.testing.assert_array_equal(r0["actions"], ref["actions"])
     for k in speculations:
         g = pb.plan_gpu(args_factory(k))
         assert g["valid"] == ref["valid"]
