@@ -103,6 +103,23 @@ int mplx_set_potential(mplx_ctx *ctx, const int8_t *data, double potential_weigh
  * One byte per voxel, non-zero = inside the tunnel; NULL restores search_region_.empty(). */
 int mplx_set_search_region(mplx_ctx *ctx, const uint8_t *in_region);
 
+/* MapPlanner<Dim>::updatePotentialMap(pos) with createMask (src/mpl_planner/map_planner.cpp:286-391),
+ * on the device grid: builds the potential field around every cell with map > 0 (inside the optional
+ * source range: `range` = potential_map_range_, `pos` its centre; NULL or all-zero range = whole
+ * map), radius = potential_radius_ (metres; radius[0] is used for x and y as in the reference,
+ * radius[2] for z), pow = pow_ (map_planner.h:113).  Like the reference it then OVERWRITES the grid
+ * with the result (map_util_->setMap(dmap), :387) and installs it as the potential map (:388) with
+ * the given weights.  out_map (host, one int8 per voxel) receives the new grid, or NULL. */
+int mplx_update_potential_map(mplx_ctx *ctx, const double *radius, double pow, const double *range,
+                              const double *pos, double potential_weight, double gradient_weight,
+                              int8_t *out_map);
+
+/* MapPlanner<Dim>::setSearchRegion(path, dense) (src/mpl_planner/map_planner.cpp:46-95): the tunnel
+ * of half-width ceil(radius/res) cells around the ray-traced path (n_pts points of ctx-dim doubles)
+ * becomes the search region.  out_region (host, one byte per voxel) receives it, or NULL. */
+int mplx_set_search_region_path(mplx_ctx *ctx, const double *path, int n_pts, const double *radius,
+                                int dense, uint8_t *out_region);
+
 /* env_base::set_u / set_dt / set_w / set_wyaw / set_v_max / set_a_max / set_j_max /
  * set_yaw_max (env_base.h:234-287) and the Waypoint control flag.  U is nU x udim row-major,
  * udim = dim (+1 when the control carries a yaw rate, primitive.h:235-248). */

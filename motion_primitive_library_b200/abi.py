@@ -34,6 +34,8 @@ EXPORTED_SYMBOLS = (
     "mplx_set_map",
     "mplx_set_potential",
     "mplx_set_search_region",
+    "mplx_update_potential_map",
+    "mplx_set_search_region_path",
     "mplx_set_params",
     "mplx_expand",
     "mplx_expand_device",
@@ -117,6 +119,10 @@ def load() -> C.CDLL:
     lib.mplx_set_potential.restype = i32
     lib.mplx_set_search_region.argtypes = [vp, vp]
     lib.mplx_set_search_region.restype = i32
+    lib.mplx_update_potential_map.argtypes = [vp, vp, f64, vp, vp, f64, f64, vp]
+    lib.mplx_update_potential_map.restype = i32
+    lib.mplx_set_search_region_path.argtypes = [vp, vp, i32, vp, i32, vp]
+    lib.mplx_set_search_region_path.restype = i32
     lib.mplx_set_params.argtypes = [vp, i32, f64, f64, f64, f64, f64, f64, f64, vp, i32, i32]
     lib.mplx_set_params.restype = i32
     lib.mplx_expand.argtypes = [vp, vp, i32, C.POINTER(SuccOut)]

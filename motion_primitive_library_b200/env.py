@@ -189,6 +189,29 @@ class env_map:
             raise ValueError("search region size does not match the grid")
         abi.check(self._lib.mplx_set_search_region(self._h, r.ctypes.data))
 
+    def update_potential_map(self, radius, pow_=1.0, range_=None, pos=None):
+        """MapPlanner::updatePotentialMap on the device (mplx_update_potential_map).  As in the
+        reference (map_planner.cpp:387-388) the MapUtil grid is replaced by the potential field,
+        which also becomes the env's potential map.  Returns the new grid."""
+        rad = np.ascontiguousarray(radius, dtype=np.float64)
+        rng = None if range_ is None else np.ascontiguousarray(range_, dtype=np.float64)
+        p = None if pos is None else np.ascontiguousarray(pos, dtype=np.float64)
+        out = np.empty(self.map_util_.map.size, dtype=np.int8)
+        abi.check(self._lib.mplx_update_potential_map(self._h, rad.ctypes.data, float(pow_), abi.ptr(rng), abi.ptr(p),
+                                                      self.potential_weight_, self.gradient_weight_, out.ctypes.data))
+        self.map_util_.map = out
+        self._potential = out
+        return out
+
+    def set_search_region_path(self, path, radius, dense=False):
+        """MapPlanner::setSearchRegion on the device (mplx_set_search_region_path); returns the region bytes."""
+        path = np.ascontiguousarray(path, dtype=np.float64).reshape(-1, self.Dim)
+        rad = np.ascontiguousarray(radius, dtype=np.float64)
+        out = np.empty(self.map_util_.map.size, dtype=np.uint8)
+        abi.check(self._lib.mplx_set_search_region_path(self._h, path.ctypes.data, len(path), rad.ctypes.data,
+                                                        1 if dense else 0, out.ctypes.data))
+        return out
+
     def _sync_params(self):
         if not self._dirty:
             return

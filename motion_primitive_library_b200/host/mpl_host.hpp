@@ -197,7 +197,7 @@ class env_base {
   virtual void set_potential_weight(decimal_t) {}
   virtual void set_gradient_weight(decimal_t) {}
   virtual void set_potential_map(const std::vector<int8_t> &) {}
-  void set_search_region(const std::vector<bool> &r) { search_region_ = r; touch(); }
+  virtual void set_search_region(const std::vector<bool> &r) { search_region_ = r; touch(); }
   decimal_t get_dt() const { return dt_; }
   virtual bool is_free(const Vecf<Dim> &) const { return true; }
   /// env_base.h:358-362
@@ -269,7 +269,8 @@ class env_map_gpu : public env_map_host<Dim> {
   ~env_map_gpu() override { mplx_destroy(ctx_); }
   env_map_gpu(const env_map_gpu &) = delete;
 
-  void set_potential_map(const std::vector<int8_t> &map) override { potential_map_ = map; this->touch(); }
+  void set_potential_map(const std::vector<int8_t> &map) override { potential_map_ = map; potential_on_device_ = false; this->touch(); }
+  void set_search_region(const std::vector<bool> &r) override { region_on_device_ = false; env_base<Dim>::set_search_region(r); }
   void set_potential_weight(decimal_t w) override { potential_weight_ = w; this->touch(); }
   void set_gradient_weight(decimal_t w) override { gradient_weight_ = w; this->touch(); }
   void set_control(int control) { control_ = control; this->touch(); }
@@ -311,6 +312,29 @@ class env_map_gpu : public env_map_host<Dim> {
     pending_keys_ = keys;
   }
   const std::size_t *last_succ_keys() const override { return last_keys_.data(); }
+
+  /// MapPlanner::updatePotentialMap on the device (mplx_update_potential_map): the MapUtil grid is
+  /// replaced by the potential field, which also becomes the potential map (map_planner.cpp:387-388).
+  void update_potential_map(const Vecf<Dim> &radius, decimal_t pow_, const Vecf<Dim> &range, const Vecf<Dim> &pos) {
+    sync();
+    Tmap out(map_util_->map().size());
+    check(mplx_update_potential_map(ctx_, radius.d, pow_, range.d, pos.d, potential_weight_, gradient_weight_,
+                                    (int8_t *)out.data()));
+    map_util_->setMap(map_util_->getOrigin(), map_util_->getDim(), out, map_util_->getRes());
+    map_version_ = map_util_->version();  // the device already holds this grid
+    potential_map_.assign(out.begin(), out.end());
+    potential_on_device_ = true;
+  }
+  /// MapPlanner::setSearchRegion on the device (mplx_set_search_region_path)
+  void set_search_region_path(const vec_E<Vecf<Dim>> &path, const Vecf<Dim> &radius, bool dense) {
+    sync();
+    std::vector<double> flat;
+    for (const auto &p : path) for (int k = 0; k < Dim; k++) flat.push_back(p(k));
+    std::vector<uint8_t> out(map_util_->map().size());
+    check(mplx_set_search_region_path(ctx_, flat.data(), (int)path.size(), radius.d, dense ? 1 : 0, out.data()));
+    this->search_region_.assign(out.begin(), out.end());
+    region_on_device_ = true;
+  }
 
   /// Packed batched expansion for lock-step drivers (mplx_expand_packed, +inf successors dropped
   /// on the device: A* skips them, graph_search.h:81).  Results stay in the env's buffers until the
@@ -391,12 +415,15 @@ class env_map_gpu : public env_map_host<Dim> {
       for (const auto &u : this->U_) for (int k = 0; k < udim; k++) U.push_back(u[k]);
       check(mplx_set_params(ctx_, control_, this->dt_, this->w_, this->wyaw_, this->v_max_, this->a_max_,
                             this->j_max_, this->yaw_max_, U.data(), (int)this->U_.size(), udim));
-      check(mplx_set_potential(ctx_, potential_map_.empty() ? nullptr : potential_map_.data(), potential_weight_,
-                               gradient_weight_));
-      if (this->search_region_.empty()) check(mplx_set_search_region(ctx_, nullptr));
-      else {
-        std::vector<uint8_t> r(this->search_region_.begin(), this->search_region_.end());
-        check(mplx_set_search_region(ctx_, r.data()));
+      if (!potential_on_device_)
+        check(mplx_set_potential(ctx_, potential_map_.empty() ? nullptr : potential_map_.data(), potential_weight_,
+                                 gradient_weight_));
+      if (!region_on_device_) {
+        if (this->search_region_.empty()) check(mplx_set_search_region(ctx_, nullptr));
+        else {
+          std::vector<uint8_t> r(this->search_region_.begin(), this->search_region_.end());
+          check(mplx_set_search_region(ctx_, r.data()));
+        }
       }
       sent_version_ = this->params_version_;
     }
@@ -424,6 +451,7 @@ class env_map_gpu : public env_map_host<Dim> {
 
   mplx_ctx *ctx_ = nullptr;
   int control_ = Control::NONE, speculate_ = 1;
+  bool potential_on_device_ = false, region_on_device_ = false;
   std::vector<int8_t> potential_map_;
   decimal_t potential_weight_{0.1}, gradient_weight_{0.0};
   mutable unsigned long map_version_ = ~0ul, sent_version_ = 0;
@@ -787,6 +815,20 @@ class MapPlanner : public PlannerBase<Dim> {
   void setEnv(const std::shared_ptr<env_base<Dim>> &env) { this->ENV_ = env; gpu_env_.reset(); }
   void setControl(int control) { if (gpu_env_) gpu_env_->set_control(control); }
   void setSpeculation(int k) { if (gpu_env_) gpu_env_->set_speculation(k); this->setLookahead(k > 1 ? 4 * k : 0); }
+  /// map_planner.cpp:20-43
+  void setPotentialRadius(const Vecf<Dim> &radius) { potential_radius_ = radius; }
+  void setPotentialMapRange(const Vecf<Dim> &range) { potential_map_range_ = range; }
+  void setSearchRadius(const Vecf<Dim> &radius) { search_radius_ = radius; }
+  /// map_planner.cpp:323-391, on the device
+  void updatePotentialMap(const Vecf<Dim> &pos) {
+    if (!gpu_env_) throw std::runtime_error("updatePotentialMap needs the GPU env (setMapUtil)");
+    gpu_env_->update_potential_map(potential_radius_, pow_, potential_map_range_, pos);
+  }
+  /// map_planner.cpp:46-95, on the device
+  void setSearchRegion(const vec_E<Vecf<Dim>> &path, bool dense = false) {
+    if (!gpu_env_) throw std::runtime_error("setSearchRegion needs the GPU env (setMapUtil)");
+    gpu_env_->set_search_region_path(path, search_radius_, dense);
+  }
   void setPotentialWeight(decimal_t w) { this->ENV_->set_potential_weight(w); }
   void setGradientWeight(decimal_t w) { this->ENV_->set_gradient_weight(w); }
   env_map_gpu<Dim> *gpu_env() { return gpu_env_.get(); }
@@ -794,6 +836,8 @@ class MapPlanner : public PlannerBase<Dim> {
  protected:
   std::shared_ptr<MapUtil<Dim>> map_util_;
   std::shared_ptr<env_map_gpu<Dim>> gpu_env_;
+  Vecf<Dim> potential_radius_, potential_map_range_, search_radius_;
+  decimal_t pow_{1.0};  // map_planner.h:113
 };
 typedef MapPlanner<2> OccMapPlanner;
 typedef MapPlanner<3> VoxelMapPlanner;
