@@ -15,7 +15,12 @@
 // of (node, env), so speculation cannot change which nodes A* expands or in which order.
 #pragma once
 #include <algorithm>
+#include <atomic>
 #include <chrono>
+#include <condition_variable>
+#include <functional>
+#include <mutex>
+#include <thread>
 #include <cmath>
 #include <cstdint>
 #include <cstdio>
@@ -842,6 +847,84 @@ class MapPlanner : public PlannerBase<Dim> {
 typedef MapPlanner<2> OccMapPlanner;
 typedef MapPlanner<3> VoxelMapPlanner;
 
+/// Minimal persistent worker pool for the host side of the lock-step driver: the per-query
+/// bookkeeping (hash map, heap) of different queries is independent, so it is spread over the host
+/// cores while the device expands the next batch's nodes.
+class WorkerPool {
+ public:
+  explicit WorkerPool(int n_threads) {
+    n_ = n_threads < 1 ? 1 : n_threads;
+    for (int t = 1; t < n_; t++) th_.emplace_back([this] { loop(); });
+  }
+  ~WorkerPool() {
+    {
+      std::lock_guard<std::mutex> lk(m_);
+      stop_ = true;
+      gen_++;
+    }
+    cv_.notify_all();
+    for (auto &t : th_) t.join();
+  }
+  int size() const { return n_; }
+  /// fn(i) for i in [0, count), dynamically chunked; returns when all are done
+  void run(std::size_t count, const std::function<void(std::size_t)> &fn) {
+    if (count == 0) return;
+    if (n_ == 1 || count < 64) {
+      for (std::size_t i = 0; i < count; i++) fn(i);
+      return;
+    }
+    {
+      std::lock_guard<std::mutex> lk(m_);
+      fn_ = &fn;
+      count_ = count;
+      next_.store(0);
+      pending_ = n_ - 1;
+      gen_++;
+    }
+    cv_.notify_all();
+    work();
+    std::unique_lock<std::mutex> lk(m_);
+    done_.wait(lk, [this] { return pending_ == 0; });
+  }
+
+ private:
+  void work() {
+    const std::size_t chunk = 16;
+    for (;;) {
+      const std::size_t b = next_.fetch_add(chunk);
+      if (b >= count_) break;
+      const std::size_t e = b + chunk < count_ ? b + chunk : count_;
+      for (std::size_t i = b; i < e; i++) (*fn_)(i);
+    }
+  }
+  void loop() {
+    unsigned long seen = 0;
+    for (;;) {
+      {
+        std::unique_lock<std::mutex> lk(m_);
+        cv_.wait(lk, [&] { return gen_ != seen; });
+        seen = gen_;
+        if (stop_) return;
+      }
+      work();
+      {
+        std::lock_guard<std::mutex> lk(m_);
+        if (--pending_ == 0) done_.notify_one();
+      }
+    }
+  }
+  int n_;
+  std::vector<std::thread> th_;
+  std::mutex m_;
+  std::condition_variable cv_, done_;
+  const std::function<void(std::size_t)> *fn_ = nullptr;
+  std::size_t count_ = 0;
+  std::atomic<std::size_t> next_{0};
+  int pending_ = 0;
+  unsigned long gen_ = 0;
+  bool stop_ = false;
+};
+
 /// Lock-step batched A* over many independent (start, goal) queries on one map — BASELINE.json
 /// config 5.  Every iteration pops the best open node of each live query (AstarStepper::pop) and
 /// expands all of them in ONE device launch (env_map_gpu::expand_packed); each query then relaxes
@@ -864,8 +947,12 @@ class MultiQueryPlanner {
   long iterations() const { return iterations_; }
   long nodes_expanded() const { return nodes_; }
 
+  /// host threads used for the per-query bookkeeping (default: all cores)
+  void setHostThreads(int n) { host_threads_ = n; }
+
   std::vector<Result> plan(const vec_E<Waypoint<Dim>> &starts, const vec_E<Waypoint<Dim>> &goals, decimal_t eps,
                            int max_expand) {
+    WorkerPool pool(host_threads_ > 0 ? host_threads_ : (int)std::thread::hardware_concurrency());
     // per-query host env: goal test + heuristic only (its get_succ is never called)
     struct QueryEnv : env_map_host<Dim> {
       using env_map_host<Dim>::env_map_host;
@@ -888,29 +975,27 @@ class MultiQueryPlanner {
     }
     std::vector<mplx_waypoint> batch;
     std::vector<std::size_t> who;
-    std::vector<int> act;
     iterations_ = nodes_ = 0;
     for (;;) {
-      batch.clear();
+      // pop phase: one node per live query (independent heaps -> parallel), then compact
       who.clear();
       for (std::size_t q = 0; q < Q; q++)
-        if (st[q]->active()) {
-          batch.push_back(env_map_gpu<Dim>::pod(st[q]->pop()));
-          who.push_back(q);
-        }
-      if (batch.empty()) break;
+        if (st[q]->active()) who.push_back(q);
+      if (who.empty()) break;
+      batch.resize(who.size());
+      pool.run(who.size(), [&](std::size_t b) { batch[b] = env_map_gpu<Dim>::pod(st[who[b]]->pop()); });
       gpu_->expand_packed(batch);
       iterations_++;
       nodes_ += (long)batch.size();
-      for (std::size_t b = 0; b < who.size(); b++) {
+      // relax phase: every query consumes its own successors (independent state spaces -> parallel)
+      pool.run(who.size(), [&](std::size_t b) {
         const std::size_t r0 = (std::size_t)gpu_->p_offset[b];
         const int cnt = gpu_->p_count[b];
-        act.resize(cnt);
+        int act[kMaxSucc];
         for (int j = 0; j < cnt; j++) act[j] = gpu_->p_action[r0 + j];
         st[who[b]]->consume(cnt, [&](int s) { return gpu_->packed_waypoint(r0 + s, batch[b]); },
-                            gpu_->p_cost.data() + r0, act.data(),
-                            [&](int s) { return (std::size_t)gpu_->p_key[r0 + s]; });
-      }
+                            gpu_->p_cost.data() + r0, act, [&](int s) { return (std::size_t)gpu_->p_key[r0 + s]; });
+      });
     }
     for (std::size_t q = 0; q < Q; q++) {
       std::vector<Edge<Dim>> traj;
@@ -927,5 +1012,7 @@ class MultiQueryPlanner {
   std::shared_ptr<MapUtil<Dim>> map_util_;
   std::unique_ptr<env_map_gpu<Dim>> gpu_;
   long iterations_ = 0, nodes_ = 0;
+  int host_threads_ = 0;
+  static constexpr int kMaxSucc = 1024;  // |U| upper bound of libmplx
 };
 }  // namespace MPL
