@@ -192,10 +192,18 @@ def cpu_reference(sc, nodes, threads, budget_s):
     return dict(rate=done / secs, n=done, seconds=secs, kind=arm.kind, desc=arm.describe(threads))
 
 
+def host_threads():
+    """Threads for the CPU arm: every CPU the process may use (cgroup quota respected — running 128
+    threads inside a 16-CPU quota only adds throttling and would flatter the GPU)."""
+    from motion_primitive_library_b200.scenarios import effective_cpus
+
+    return effective_cpus()
+
+
 def run_reference(args, sc, rank, world):
     if rank != 0:
         return
-    threads = os.cpu_count() or 1
+    threads = host_threads()
     arm = CpuArm(sc)
     nodes = sc.frontier(max(4096, 64 * threads), seed=7)
     # size a step at ~1.5 s of all-core CPU work
@@ -406,7 +414,7 @@ def main():
 
     cpu_baseline = None
     if world == 1 and not args.no_cpu_baseline:
-        threads = os.cpu_count() or 1
+        threads = host_threads()
         r = cpu_reference(sc, nodes_np, threads, args.cpu_seconds)
         cpu_baseline = {"value": r["rate"], "unit": UNIT, "cores": threads, "kind": r["kind"],
                         "sample": f"{r['n']} expansions drawn from the same frontier, {r['seconds']:.1f} s; {r['desc']}"}

@@ -24,6 +24,7 @@
 #include <cmath>
 #include <cstdint>
 #include <cstdio>
+#include <cstdlib>
 #include <limits>
 #include <memory>
 #include <stdexcept>
@@ -847,6 +848,24 @@ class MapPlanner : public PlannerBase<Dim> {
 typedef MapPlanner<2> OccMapPlanner;
 typedef MapPlanner<3> VoxelMapPlanner;
 
+/// CPUs this process may actually use: the hardware thread count capped by the cgroup v2 CPU quota
+/// (/sys/fs/cgroup/cpu.max = "<quota> <period>"); oversubscribing a quota only adds throttling.
+inline int effective_cpus() {
+  int n = (int)std::thread::hardware_concurrency();
+  if (n < 1) n = 1;
+  if (FILE *f = std::fopen("/sys/fs/cgroup/cpu.max", "r")) {
+    char q[64];
+    long period = 0;
+    if (std::fscanf(f, "%63s %ld", q, &period) == 2 && period > 0 && q[0] != 'm') {
+      const long quota = std::atol(q);
+      const int cap = (int)((quota + period - 1) / period);
+      if (cap >= 1 && cap < n) n = cap;
+    }
+    std::fclose(f);
+  }
+  return n;
+}
+
 /// Minimal persistent worker pool for the host side of the lock-step driver: the per-query
 /// bookkeeping (hash map, heap) of different queries is independent, so it is spread over the host
 /// cores while the device expands the next batch's nodes.
@@ -945,6 +964,10 @@ class MultiQueryPlanner {
   /// the shared env: set U, limits, weights, control, tolerances on it
   env_map_gpu<Dim> &env() { return *gpu_; }
   long iterations() const { return iterations_; }
+  /// seconds spent in the three phases of the last plan(): pop, device expansion (incl. PCIe), relax
+  double t_pop() const { return t_pop_; }
+  double t_device() const { return t_dev_; }
+  double t_relax() const { return t_relax_; }
   long nodes_expanded() const { return nodes_; }
 
   /// host threads used for the per-query bookkeeping (default: all cores)
@@ -952,7 +975,7 @@ class MultiQueryPlanner {
 
   std::vector<Result> plan(const vec_E<Waypoint<Dim>> &starts, const vec_E<Waypoint<Dim>> &goals, decimal_t eps,
                            int max_expand) {
-    WorkerPool pool(host_threads_ > 0 ? host_threads_ : (int)std::thread::hardware_concurrency());
+    WorkerPool pool(host_threads_ > 0 ? host_threads_ : effective_cpus());
     // per-query host env: goal test + heuristic only (its get_succ is never called)
     struct QueryEnv : env_map_host<Dim> {
       using env_map_host<Dim>::env_map_host;
@@ -976,6 +999,7 @@ class MultiQueryPlanner {
     std::vector<mplx_waypoint> batch;
     std::vector<std::size_t> who;
     iterations_ = nodes_ = 0;
+    t_pop_ = t_dev_ = t_relax_ = 0;
     for (;;) {
       // pop phase: one node per live query (independent heaps -> parallel), then compact
       who.clear();
@@ -983,8 +1007,11 @@ class MultiQueryPlanner {
         if (st[q]->active()) who.push_back(q);
       if (who.empty()) break;
       batch.resize(who.size());
+      auto t0 = std::chrono::steady_clock::now();
       pool.run(who.size(), [&](std::size_t b) { batch[b] = env_map_gpu<Dim>::pod(st[who[b]]->pop()); });
+      auto t1 = std::chrono::steady_clock::now();
       gpu_->expand_packed(batch);
+      auto t2 = std::chrono::steady_clock::now();
       iterations_++;
       nodes_ += (long)batch.size();
       // relax phase: every query consumes its own successors (independent state spaces -> parallel)
@@ -996,6 +1023,10 @@ class MultiQueryPlanner {
         st[who[b]]->consume(cnt, [&](int s) { return gpu_->packed_waypoint(r0 + s, batch[b]); },
                             gpu_->p_cost.data() + r0, act, [&](int s) { return (std::size_t)gpu_->p_key[r0 + s]; });
       });
+      auto t3 = std::chrono::steady_clock::now();
+      t_pop_ += std::chrono::duration<double>(t1 - t0).count();
+      t_dev_ += std::chrono::duration<double>(t2 - t1).count();
+      t_relax_ += std::chrono::duration<double>(t3 - t2).count();
     }
     for (std::size_t q = 0; q < Q; q++) {
       std::vector<Edge<Dim>> traj;
@@ -1012,6 +1043,7 @@ class MultiQueryPlanner {
   std::shared_ptr<MapUtil<Dim>> map_util_;
   std::unique_ptr<env_map_gpu<Dim>> gpu_;
   long iterations_ = 0, nodes_ = 0;
+  double t_pop_ = 0, t_dev_ = 0, t_relax_ = 0;
   int host_threads_ = 0;
   static constexpr int kMaxSucc = 1024;  // |U| upper bound of libmplx
 };

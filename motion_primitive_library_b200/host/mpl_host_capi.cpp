@@ -1,5 +1,7 @@
 // libmpl_host.so — C entry point that runs MPL::MapPlanner<Dim>::plan() with the GPU env
 // (env_map_gpu -> libmplx).  Used by the Python tests and tools; C++ users include mpl_host.hpp.
+#include <cstdlib>
+
 #include "plan_capi.hpp"
 
 static thread_local std::string g_err;
@@ -41,7 +43,8 @@ int mplh_plan(const mplh_plan_args *a, mplh_plan_result *r, uint64_t *closed_key
 
 /* Lock-step batched A* over n_q (start, goal) pairs on the map/params of `a` (a->start/goal are
  * ignored).  totals[0] = lock-step iterations (= device launches of the expansion kernel),
- * totals[1] = nodes expanded over all queries, totals[2] = wall seconds of the search. */
+ * totals[1] = nodes expanded over all queries, totals[2] = wall seconds of the search,
+ * totals[3..5] = seconds in the pop / device expansion (incl. PCIe) / relax phases. */
 int mplh_plan_batch(const mplh_plan_args *a, const mplx_waypoint *starts, const mplx_waypoint *goals, int n_q,
                     mplh_query_result *out, double *totals) {
   try {
@@ -49,6 +52,7 @@ int mplh_plan_batch(const mplh_plan_args *a, const mplx_waypoint *starts, const 
       constexpr int Dim = decltype(dimtag)::value;
       MPL::MultiQueryPlanner<Dim> mq(mplh::make_map<Dim>(a), a->device);
       auto &e = mq.env();
+      if (const char *t = std::getenv("MPLH_THREADS")) mq.setHostThreads(std::atoi(t));
       vec_E<VecDf> U;
       for (int i = 0; i < a->nU; i++) U.push_back(VecDf(a->U + (size_t)i * a->udim, a->U + (size_t)(i + 1) * a->udim));
       e.set_u(U); e.set_control(a->control);
@@ -77,7 +81,10 @@ int mplh_plan_batch(const mplh_plan_args *a, const mplx_waypoint *starts, const 
         out[q].n_closed = (int)res[q].n_closed;
         out[q].n_actions = (int)res[q].actions.size();
       }
-      if (totals) { totals[0] = (double)mq.iterations(); totals[1] = (double)mq.nodes_expanded(); totals[2] = secs; }
+      if (totals) {
+        totals[0] = (double)mq.iterations(); totals[1] = (double)mq.nodes_expanded(); totals[2] = secs;
+        totals[3] = mq.t_pop(); totals[4] = mq.t_device(); totals[5] = mq.t_relax();
+      }
     };
     if (a->dim == 2) go(std::integral_constant<int, 2>());
     else if (a->dim == 3) go(std::integral_constant<int, 3>());

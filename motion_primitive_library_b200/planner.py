@@ -120,11 +120,12 @@ def plan_batch(args, starts, goals):
     goals = np.ascontiguousarray(goals, dtype=WAYPOINT_DTYPE)
     nq = len(starts)
     out = (QueryResult * max(nq, 1))()
-    totals = np.zeros(3)
+    totals = np.zeros(6)
     rc = lib.mplh_plan_batch(C.byref(args), starts.ctypes.data, goals.ctypes.data, nq, out, totals.ctypes.data)
     if rc != 0:
         raise RuntimeError(lib.mplh_last_error().decode())
     res = np.zeros(nq, dtype=[("valid", "i4"), ("cost", "f8"), ("expanded", "i4"), ("n_closed", "i4"), ("n_actions", "i4")])
     for q in range(nq):
         res[q] = (out[q].valid, out[q].cost, out[q].expanded, out[q].n_closed, out[q].n_actions)
-    return res, dict(iterations=int(totals[0]), nodes=int(totals[1]), seconds=float(totals[2]))
+    return res, dict(iterations=int(totals[0]), nodes=int(totals[1]), seconds=float(totals[2]), t_pop=float(totals[3]),
+                     t_device=float(totals[4]), t_relax=float(totals[5]))

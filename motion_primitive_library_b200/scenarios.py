@@ -15,6 +15,20 @@ import numpy as np
 from .abi import ACC, ACCxYAW, JRK, WAYPOINT_DTYPE
 
 
+def effective_cpus() -> int:
+    """CPUs this process may use: os.cpu_count() capped by the cgroup v2 CPU quota (cpu.max)."""
+    import os
+
+    n = os.cpu_count() or 1
+    try:
+        q, period = open("/sys/fs/cgroup/cpu.max").read().split()
+        if q != "max":
+            n = max(1, min(n, -(-int(q) // int(period))))
+    except (OSError, ValueError):
+        pass
+    return n
+
+
 def control_set(u_max: float, n_disc: int, dim: int, yaw_rates=None) -> np.ndarray:
     """U = {-u_max..u_max}^dim (x yaw_rates), first axis outermost (reference test loop order)."""
     vals = np.linspace(-u_max, u_max, n_disc) if n_disc > 1 else np.array([0.0])
