@@ -4,18 +4,17 @@
 // Work decomposition.  A CTA of 256 threads covers NPB = 256/|U| whole frontier nodes, one
 // thread per (node, control) primitive:
 //   phase A  build the primitive (primitive.h:220-256), evaluate the end state tn
-//            (:321-331), its lattice key (waypoint.h:93-125) and the dynamic validity
-//            (primitive.h:449-525) in registers;
+//            (:321-331), the dynamic validity (primitive.h:449-525) and, for the survivors, the
+//            lattice key (waypoint.h:93-125) in registers;
 //   phase B  stable, control-ordered compaction of each node's successors with warp ballots
 //            (the push_back order of env_map.h:155-170) and write-out of tn/key/action;
-//   phase C  traverse_primitive (env_map.h:90-132).  "flat" kernel: the samples of the 32
-//            primitives of a warp are laid end to end and dealt to the lanes round-robin —
-//            coefficients staged in shared memory, sample times read from the table that
-//            reproduces the `t += dt` running sum — so every lane does useful work and the
-//            voxel loads of a warp are 32 independent requests (the per-primitive loop is a
-//            chain of dependent loads).  A per-primitive atomicMin records the first blocking
-//            sample (= the reference's early `return inf`).  The "seq" kernel keeps the literal
-//            per-thread loop; it serves |U| > 256 and is the in-kernel fallback for n > maxn.
+//   phase C  traverse_primitive (env_map.h:90-132), three interchangeable implementations:
+//     expand_reg_kernel  (default) thread = primitive, quotients in registers, the reference's
+//                        t += dt loop in groups of 4 samples with group-level control flow;
+//     expand_flat_kernel the samples of a warp's 32 primitives laid end to end and dealt to the
+//                        lanes (quotients staged in shared memory, sample times from the table
+//                        that reproduces the running sum, atomicMin of the first blocking sample);
+//     expand_seq_kernel  the literal per-primitive loop; serves |U| > 256.
 // The occupancy grid is read as 1 bit/voxel (16 MiB at 512^3: L2-resident); potential-field
 // planning reads the int8 grid.  No tensor cores: there is no dense contraction on this path.
 //
@@ -70,35 +69,6 @@ __device__ __forceinline__ bool voxel_classify(const EnvParams &P, VoxelRaw r, d
     return false;
   }
   return r & 1u;
-}
-// Three-register form of the same two steps (the register kernel's loop compiles best with it).
-struct VoxelRaw3 {
-  uint32_t region_word, occ_word;
-  int pot;
-};
-__device__ __forceinline__ VoxelRaw3 voxel_fetch3(const EnvParams &P, int idx) {
-  VoxelRaw3 r;
-  r.region_word = 0xffffffffu;
-  r.occ_word = 0;
-  r.pot = 0;
-  if (P.region_bits != nullptr) r.region_word = __ldg(P.region_bits + (idx >> 5));
-  if (P.pot != nullptr)
-    r.pot = (int)__ldg(P.pot + idx);
-  else
-    r.occ_word = __ldg(P.occ_bits + (idx >> 5));
-  return r;
-}
-__device__ __forceinline__ bool voxel_classify3(const EnvParams &P, const VoxelRaw3 &r, int idx, double dt,
-                                               double vnorm_w, double &term) {
-  if (!((r.region_word >> (idx & 31)) & 1u)) return true;  // outside the tunnel (env_map.h:104-106)
-  if (P.pot != nullptr) {
-    if (r.pot < 100 && r.pot > 0)
-      term += dt * (P.pot_w * r.pot + vnorm_w);
-    else if (r.pot >= 100)
-      return true;
-    return false;
-  }
-  return (r.occ_word >> (idx & 31)) & 1u;
 }
 __device__ __forceinline__ bool voxel_blocks(const EnvParams &P, int idx, double dt, double vnorm_w,
                                              double &term) {
@@ -502,7 +472,7 @@ expand_seq_kernel(const __grid_constant__ EnvParams P, const mplx_waypoint *__re
 // n_samples counts what the reference's loop visits (up to and including the first blocking
 // sample) and is only maintained when the stats counters are on.
 template <int DIM, int ORD, bool YAW, int UNR>
-__device__ __forceinline__ double traverse_regs3(const EnvParams &P, const double (&cf)[CoefLayout<DIM, ORD, YAW>::NCMAX],
+__device__ __forceinline__ double traverse_groups(const EnvParams &P, const double (&cf)[CoefLayout<DIM, ORD, YAW>::NCMAX],
                                                  bool need_vel, double dt, unsigned &n_samples) {
   using CL = CoefLayout<DIM, ORD, YAW>;
   const double T = P.T;
@@ -585,57 +555,6 @@ __device__ __forceinline__ double traverse_regs3(const EnvParams &P, const doubl
   }
 }
 
-template <int DIM, int ORD, bool YAW, bool VEL, int UNR>
-__device__ __forceinline__ double traverse_regs(const EnvParams &P, const double (&cf)[CoefLayout<DIM, ORD, YAW>::NCMAX],
-                                                double dt, unsigned &n_samples) {
-  using CL = CoefLayout<DIM, ORD, YAW>;
-  const double T = P.T;
-  constexpr int NC = CL::NCP + (VEL ? CL::NCV : 0) + (YAW ? 2 : 0);
-  double c = 0;
-  double t = 0;
-  while (t < T) {
-    const double t0 = t;
-    int idx[UNR];
-    VoxelRaw raw[UNR];
-#pragma unroll
-    for (int j = 0; j < UNR; j++) {
-      idx[j] = -2;
-      if (t < T) {
-        double pk[DIM];
-        eval_pos<DIM, ORD>(cf, t, pk);
-        idx[j] = sample_index<DIM>(P, pk);
-      }
-      t += dt;  // the reference's running sum; harmless past T
-    }
-#pragma unroll
-    for (int j = 0; j < UNR; j++) {
-      raw[j] = kVoxelNone;
-      if (idx[j] >= 0) raw[j] = voxel_fetch(P, idx[j]);
-    }
-    double tj = t0;
-#pragma unroll
-    for (int j = 0; j < UNR; j++) {
-      if (idx[j] == -2) return c;  // t_j >= T: the loop has ended
-      n_samples++;
-      if (idx[j] < 0) return INFINITY;
-      double vel[DIM];
-      double gterm = 0.0;
-      if (VEL) {
-        eval_vel<DIM, ORD>(cf + CL::NCP, tj, vel);
-        gterm = grad_term<DIM>(P, vel);
-      }
-      double term = 0.0;
-      if (voxel_classify(P, raw[j], dt, gterm, term)) return INFINITY;
-      c += term;
-      if (YAW) {
-        if (P.wyaw > 0) c += yaw_term(P, vel[0], vel[1], normalize_angle(cf[NC - 2] * tj + cf[NC - 1]), dt);
-      }
-      if (VEL) tj += dt;  // same running sum as t
-    }
-  }
-  return c;
-}
-
 // n = max(5, (int)ceil(max_v*T/res)), dt = T/n  (env_map.h:95,98): exact quotient + ceiling;
 // T/n from the table for n <= kNMax, a true division beyond it.
 __device__ __forceinline__ int sample_count_n(const EnvParams &P, double max_v, double &dt) {
@@ -669,12 +588,9 @@ expand_reg_kernel(const __grid_constant__ EnvParams P, const mplx_waypoint *__re
     if (!same) {
       double cf[CoefLayout<DIM, ORD, YAW>::NCMAX];
       fill_coef<DIM, ORD, YAW>(pr, VEL, cf);
-      // n = max(5, (int)ceil(max_v*T/res)), dt = T/n  (env_map.h:95,98): exact quotient + ceiling;
-      // T/n from the table for n <= kNMax, a true division beyond it
-      const double nd = ceil_exact(div_exact(max_v * P.T, P.res, P.rinv));
-      const int n = nd < 5.0 ? 5 : (nd < 2.0e9 ? (int)nd : 2000000000);
-      const double dt = n <= kNMax ? __ldg(P.tdt + n) : P.T / n;
-      cost = traverse_regs3<DIM, ORD, YAW, UNR>(P, cf, VEL, dt, n_samples);
+      double dt;
+      sample_count_n(P, max_v, dt);
+      cost = traverse_groups<DIM, ORD, YAW, UNR>(P, cf, VEL, dt, n_samples);
     }
     if (!isinf(cost)) cost += intrinsic;
     if (o.cost) o.cost[slot] = cost;
@@ -682,100 +598,6 @@ expand_reg_kernel(const __grid_constant__ EnvParams P, const mplx_waypoint *__re
   if (P.stats) {
     atomicAdd(&s_stats[0], (unsigned long long)n_samples);
     if (emit) atomicAdd(&s_stats[1], 1ull);
-    __syncthreads();
-    if (threadIdx.x < 2) atomicAdd(&P.stats[threadIdx.x], s_stats[threadIdx.x]);
-  }
-}
-
-// Sorted variant: after phases A/B the CTA's emitted primitives are re-dealt to its threads in
-// order of decreasing sample count n (counting sort through shared memory: quotients, dt,
-// intrinsic cost and output slot travel with the primitive), so the 32 lanes of a warp walk loops
-// of (nearly) equal length instead of idling behind the longest one.  Which thread samples which
-// primitive has no effect on any result: every primitive still writes its own cost to its slot.
-template <int DIM, int ORD, bool YAW, bool VEL, int UNR, int MINB>
-__global__ void __launch_bounds__(kThreads, MINB)
-expand_sort_kernel(const __grid_constant__ EnvParams P, const mplx_waypoint *__restrict__ nodes, int n_nodes,
-                   int npb, const __grid_constant__ OutPtrs o) {
-  using CL = CoefLayout<DIM, ORD, YAW>;
-  constexpr int NC = CL::NCP + (VEL ? CL::NCV : 0) + (YAW ? 2 : 0);
-  constexpr int STRIDE = NC + 3;  // quotients, dt, intrinsic, slot (8 bytes)
-  constexpr int NB = kNMax + 2;   // buckets: n = 0..kNMax and one for n > kNMax
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  __shared__ uint32_t vbits[9];
-  __shared__ unsigned long long s_stats[2];
-  __shared__ int s_hist[NB], s_total;
-  double *s_item = reinterpret_cast<double *>(smem_raw);
-  const int nU = P.nU;
-  const int items = npb * nU;  // <= 256
-  const int node0 = blockIdx.x * npb;
-  const int words = (items + 31) >> 5;
-  if (threadIdx.x < 2) s_stats[threadIdx.x] = 0;
-  for (int b = threadIdx.x; b < NB; b += kThreads) s_hist[b] = 0;
-  int bucket = 0, within = 0;
-  bool work;
-  {
-    PrimState<DIM, ORD, YAW> pr;
-    bool emit, same;
-    double max_v;
-    size_t slot;
-    phase_ab<DIM, ORD, YAW>(P, nodes, n_nodes, threadIdx.x, items, nU, node0, vbits, words, o, pr, emit, same,
-                            max_v, slot);  // contains a __syncthreads(): s_hist is zeroed by now
-    work = emit && !same;
-    if (P.stats && emit) atomicAdd(&s_stats[1], 1ull);
-    if (emit) {
-      const double intrinsic = intrinsic_cost<DIM, ORD, YAW>(P, pr);
-      if (work) {
-        double dt;
-        const int n = sample_count_n(P, max_v, dt);
-        bucket = n > kNMax ? kNMax + 1 : n;
-        within = atomicAdd(&s_hist[bucket], 1);
-        // park the item in this thread's own row; it moves to its sorted row after the scan
-        double *it = s_item + (size_t)threadIdx.x * STRIDE;
-        fill_coef<DIM, ORD, YAW>(pr, VEL, it);
-        it[NC] = dt;
-        it[NC + 1] = intrinsic;
-        reinterpret_cast<unsigned long long *>(it)[NC + 2] = (unsigned long long)slot;
-      } else if (o.cost) {
-        o.cost[slot] = intrinsic;  // curr.pos == tn.pos: cost = 0 + intrinsic (env_map.h:163-165)
-      }
-    }
-  }
-  __syncthreads();
-  if (threadIdx.x < 32) {
-    // exclusive scan over the buckets in order of decreasing n, by one warp
-    int carry = 0;
-    for (int b0 = NB - 1; b0 >= 0; b0 -= 32) {
-      const int b = b0 - (int)threadIdx.x;
-      const int v = b >= 0 ? s_hist[b] : 0;
-      int incl = v;
-#pragma unroll
-      for (int d = 1; d < 32; d <<= 1) {
-        const int u = __shfl_up_sync(0xffffffffu, incl, d);
-        if ((int)threadIdx.x >= d) incl += u;
-      }
-      if (b >= 0) s_hist[b] = carry + incl - v;
-      carry += __shfl_sync(0xffffffffu, incl, 31);
-    }
-    if (threadIdx.x == 0) s_total = carry;
-  }
-  __syncthreads();
-  // permutation: thread p works on the item parked by thread s_perm[p]
-  unsigned char *s_perm = reinterpret_cast<unsigned char *>(s_item + (size_t)kThreads * STRIDE);
-  if (work) s_perm[s_hist[bucket] + within] = (unsigned char)threadIdx.x;
-  __syncthreads();
-  unsigned n_samples = 0;
-  if ((int)threadIdx.x < s_total) {
-    const double *it = s_item + (size_t)s_perm[threadIdx.x] * STRIDE;
-    double cf[CL::NCMAX];
-#pragma unroll
-    for (int c = 0; c < NC; c++) cf[c] = it[c];
-    const double dt = it[NC];
-    double cost = traverse_regs<DIM, ORD, YAW, VEL, UNR>(P, cf, dt, n_samples);
-    if (!isinf(cost)) cost += it[NC + 1];
-    if (o.cost) o.cost[(size_t) reinterpret_cast<const unsigned long long *>(it)[NC + 2]] = cost;
-  }
-  if (P.stats) {
-    atomicAdd(&s_stats[0], (unsigned long long)n_samples);
     __syncthreads();
     if (threadIdx.x < 2) atomicAdd(&P.stats[threadIdx.x], s_stats[threadIdx.x]);
   }
@@ -935,196 +757,6 @@ expand_flat_kernel(const __grid_constant__ EnvParams P, const mplx_waypoint *__r
   }
 }
 
-// ---- unit kernel (|U| <= 256): flat dealing of UNIT-sample chunks ------------------------------
-// The best of the two designs above.  Phase C work is cut into units of UNIT consecutive samples
-// of one primitive; a warp lays the units of its 32 primitives end to end and deals them to its
-// lanes round-robin.  A lane loads the primitive's quotients and the unit's sample times once,
-// computes the UNIT cell indices, issues the UNIT voxel loads back to back and classifies them in
-// order (atomicMin of the first blocking sample index per primitive = the reference's early
-// return).  So: every lane has work (only a primitive's last unit can be partly empty), the
-// per-sample staging overhead of the flat kernel is divided by UNIT, UNIT loads are in flight per
-// lane, and all warps of a CTA finish together.
-template <int DIM, int ORD, bool YAW, bool VEL>
-struct UnitLayout {
-  using CL = CoefLayout<DIM, ORD, YAW>;
-  static constexpr int NC = CL::NCP + (VEL ? CL::NCV : 0) + (YAW ? 2 : 0);
-  __host__ __device__ static size_t warp_bytes(int maxunits) {
-    size_t b = (size_t)32 * NC * 8 + 32 * 8 * 2 + 32 * 4 * 3 + (size_t)32 * maxunits * 2;
-    return (b + 15) & ~(size_t)15;
-  }
-};
-
-template <int DIM, int ORD, bool YAW, bool VEL, int UNIT, int MINB>
-__global__ void __launch_bounds__(kThreads, MINB)
-expand_unit_kernel(const __grid_constant__ EnvParams P, const mplx_waypoint *__restrict__ nodes, int n_nodes,
-                   int npb, const __grid_constant__ OutPtrs o, int maxunits) {
-  extern __shared__ __align__(16) unsigned char smem[];
-  __shared__ uint32_t vbits[9];
-  __shared__ unsigned long long s_stats[2];
-  using L = UnitLayout<DIM, ORD, YAW, VEL>;
-  using CL = CoefLayout<DIM, ORD, YAW>;
-  constexpr int NC = L::NC;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  unsigned char *wb = smem + (size_t)warp * L::warp_bytes(maxunits);
-  double *w_coef = reinterpret_cast<double *>(wb);
-  double *w_cost = w_coef + 32 * NC;
-  double *w_dt = w_cost + 32;
-  int *w_n = reinterpret_cast<int *>(w_dt + 32);
-  int *w_ns = w_n + 32;
-  int *w_first = w_ns + 32;
-  unsigned short *w_owner = reinterpret_cast<unsigned short *>(w_first + 32);
-
-  const int nU = P.nU;
-  const int items = npb * nU;  // <= 256
-  const int node0 = blockIdx.x * npb;
-  const int words = (items + 31) >> 5;
-  if (threadIdx.x < 2) s_stats[threadIdx.x] = 0;
-
-  bool emit, same, seq = false;
-  size_t slot;
-  double intrinsic = 0.0, cost_seq = 0.0;
-  unsigned seq_samples = 0;
-  int ns = 0, units = 0;
-  {
-    PrimState<DIM, ORD, YAW> pr;
-    double max_v;
-    phase_ab<DIM, ORD, YAW>(P, nodes, n_nodes, threadIdx.x, items, nU, node0, vbits, words, o, pr, emit, same,
-                            max_v, slot);
-    // ---- phase C set-up: quotient slot, n, sample and unit counts ----
-    int n = 0;
-    double dt = 0.0;
-    if (emit) {
-      intrinsic = intrinsic_cost<DIM, ORD, YAW>(P, pr);
-      if (!same) {
-        fill_coef<DIM, ORD, YAW>(pr, VEL, w_coef + lane * NC);
-        n = sample_count_n(P, max_v, dt);
-        if (n <= P.maxn) {
-          ns = __ldg(P.tcount + n);
-          units = (ns + UNIT - 1) / UNIT;
-        } else {
-          seq = true;  // beyond the table: literal loop in this lane, quotients from its smem slot
-          cost_seq = traverse_loop_cold<DIM, ORD, YAW>(&P, w_coef + lane * NC, VEL, max_v, &seq_samples);
-        }
-      }
-    }
-    w_cost[lane] = 0.0;
-    w_dt[lane] = dt;
-    w_n[lane] = n;
-    w_ns[lane] = ns;
-    w_first[lane] = kNoBlock;
-  }
-  int incl = units;
-#pragma unroll
-  for (int d = 1; d < 32; d <<= 1) {
-    const int v = __shfl_up_sync(0xffffffffu, incl, d);
-    if (lane >= d) incl += v;
-  }
-  const int start = incl - units;
-  const int Utot = __shfl_sync(0xffffffffu, incl, 31);
-  for (int c = 0; c < units; c++) w_owner[start + c] = (unsigned short)((lane << 8) | c);
-  __syncwarp();
-
-  // ---- phase C ----
-  for (int u = lane; u < Utot; u += 32) {
-    const unsigned ow = w_owner[u];
-    const int i = (int)(ow >> 8);
-    const int k0 = (int)(ow & 255u) * UNIT;
-    // an earlier sample of this primitive already blocks: the result is inf whatever this unit says
-    if (*(volatile int *)(w_first + i) < k0) continue;
-    const int cnt = min(UNIT, w_ns[i] - k0);
-    double cf[NC];
-#pragma unroll
-    for (int c = 0; c < NC; c++) cf[c] = w_coef[i * NC + c];
-    const double *tp = P.ttab + w_n[i] * kTStride + k0;
-    double ts[UNIT];
-#pragma unroll
-    for (int j = 0; j < UNIT; j++) ts[j] = __ldg(tp + j);  // the table is padded past the last row
-    int idx[UNIT];
-    VoxelRaw raw[UNIT];
-#pragma unroll
-    for (int j = 0; j < UNIT; j++) {
-      idx[j] = -2;
-      if (j < cnt) {
-        double pk[DIM];
-        eval_pos<DIM, ORD>(cf, ts[j], pk);
-        idx[j] = sample_index<DIM>(P, pk);
-      }
-    }
-#pragma unroll
-    for (int j = 0; j < UNIT; j++) {
-      raw[j] = kVoxelNone;
-      if (idx[j] >= 0) raw[j] = voxel_fetch(P, idx[j]);
-    }
-    const double dt = w_dt[i];
-    double acc = 0.0;
-    int blocked_at = -1;
-#pragma unroll
-    for (int j = 0; j < UNIT; j++) {
-      if (blocked_at < 0 && idx[j] != -2) {
-        if (idx[j] < 0) {
-          blocked_at = k0 + j;
-        } else {
-          double vel[DIM];
-          double gterm = 0.0;
-          if (VEL) {
-            eval_vel<DIM, ORD>(cf + CL::NCP, ts[j], vel);
-            gterm = grad_term<DIM>(P, vel);
-          }
-          double term = 0.0;
-          if (voxel_classify(P, raw[j], dt, gterm, term)) {
-            blocked_at = k0 + j;
-          } else {
-            if (YAW) {
-              if (P.wyaw > 0) term += yaw_term(P, vel[0], vel[1], normalize_angle(cf[NC - 2] * ts[j] + cf[NC - 1]), dt);
-            }
-            acc += term;
-          }
-        }
-      }
-    }
-    if (blocked_at >= 0)
-      atomicMin(w_first + i, blocked_at);
-    else if (acc != 0.0)
-      atomicAdd(w_cost + i, acc);
-  }
-  __syncwarp();
-
-  if (emit) {
-    const int fb = w_first[lane];
-    double cost = same ? 0.0 : seq ? cost_seq : (fb != kNoBlock ? (double)INFINITY : w_cost[lane]);
-    if (!isinf(cost)) cost += intrinsic;
-    if (o.cost) o.cost[slot] = cost;
-    if (P.stats) {
-      // samples the reference loop visits: up to and including the first blocking one
-      const unsigned visited = seq ? seq_samples : (fb != kNoBlock ? (unsigned)fb + 1u : (unsigned)ns);
-      atomicAdd(&s_stats[0], (unsigned long long)visited);
-      atomicAdd(&s_stats[1], 1ull);
-    }
-  }
-  if (P.stats) {
-    __syncthreads();
-    if (threadIdx.x < 2) atomicAdd(&P.stats[threadIdx.x], s_stats[threadIdx.x]);
-  }
-}
-
-template <int DIM, int ORD, bool YAW, bool VEL>
-static cudaError_t launch_unit(const EnvParams &P, const mplx_waypoint *d_nodes, int n_nodes, int npb, int grid,
-                               const OutPtrs &o, cudaStream_t st) {
-  constexpr int UNIT = 4;
-  using L = UnitLayout<DIM, ORD, YAW, VEL>;
-  const int maxunits = (P.maxn + 1 + UNIT - 1) / UNIT;
-  const size_t smem = kWarps * L::warp_bytes(maxunits);
-  static thread_local size_t configured = 0;
-  if (smem > 48 * 1024 && smem > configured) {
-    cudaError_t e = cudaFuncSetAttribute(expand_unit_kernel<DIM, ORD, YAW, VEL, UNIT, 4>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    configured = smem;
-  }
-  expand_unit_kernel<DIM, ORD, YAW, VEL, UNIT, 4><<<grid, kThreads, smem, st>>>(P, d_nodes, n_nodes, npb, o, maxunits);
-  return cudaGetLastError();
-}
-
 template <int DIM, int ORD, bool YAW>
 static cudaError_t launch_t(const EnvParams &P, const mplx_waypoint *d_nodes, int n_nodes,
                             const mplx_succ_out &so, cudaStream_t st, int force_seq) {
@@ -1136,11 +768,7 @@ static cudaError_t launch_t(const EnvParams &P, const mplx_waypoint *d_nodes, in
     return cudaGetLastError();
   }
   const bool nv = YAW || (P.pot != nullptr && P.grad_w != 0.0);
-  if (force_seq == 4) {  // unit kernel
-    return nv ? launch_unit<DIM, ORD, YAW, true>(P, d_nodes, n_nodes, npb, grid, o, st)
-              : launch_unit<DIM, ORD, YAW, YAW>(P, d_nodes, n_nodes, npb, grid, o, st);
-  }
-  if (force_seq == 0 || force_seq == 2) {  // register kernel (default)
+  if (force_seq != 3) {  // register kernel (default)
     // samples in flight per lane: 4, or 2 when every primitive of the plan has a short loop
     // (n <= 15: a group of 4 would mostly run past the end of the loop)
     const bool short_loops = P.maxn <= 15;
@@ -1154,29 +782,6 @@ static cudaError_t launch_t(const EnvParams &P, const mplx_waypoint *d_nodes, in
         expand_reg_kernel<DIM, ORD, YAW, YAW, 2, 4><<<grid, kThreads, 0, st>>>(P, d_nodes, n_nodes, npb, o);
       else
         expand_reg_kernel<DIM, ORD, YAW, YAW, 4, 4><<<grid, kThreads, 0, st>>>(P, d_nodes, n_nodes, npb, o);
-    }
-    return cudaGetLastError();
-  }
-  if (force_seq == 5) {  // register kernel with the CTA-level sort by sample count
-    const size_t sm = (size_t)kThreads * (CoefLayout<DIM, ORD, YAW>::ncoef(nv) + 3) * sizeof(double) + kThreads;
-    if (nv) {
-      static thread_local size_t conf_v = 0;
-      if (sm > 48 * 1024 && sm > conf_v) {
-        cudaError_t e = cudaFuncSetAttribute(expand_sort_kernel<DIM, ORD, YAW, true, 4, 4>,
-                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
-        if (e != cudaSuccess) return e;
-        conf_v = sm;
-      }
-      expand_sort_kernel<DIM, ORD, YAW, true, 4, 4><<<grid, kThreads, sm, st>>>(P, d_nodes, n_nodes, npb, o);
-    } else {
-      static thread_local size_t conf_p = 0;
-      if (sm > 48 * 1024 && sm > conf_p) {
-        cudaError_t e = cudaFuncSetAttribute(expand_sort_kernel<DIM, ORD, YAW, YAW, 4, 4>,
-                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
-        if (e != cudaSuccess) return e;
-        conf_p = sm;
-      }
-      expand_sort_kernel<DIM, ORD, YAW, YAW, 4, 4><<<grid, kThreads, sm, st>>>(P, d_nodes, n_nodes, npb, o);
     }
     return cudaGetLastError();
   }
