@@ -281,7 +281,9 @@ struct OutPtrs {
 };
 
 // Phases A and B for one item (all threads of the CTA must call it: it contains a barrier).
-template <int DIM, int ORD, bool YAW>
+// LAT: the caller asked for the lattice ints (mplx_succ_out.lattice); without it the 13-entry
+// array never exists (it would cost 13 registers through phase A).
+template <int DIM, int ORD, bool YAW, bool LAT>
 __device__ __forceinline__ void phase_ab(const EnvParams &P, const mplx_waypoint *__restrict__ nodes,
                                          int n_nodes, int item, int items, int nU, int node0,
                                          uint32_t *vbits, int words, const OutPtrs &o,
@@ -297,7 +299,7 @@ __device__ __forceinline__ void phase_ab(const EnvParams &P, const mplx_waypoint
   slot = 0;
 
   mplx_waypoint tn;
-  int lat[MPLX_LATTICE_MAX];
+  int lat[LAT ? MPLX_LATTICE_MAX : 1];
   uint64_t key = 0;
   if (active) {
     const mplx_waypoint *cp = nodes + ni;
@@ -360,20 +362,22 @@ __device__ __forceinline__ void phase_ab(const EnvParams &P, const mplx_waypoint
         if (ORD >= 4) hash_combine(hcurr, lattice_id(cp->jrk[k], 0.1, 10.0));
         int id = lattice_id(tn.pos[k], 0.01, 100.0);
         hash_combine(key, id);
-        lat[nl_++] = id;
-        if (ORD >= 2) { id = lattice_id(tn.vel[k], 0.1, 10.0); hash_combine(key, id); lat[nl_++] = id; }
-        if (ORD >= 3) { id = lattice_id(tn.acc[k], 0.1, 10.0); hash_combine(key, id); lat[nl_++] = id; }
-        if (ORD >= 4) { id = lattice_id(tn.jrk[k], 0.1, 10.0); hash_combine(key, id); lat[nl_++] = id; }
+        if (LAT) lat[nl_++] = id;
+        if (ORD >= 2) { id = lattice_id(tn.vel[k], 0.1, 10.0); hash_combine(key, id); if (LAT) lat[nl_++] = id; }
+        if (ORD >= 3) { id = lattice_id(tn.acc[k], 0.1, 10.0); hash_combine(key, id); if (LAT) lat[nl_++] = id; }
+        if (ORD >= 4) { id = lattice_id(tn.jrk[k], 0.1, 10.0); hash_combine(key, id); if (LAT) lat[nl_++] = id; }
       }
       if (YAW) {
         hash_combine(hcurr, lattice_id(cp->yaw, 0.1, 10.0));
         const int id = lattice_id(tn.yaw, 0.1, 10.0);
         hash_combine(key, id);
-        lat[nl_++] = id;
+        if (LAT) lat[nl_++] = id;
       }
+      if (LAT) {
 #pragma unroll
-      for (int q = 0; q < MPLX_LATTICE_MAX; q++)
-        if (q >= nl_) lat[q] = 0;
+        for (int q = 0; q < MPLX_LATTICE_MAX; q++)
+          if (q >= nl_) lat[q] = 0;
+      }
       ok = key != hcurr;
     }
     emit = ok;
@@ -399,7 +403,7 @@ __device__ __forceinline__ void phase_ab(const EnvParams &P, const mplx_waypoint
       if (o.succ) o.succ[slot] = tn;
       if (o.action) o.action[slot] = ci;
       if (o.key) o.key[slot] = key;
-      if (o.lattice) {
+      if (LAT && o.lattice) {
 #pragma unroll
         for (int q = 0; q < MPLX_LATTICE_MAX; q++) o.lattice[slot * MPLX_LATTICE_MAX + q] = lat[q];
       }
@@ -434,7 +438,7 @@ expand_seq_kernel(const __grid_constant__ EnvParams P, const mplx_waypoint *__re
     bool emit, same;
     double max_v;
     size_t slot;
-    phase_ab<DIM, ORD, YAW>(P, nodes, n_nodes, base + threadIdx.x, items, nU, node0, vbits, words, o, pr, emit,
+    phase_ab<DIM, ORD, YAW, true>(P, nodes, n_nodes, base + threadIdx.x, items, nU, node0, vbits, words, o, pr, emit,
                             same, max_v, slot);
     unsigned n_samples = 0;
     if (emit) {
@@ -564,7 +568,7 @@ __device__ __forceinline__ int sample_count_n(const EnvParams &P, double max_v, 
   return n;
 }
 
-template <int DIM, int ORD, bool YAW, bool VEL, int UNR, int MINB>
+template <int DIM, int ORD, bool YAW, bool VEL, int UNR, int MINB, bool LAT>
 __global__ void __launch_bounds__(kThreads, MINB)
 expand_reg_kernel(const __grid_constant__ EnvParams P, const mplx_waypoint *__restrict__ nodes, int n_nodes,
                   int npb, const __grid_constant__ OutPtrs o) {
@@ -579,8 +583,8 @@ expand_reg_kernel(const __grid_constant__ EnvParams P, const mplx_waypoint *__re
   bool emit, same;
   double max_v;
   size_t slot;
-  phase_ab<DIM, ORD, YAW>(P, nodes, n_nodes, threadIdx.x, items, nU, node0, vbits, words, o, pr, emit, same,
-                          max_v, slot);
+  phase_ab<DIM, ORD, YAW, LAT>(P, nodes, n_nodes, threadIdx.x, items, nU, node0, vbits, words, o, pr, emit, same,
+                               max_v, slot);
   unsigned n_samples = 0;
   if (emit) {
     double cost = 0.0;
@@ -646,8 +650,8 @@ expand_flat_kernel(const __grid_constant__ EnvParams P, const mplx_waypoint *__r
   bool emit, same;
   double max_v;
   size_t slot;
-  phase_ab<DIM, ORD, YAW>(P, nodes, n_nodes, threadIdx.x, items, nU, node0, vbits, words, o, pr, emit, same,
-                          max_v, slot);
+  phase_ab<DIM, ORD, YAW, true>(P, nodes, n_nodes, threadIdx.x, items, nU, node0, vbits, words, o, pr, emit, same,
+                                max_v, slot);
 
   // ---- phase C set-up: coefficient slot, n, sample count ----
   const double T = P.T;
@@ -772,17 +776,17 @@ static cudaError_t launch_t(const EnvParams &P, const mplx_waypoint *d_nodes, in
     // samples in flight per lane: 4, or 2 when every primitive of the plan has a short loop
     // (n <= 15: a group of 4 would mostly run past the end of the loop)
     const bool short_loops = P.maxn <= 15;
+    const bool lat = o.lattice != nullptr;
+#define MPLX_LAUNCH_REG(VEL, UNR, LAT) \
+  expand_reg_kernel<DIM, ORD, YAW, VEL, UNR, 4, LAT><<<grid, kThreads, 0, st>>>(P, d_nodes, n_nodes, npb, o)
     if (nv) {
-      if (short_loops)
-        expand_reg_kernel<DIM, ORD, YAW, true, 2, 4><<<grid, kThreads, 0, st>>>(P, d_nodes, n_nodes, npb, o);
-      else
-        expand_reg_kernel<DIM, ORD, YAW, true, 4, 4><<<grid, kThreads, 0, st>>>(P, d_nodes, n_nodes, npb, o);
+      if (short_loops) { if (lat) MPLX_LAUNCH_REG(true, 2, true); else MPLX_LAUNCH_REG(true, 2, false); }
+      else { if (lat) MPLX_LAUNCH_REG(true, 4, true); else MPLX_LAUNCH_REG(true, 4, false); }
     } else {
-      if (short_loops)
-        expand_reg_kernel<DIM, ORD, YAW, YAW, 2, 4><<<grid, kThreads, 0, st>>>(P, d_nodes, n_nodes, npb, o);
-      else
-        expand_reg_kernel<DIM, ORD, YAW, YAW, 4, 4><<<grid, kThreads, 0, st>>>(P, d_nodes, n_nodes, npb, o);
+      if (short_loops) { if (lat) MPLX_LAUNCH_REG(YAW, 2, true); else MPLX_LAUNCH_REG(YAW, 2, false); }
+      else { if (lat) MPLX_LAUNCH_REG(YAW, 4, true); else MPLX_LAUNCH_REG(YAW, 4, false); }
     }
+#undef MPLX_LAUNCH_REG
     return cudaGetLastError();
   }
   using L = FlatLayout<DIM, ORD, YAW>;
