@@ -15,6 +15,7 @@
 // that chunk k's results cross PCIe while chunk k+1 is expanded.
 #include <cuda_runtime.h>
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <vector>
@@ -93,7 +94,10 @@ extern "C" int mplx_expand_packed(mplx_ctx *c, const mplx_waypoint *nodes, int n
   if (nU > 65535) return fail(MPLX_ERR_ARG, "action ids are uint16 in the packed stream");
   const int drop_inf = (flags & MPLX_PACK_DROP_INF) ? 1 : 0;
 
-  int chunk = (1 << 19) / nU;
+  // successor slots per pipeline chunk (2 chunks in flight); MPLX_PACK_CHUNK_LOG2 overrides for tuning
+  int chunk_log2 = 20;
+  if (const char *e = getenv("MPLX_PACK_CHUNK_LOG2")) chunk_log2 = atoi(e) < 10 ? 10 : (atoi(e) > 26 ? 26 : atoi(e));
+  int chunk = (1 << chunk_log2) / nU;
   if (chunk < 1) chunk = 1;
   if (chunk > n_nodes) chunk = n_nodes;
   const size_t slots = (size_t)chunk * nU;
