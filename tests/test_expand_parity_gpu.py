@@ -279,6 +279,23 @@ def _check_packed(env, sc, orc, nodes, drop_inf):
     g, o = p["cost"][idx], orc["cost"][sel]
     np.testing.assert_array_equal(np.isinf(g), np.isinf(o))
     np.testing.assert_allclose(g[~np.isinf(o)], o[~np.isinf(o)], rtol=1e-6, atol=0)
+    # the documented reconstruction rule (include/mplx.h, mplx_packed_out): state fields from the
+    # record, the first derivative above the state order = 0 + U[action], higher ones 0, yaw 0
+    # without a yaw control, t = parent.t + dt  ==>  the full successor Waypoint, bit for bit
+    nf = len(fields)
+    full = np.zeros(len(idx), dtype=ob.WAYPOINT_DTYPE)
+    st = p["state"][idx]
+    act = p["action"][idx].astype(np.int64)
+    for f_i, name in enumerate(["pos", "vel", "acc", "jrk"]):
+        if f_i < nf:
+            full[name][:, :D] = st[:, f_i * D:(f_i + 1) * D]
+        elif f_i == nf:
+            full[name][:, :D] = 0.0 + sc.U[act][:, :D]
+    if sc.control & 16:
+        full["yaw"] = st[:, nf * D]
+    parent = np.repeat(np.arange(len(nodes)), p["count"])
+    full["t"] = nodes["t"][parent] + sc.T
+    assert full.tobytes() == orc["succ"][sel].tobytes()
 
 
 def test_packed_stream_matches_oracle():
