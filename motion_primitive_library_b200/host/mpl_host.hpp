@@ -25,6 +25,7 @@
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
+#include <deque>
 #include <limits>
 #include <memory>
 #include <stdexcept>
@@ -476,9 +477,14 @@ template <int Dim>
 struct State {
   Waypoint<Dim> coord;
   std::size_t key;
-  std::vector<std::size_t> pred_key;
-  std::vector<int> pred_action_id;
-  std::vector<decimal_t> pred_action_cost;
+  /// pred_coord / pred_action_id / pred_action_cost of the reference (state_space.h:47-52), kept as
+  /// one array of records (a predecessor is identified by its lattice key)
+  struct Pred {
+    State *node;
+    decimal_t action_cost;
+    int action_id;
+  };
+  std::vector<Pred> pred;
   int heap_idx = -1;
   decimal_t fval = 0;
   decimal_t g = std::numeric_limits<decimal_t>::infinity();
@@ -537,7 +543,13 @@ class PriorityQueue {
 template <int Dim>
 struct StateSpace {
   PriorityQueue<Dim> pq_;
-  std::unordered_map<std::size_t, std::unique_ptr<State<Dim>>> hm_;
+  /// hashMap (state_space.h:77-79): key -> state; the states live in an arena owned by the space
+  std::unordered_map<std::size_t, State<Dim> *> hm_;
+  std::deque<State<Dim>> arena_;
+  State<Dim> *make_state(const Waypoint<Dim> &c, std::size_t k) {
+    arena_.emplace_back(c, k);
+    return &arena_.back();
+  }
   decimal_t eps_;
   decimal_t dt_{1};
   std::vector<State<Dim> *> best_child_;
@@ -572,9 +584,9 @@ class AstarStepper {
       return;
     }
     if (ss_ptr->pq_.empty()) {
-      auto &slot = ss_ptr->hm_[start_key_];
-      slot.reset(new S(start_coord, start_key_));
-      S *n = slot.get();
+      S *&slot = ss_ptr->hm_[start_key_];
+      slot = ss_ptr->make_state(start_coord, start_key_);
+      S *n = slot;
       n->g = 0;
       n->h = ss_ptr->eps_ == 0 ? 0 : ENV->get_heur(start_coord);
       n->fval = n->g + ss_ptr->eps_ * n->h;
@@ -602,15 +614,13 @@ class AstarStepper {
     for (int s = 0; s < n_succ; ++s) {
       if (std::isinf(succ_cost[s])) continue;  // graph_search.h:81
       const std::size_t skey = key_at(s);
-      auto &slot = ss_ptr->hm_[skey];
+      S *&slot = ss_ptr->hm_[skey];
       if (!slot) {
-        slot.reset(new S(succ_at(s), skey));
+        slot = ss_ptr->make_state(succ_at(s), skey);
         slot->h = ss_ptr->eps_ == 0 ? 0 : ENV->get_heur(slot->coord);
       }
-      S *succNode_ptr = slot.get();
-      succNode_ptr->pred_key.push_back(curr_->key);
-      succNode_ptr->pred_action_cost.push_back(succ_cost[s]);
-      succNode_ptr->pred_action_id.push_back(succ_act_id[s]);
+      S *succNode_ptr = slot;
+      succNode_ptr->pred.push_back(typename S::Pred{curr_, succ_cost[s], succ_act_id[s]});
       const decimal_t tentative_gval = curr_->g + succ_cost[s];
       if (tentative_gval < succNode_ptr->g) {
         succNode_ptr->g = tentative_gval;
@@ -652,18 +662,18 @@ class AstarStepper {
     ss_ptr->best_child_.clear();
     bool find_traj = false;
     std::vector<Edge<Dim>> prs;
-    while (!currNode_ptr->pred_key.empty()) {
+    while (!currNode_ptr->pred.empty()) {
       ss_ptr->best_child_.push_back(currNode_ptr);
       int min_id = -1;
       decimal_t min_rhs = inf, min_g = inf;
-      for (unsigned int i = 0; i < currNode_ptr->pred_key.size(); i++) {
-        S *pred = ss_ptr->hm_[currNode_ptr->pred_key[i]].get();
-        if (min_rhs > pred->g + currNode_ptr->pred_action_cost[i]) {
-          min_rhs = pred->g + currNode_ptr->pred_action_cost[i];
+      for (unsigned int i = 0; i < currNode_ptr->pred.size(); i++) {
+        const S *pred = currNode_ptr->pred[i].node;
+        const decimal_t ac = currNode_ptr->pred[i].action_cost;
+        if (min_rhs > pred->g + ac) {
+          min_rhs = pred->g + ac;
           min_g = pred->g;
           min_id = i;
-        } else if (!std::isinf(currNode_ptr->pred_action_cost[i]) &&
-                   min_rhs == pred->g + currNode_ptr->pred_action_cost[i]) {
+        } else if (!std::isinf(ac) && min_rhs == pred->g + ac) {
           if (min_g < pred->g) {
             min_g = pred->g;
             min_id = i;
@@ -671,8 +681,8 @@ class AstarStepper {
         }
       }
       if (min_id >= 0) {
-        int action_idx = currNode_ptr->pred_action_id[min_id];
-        currNode_ptr = ss_ptr->hm_[currNode_ptr->pred_key[min_id]].get();
+        int action_idx = currNode_ptr->pred[min_id].action_id;
+        currNode_ptr = currNode_ptr->pred[min_id].node;
         prs.push_back(Edge<Dim>{currNode_ptr->coord, action_idx});  // forward_action(coord, action): env_base.h:228-231
       } else
         break;
@@ -755,12 +765,12 @@ class PlannerBase {
   /// getCloseSet (planner_base.h): states with iterationclosed
   std::vector<const State<Dim> *> getCloseSetStates() const {
     std::vector<const State<Dim> *> v;
-    for (const auto &it : ss_ptr_->hm_) if (it.second && it.second->iterationclosed) v.push_back(it.second.get());
+    for (const auto &st : ss_ptr_->arena_) if (st.iterationclosed) v.push_back(&st);
     return v;
   }
   std::size_t getOpenSetSize() const {
     std::size_t n = 0;
-    for (const auto &it : ss_ptr_->hm_) if (it.second && it.second->iterationopened && !it.second->iterationclosed) n++;
+    for (const auto &st : ss_ptr_->arena_) if (st.iterationopened && !st.iterationclosed) n++;
     return n;
   }
   void setVmax(decimal_t v) { ENV_->set_v_max(v); }
@@ -1034,7 +1044,7 @@ class MultiQueryPlanner {
       res[q].valid = !std::isinf(res[q].cost);
       res[q].expanded = st[q]->expanded();
       for (const auto &e : traj) res[q].actions.push_back(e.action_id);
-      for (const auto &it : ss[q]->hm_) if (it.second && it.second->iterationclosed) res[q].n_closed++;
+      for (const auto &stt : ss[q]->arena_) if (stt.iterationclosed) res[q].n_closed++;
     }
     return res;
   }
