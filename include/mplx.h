@@ -171,6 +171,27 @@ typedef struct {
 int mplx_expand_packed(mplx_ctx *ctx, const mplx_waypoint *nodes, int n_nodes, int flags,
                        mplx_packed_out *out);
 
+/* ---- stored-edge re-validation (the incremental / LPA* callers of the path) ------------ */
+/* An edge of the search graph is (parent state, action id): pr = Primitive(parent, U[action], dt)
+ * (env_base::forward_action, include/mpl_planner/common/env_base.h:228-231).  Host buffers. */
+
+/* env_map<Dim>::is_free(const Primitive&) (include/mpl_planner/env/env_map.h:60-76) for n_edges
+ * edges: out_free[e] = 1 iff none of the n+1 samples of pr.sample(n), n = ceil(max_v*T/res)
+ * (primitive.h:415-420), is occupied, outside the map or outside the search region.  out_cost
+ * (NULL or n_edges doubles) receives calculate_intrinsic_cost(pr) (env_base.h:343-345), the cost
+ * StateSpace::decreaseCost installs for a re-opened edge (state_space.h:236-243). */
+int mplx_edges_is_free(mplx_ctx *ctx, const mplx_waypoint *parents, const int32_t *actions, int n_edges,
+                       uint8_t *out_free, double *out_cost);
+
+/* The voxel walk of MapPlanner<Dim>::getLinkedNodes (src/mpl_planner/map_planner.cpp:135-151): for
+ * edge e the cells floatToInt(w.pos) of the samples w of pr.sample(n), an entry being emitted
+ * whenever getIndex differs from the previous sample's.  Edge e owns entries
+ * [out_offset[e], out_offset[e+1]) of out_cells, ctx-dim int32 each; out_offset has n_edges+1
+ * entries and *out_total = out_offset[n_edges].  If capacity (entries) is too small the call fails
+ * with MPLX_ERR_ARG after filling out_offset and *out_total, so the caller can size and retry. */
+int mplx_edges_cells(mplx_ctx *ctx, const mplx_waypoint *parents, const int32_t *actions, int n_edges,
+                     int64_t *out_offset, int32_t *out_cells, int64_t capacity, int64_t *out_total);
+
 /* Kernel selection (diagnostics): 0 = auto (the register kernel whenever |U| <= 256),
  * 1 = the sequential kernel that keeps traverse_primitive's literal per-primitive loop
  * (env_map.h:99-130), 2 = the register kernel, 3 = the flat (sample-parallel, shared-memory

@@ -40,6 +40,8 @@ EXPORTED_SYMBOLS = (
     "mplx_expand",
     "mplx_expand_device",
     "mplx_expand_packed",
+    "mplx_edges_is_free",
+    "mplx_edges_cells",
     "mplx_set_kernel",
     "mplx_sync",
     "mplx_launch_count",
@@ -131,6 +133,10 @@ def load() -> C.CDLL:
     lib.mplx_expand_device.restype = i32
     lib.mplx_expand_packed.argtypes = [vp, vp, i32, i32, C.POINTER(PackedOut)]
     lib.mplx_expand_packed.restype = i32
+    lib.mplx_edges_is_free.argtypes = [vp, vp, vp, i32, vp, vp]
+    lib.mplx_edges_is_free.restype = i32
+    lib.mplx_edges_cells.argtypes = [vp, vp, vp, i32, vp, vp, C.c_int64, C.POINTER(C.c_int64)]
+    lib.mplx_edges_cells.restype = i32
     lib.mplx_set_kernel.argtypes = [vp, i32]
     lib.mplx_set_kernel.restype = i32
     lib.mplx_sync.argtypes = [vp]

@@ -103,7 +103,7 @@ int mplx_destroy(mplx_ctx *c) {
   cudaStreamSynchronize(c->stream);
   c->map.release(); c->pot.release(); c->region.release(); c->U.release(); c->stats.release();
   c->occ.release(); c->ttab.release(); c->tcount.release(); c->tdt.release();
-  c->cb[0].release(); c->cb[1].release();
+  c->cb[0].release(); c->cb[1].release(); c->eb.release();
   c->d_nodes.release(); c->d_succ.release(); c->d_count.release(); c->d_action.release();
   c->d_lattice.release(); c->d_cost.release(); c->d_key.release();
   c->h_nodes.release(); c->h_succ.release(); c->h_count.release(); c->h_action.release();

@@ -101,6 +101,19 @@ struct ChunkBufs {
   }
 };
 
+// staging of the edge re-validation queries (mplx_edges.cu)
+struct EdgeBufs {
+  DevBuf<mplx_waypoint> parents;
+  DevBuf<int32_t> actions, cells;
+  DevBuf<uint8_t> free_, scan_tmp;
+  DevBuf<double> cost;
+  DevBuf<long long> count, offset;
+  void release() {
+    parents.release(); actions.release(); cells.release(); free_.release(); scan_tmp.release(); cost.release();
+    count.release(); offset.release();
+  }
+};
+
 struct mplx_ctx {
   int dim = 0, device = 0;
   cudaStream_t stream = nullptr;
@@ -124,6 +137,7 @@ struct mplx_ctx {
   PinBuf<double> h_cost;
   PinBuf<uint64_t> h_key;
   ChunkBufs cb[2];
+  EdgeBufs eb;
   int64_t launches = 0;
   unsigned long long last_stats[2] = {0, 0};
 };

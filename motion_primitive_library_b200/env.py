@@ -285,6 +285,45 @@ class env_map:
         e = self.expand(node)
         return e.node(0)
 
+    def is_free_edges(self, parents: np.ndarray, actions: np.ndarray):
+        """env_map::is_free(pr) (env_map.h:60-76) for the stored edges pr = Primitive(parents[i],
+        U[actions[i]], dt), batched on the device.  Returns (free uint8[n], intrinsic cost[n]);
+        the cost is what StateSpace::decreaseCost installs for a re-opened edge (state_space.h:243)."""
+        self._sync_params()
+        parents = np.ascontiguousarray(parents, dtype=WAYPOINT_DTYPE).reshape(-1)
+        actions = np.ascontiguousarray(actions, dtype=np.int32).reshape(-1)
+        if actions.size != parents.size:
+            raise ValueError("one action id per parent state")
+        free = np.zeros(parents.size, dtype=np.uint8)
+        cost = np.zeros(parents.size, dtype=np.float64)
+        abi.check(self._lib.mplx_edges_is_free(self._h, parents.ctypes.data, actions.ctypes.data, parents.size,
+                                               free.ctypes.data, cost.ctypes.data))
+        return free, cost
+
+    def edge_cells(self, parents: np.ndarray, actions: np.ndarray):
+        """The voxel walk of MapPlanner::getLinkedNodes (map_planner.cpp:135-151) for stored edges:
+        returns (offset int64[n+1], cells int32[total, Dim]); edge i passes through
+        cells[offset[i]:offset[i+1]] (consecutive repeats removed)."""
+        self._sync_params()
+        parents = np.ascontiguousarray(parents, dtype=WAYPOINT_DTYPE).reshape(-1)
+        actions = np.ascontiguousarray(actions, dtype=np.int32).reshape(-1)
+        if actions.size != parents.size:
+            raise ValueError("one action id per parent state")
+        n = parents.size
+        off = np.zeros(n + 1, dtype=np.int64)
+        total = C.c_int64(0)
+        cap = max(1, 8 * n)
+        for _ in range(2):
+            cells = np.zeros((cap, self.Dim), dtype=np.int32)
+            rc = self._lib.mplx_edges_cells(self._h, parents.ctypes.data, actions.ctypes.data, n, off.ctypes.data,
+                                            cells.ctypes.data, cap, C.byref(total))
+            if rc == 0:
+                return off, cells[: total.value]
+            if total.value <= cap:
+                abi.check(rc)
+            cap = int(total.value)
+        abi.check(rc)
+
     def set_kernel(self, which: int):
         """0 = auto (register kernel), 1 = literal sequential loop, 2 = register kernel, 3 = flat kernel."""
         abi.check(self._lib.mplx_set_kernel(self._h, int(which)))

@@ -560,6 +560,54 @@ int get_succ(const orc_env *e, const orc_waypoint *curr_, orc_waypoint *succ, do
   return n_out;
 }
 
+/* env_map<Dim>::is_free(const Primitive&): include/mpl_planner/env/env_map.h:60-76, with
+ * Primitive::sample(N) (primitive.h:415-420): N+1 samples at i*(t_/N), no lower bound on N. */
+inline bool is_free_primitive(const orc_env *e, const Prim &pr) {
+  double max_v = 0;
+  for (int i = 0; i < e->dim; i++) {
+    if (pr.max_vel(i) > max_v) max_v = pr.max_vel(i);
+  }
+  int n = std::ceil(max_v * pr.t_ / e->res);
+  const double dt = pr.t_ / n;
+  for (int i = 0; i <= n; i++) {
+    const WP pt = pr.evaluate(i * dt);
+    int pn[3] = {0, 0, 0};
+    floatToInt(e, pt.pos, pn);
+    /* isOccupied(pn) || isOutside(pn): map_util.h:51-55,64-69 */
+    if (isOutside(e, pn)) return false;
+    const int64_t idx = getIndex(e, pn);
+    if (e->map[idx] == 100) return false;
+    if (e->region && !e->region[idx]) return false;
+  }
+  return true;
+}
+
+/* inner loop of MapPlanner<Dim>::getLinkedNodes: src/mpl_planner/map_planner.cpp:135-151 */
+inline int64_t linked_cells(const orc_env *e, const Prim &pr, int32_t *out, int64_t room) {
+  double max_v = 0;
+  for (int i = 0; i < e->dim; i++) max_v = std::max(max_v, pr.max_vel(i));
+  int n = 1.0 * std::ceil(max_v * pr.t_ / e->res);
+  int prev_id = -1;
+  int64_t k = 0;
+  const double dt = pr.t_ / n;
+  for (int i = 0; i <= n; i++) {
+    const WP w = pr.evaluate(i * dt);
+    int pn[3] = {0, 0, 0};
+    floatToInt(e, w.pos, pn);
+    /* getIndex in the reference's int arithmetic (map_util.h:34-41), no bounds test here */
+    unsigned uid = (unsigned)pn[0] + (unsigned)e->mdim[0] * (unsigned)pn[1];
+    if (e->dim == 3) uid += (unsigned)e->mdim[0] * (unsigned)e->mdim[1] * (unsigned)pn[2];
+    const int id = (int)uid;
+    if (id != prev_id) {
+      if (out && k < room)
+        for (int d = 0; d < e->dim; d++) out[k * e->dim + d] = pn[d];
+      k++;
+      prev_id = id;
+    }
+  }
+  return k;
+}
+
 }  // namespace
 
 extern "C" {
@@ -651,4 +699,29 @@ double orc_max_vel(const orc_env *env, const orc_waypoint *curr, int control_idx
 }
 
 int64_t orc_last_samples(void) { return g_samples; }
+
+int orc_edges_is_free(const orc_env *env, const orc_waypoint *parents, const int32_t *actions, int n,
+                      uint8_t *out_free, double *out_cost) {
+  for (int i = 0; i < n; i++) {
+    const WP c = to_wp(&parents[i], env->control);
+    Prim pr(env->dim, c, env->U + (size_t)actions[i] * env->udim, env->T); /* forward_action: env_base.h:228-231 */
+    out_free[i] = is_free_primitive(env, pr) ? 1 : 0;
+    if (out_cost) out_cost[i] = pr.J(pr.control_) + env->w * env->T; /* env_base.h:343-345 */
+  }
+  return 0;
+}
+
+int64_t orc_edges_cells(const orc_env *env, const orc_waypoint *parents, const int32_t *actions, int n,
+                        int64_t *out_offset, int32_t *out_cells, int64_t capacity) {
+  int64_t total = 0;
+  for (int i = 0; i < n; i++) {
+    const WP c = to_wp(&parents[i], env->control);
+    Prim pr(env->dim, c, env->U + (size_t)actions[i] * env->udim, env->T);
+    out_offset[i] = total;
+    total += linked_cells(env, pr, out_cells ? out_cells + total * env->dim : nullptr,
+                          capacity > total ? capacity - total : 0);
+  }
+  out_offset[n] = total;
+  return total;
+}
 }

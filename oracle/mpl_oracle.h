@@ -77,6 +77,16 @@ int orc_sample_count(double T, int n); /* iterations of for(t=0;t<T;t+=T/n) */
 double orc_max_vel(const orc_env *env, const orc_waypoint *curr, int control_idx, int axis);
 int64_t orc_last_samples(void); /* samples visited by the last orc_get_succ on this thread */
 
+/* Stored-edge queries of the incremental planner: edge = Primitive(parents[i], U[actions[i]], T).
+ * orc_edges_is_free: env_map::is_free(pr) (env_map.h:60-76) and, optionally, the intrinsic cost
+ * (env_base.h:343-345).  orc_edges_cells: the voxel walk of MapPlanner::getLinkedNodes
+ * (map_planner.cpp:135-151); entries of edge i are [out_offset[i], out_offset[i+1]) of out_cells
+ * (dim int32 each); returns the total (entries beyond capacity are counted, not written). */
+int orc_edges_is_free(const orc_env *env, const orc_waypoint *parents, const int32_t *actions, int n,
+                      uint8_t *out_free, double *out_cost);
+int64_t orc_edges_cells(const orc_env *env, const orc_waypoint *parents, const int32_t *actions, int n,
+                        int64_t *out_offset, int32_t *out_cells, int64_t capacity);
+
 #ifdef __cplusplus
 }
 #endif

@@ -151,6 +151,28 @@ int timed(const orc_env *e, const orc_waypoint *nodes, int n, int nthreads, int6
   if (seconds) *seconds = std::chrono::duration<double>(t1 - t0).count();
   return 0;
 }
+
+template <int Dim>
+int edges_free(const orc_env *e, const orc_waypoint *parents, const int32_t *actions, int n, uint8_t *out_free,
+               double *out_cost) {
+  Ref<Dim> r(e);
+  for (int i = 0; i < n; i++) {
+    Waypoint<Dim> curr((Control::Control)e->control);
+    for (int k = 0; k < Dim; k++) {
+      curr.pos(k) = parents[i].pos[k];
+      curr.vel(k) = parents[i].vel[k];
+      curr.acc(k) = parents[i].acc[k];
+      curr.jrk(k) = parents[i].jrk[k];
+    }
+    curr.yaw = parents[i].yaw;
+    curr.t = parents[i].t;
+    Primitive<Dim> pr;
+    r.env->forward_action(curr, actions[i], pr);
+    out_free[i] = r.env->is_free(pr) ? 1 : 0;
+    if (out_cost) out_cost[i] = r.env->calculate_intrinsic_cost(pr);
+  }
+  return 0;
+}
 }  // namespace
 
 extern "C" {
@@ -163,6 +185,13 @@ int ref_expand_batch_timed(const orc_env *e, const orc_waypoint *nodes, int n, i
                            double *seconds) {
   return e->dim == 2 ? timed<2>(e, nodes, n, nthreads, total_succ, seconds)
                      : timed<3>(e, nodes, n, nthreads, total_succ, seconds);
+}
+// env_map::is_free(pr) and calculate_intrinsic_cost(pr) of the reference for stored edges
+// (parent, action): pr built by env_base::forward_action (env_base.h:228-231).
+int ref_edges_is_free(const orc_env *e, const orc_waypoint *parents, const int32_t *actions, int n,
+                      uint8_t *out_free, double *out_cost) {
+  return e->dim == 2 ? edges_free<2>(e, parents, actions, n, out_free, out_cost)
+                     : edges_free<3>(e, parents, actions, n, out_free, out_cost);
 }
 const char *ref_info(void) {
   return "unmodified /root/reference/include headers (env_map.h, env_base.h, primitive.h, waypoint.h, math.h, "

@@ -60,6 +60,10 @@ def lib():
         L.orc_max_vel.restype = C.c_double
         L.orc_last_samples.argtypes = []
         L.orc_last_samples.restype = C.c_int64
+        L.orc_edges_is_free.argtypes = [C.POINTER(OrcEnv), vp, vp, C.c_int, vp, vp]
+        L.orc_edges_is_free.restype = C.c_int
+        L.orc_edges_cells.argtypes = [C.POINTER(OrcEnv), vp, vp, C.c_int, vp, vp, C.c_int64]
+        L.orc_edges_cells.restype = C.c_int64
         _lib = L
     return _lib
 
@@ -115,6 +119,29 @@ class OracleEnv:
         c = int(r["count"][0])
         return {k: (v[:c] if isinstance(v, np.ndarray) and k != "count" else v) for k, v in r.items()}
 
+    def edges_is_free(self, parents, actions):
+        """env_map::is_free(pr) + calculate_intrinsic_cost(pr) for stored edges (parent, action)."""
+        parents = np.ascontiguousarray(parents, dtype=WAYPOINT_DTYPE).reshape(-1)
+        actions = np.ascontiguousarray(actions, dtype=np.int32).reshape(-1)
+        free = np.zeros(parents.size, dtype=np.uint8)
+        cost = np.zeros(parents.size)
+        lib().orc_edges_is_free(C.byref(self.e), parents.ctypes.data, actions.ctypes.data, parents.size,
+                                free.ctypes.data, cost.ctypes.data)
+        return free, cost
+
+    def edges_cells(self, parents, actions):
+        """The getLinkedNodes voxel walk per edge: (offset[n+1], cells[total, dim])."""
+        parents = np.ascontiguousarray(parents, dtype=WAYPOINT_DTYPE).reshape(-1)
+        actions = np.ascontiguousarray(actions, dtype=np.int32).reshape(-1)
+        dim = int(self.e.dim)
+        off = np.zeros(parents.size + 1, dtype=np.int64)
+        total = lib().orc_edges_cells(C.byref(self.e), parents.ctypes.data, actions.ctypes.data, parents.size,
+                                      off.ctypes.data, None, 0)
+        cells = np.zeros((total, dim), dtype=np.int32)
+        lib().orc_edges_cells(C.byref(self.e), parents.ctypes.data, actions.ctypes.data, parents.size,
+                              off.ctypes.data, cells.ctypes.data, total)
+        return off, cells
+
     def timed(self, nodes, nthreads=1):
         nodes = np.ascontiguousarray(nodes, dtype=WAYPOINT_DTYPE).reshape(-1)
         a, b, s = C.c_int64(), C.c_int64(), C.c_double()
@@ -154,6 +181,8 @@ def ref_lib():
         L.ref_expand_batch_timed.restype = C.c_int
         L.ref_info.argtypes = []
         L.ref_info.restype = C.c_char_p
+        L.ref_edges_is_free.argtypes = [C.POINTER(OrcEnv), vp, vp, C.c_int, vp, vp]
+        L.ref_edges_is_free.restype = C.c_int
         _ref = L
     return _ref
 
@@ -170,6 +199,17 @@ def ref_expand(env: "OracleEnv", nodes, nthreads=1):
     ref_lib().ref_expand_batch(C.byref(env.e), nodes.ctypes.data, n, succ.ctypes.data, cost.ctypes.data,
                                action.ctypes.data, key.ctypes.data, count.ctypes.data, nthreads)
     return dict(count=count, succ=succ, cost=cost, action=action, key=key, lattice=None, nU=nU)
+
+
+def ref_edges_is_free(env: "OracleEnv", parents, actions):
+    """The REFERENCE's env_map::is_free(pr) / calculate_intrinsic_cost(pr) for stored edges."""
+    parents = np.ascontiguousarray(parents, dtype=WAYPOINT_DTYPE).reshape(-1)
+    actions = np.ascontiguousarray(actions, dtype=np.int32).reshape(-1)
+    free = np.zeros(parents.size, dtype=np.uint8)
+    cost = np.zeros(parents.size)
+    ref_lib().ref_edges_is_free(C.byref(env.e), parents.ctypes.data, actions.ctypes.data, parents.size,
+                                free.ctypes.data, cost.ctypes.data)
+    return free, cost
 
 
 def ref_timed(env: "OracleEnv", nodes, nthreads=1):
