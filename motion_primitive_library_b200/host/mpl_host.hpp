@@ -217,6 +217,20 @@ class env_base {
   ///  - prefetch(cands, keys): the open nodes the search is likely to pop next;
   ///  - last_succ_keys(): lattice keys of the successors returned by the last get_succ call, if the
   ///    env already has them (the device computes them); nullptr = hash on the host.
+  /// Stored-edge queries of the incremental planner, batched.  Edge k is the primitive
+  /// forward_action(parents[k], actions[k]) (env_base.h:228-231):
+  ///  - is_free_edges: is_free(pr) (env_base.h:338-341, env_map.h:60-76) and
+  ///    calculate_intrinsic_cost(pr) (env_base.h:343-345) per edge;
+  ///  - edge_cells: the cells getLinkedNodes visits along each edge (map_planner.cpp:135-151),
+  ///    edge k owning cells[offset[k]*Dim .. offset[k+1]*Dim).
+  virtual void is_free_edges(const vec_E<Waypoint<Dim>> &, const std::vector<int> &, std::vector<uint8_t> &,
+                             std::vector<decimal_t> &) const {
+    throw std::runtime_error("this env does not serve edge re-validation");
+  }
+  virtual void edge_cells(const vec_E<Waypoint<Dim>> &, const std::vector<int> &, std::vector<long long> &,
+                          std::vector<int> &) const {
+    throw std::runtime_error("this env does not serve edge re-validation");
+  }
   virtual bool wants_candidates(std::size_t) const { return false; }
   virtual void prefetch(const vec_E<Waypoint<Dim>> &, const std::vector<std::size_t> &) const {}
   virtual const std::size_t *last_succ_keys() const { return nullptr; }
@@ -341,6 +355,36 @@ class env_map_gpu : public env_map_host<Dim> {
     check(mplx_set_search_region_path(ctx_, flat.data(), (int)path.size(), radius.d, dense ? 1 : 0, out.data()));
     this->search_region_.assign(out.begin(), out.end());
     region_on_device_ = true;
+  }
+
+  /// env_map::is_free(pr) for stored edges on the device (mplx_edges_is_free)
+  void is_free_edges(const vec_E<Waypoint<Dim>> &parents, const std::vector<int> &actions, std::vector<uint8_t> &free,
+                     std::vector<decimal_t> &cost) const override {
+    sync();
+    std::vector<mplx_waypoint> in(parents.size());
+    for (std::size_t i = 0; i < parents.size(); i++) in[i] = to_pod(parents[i]);
+    free.assign(parents.size(), 0);
+    cost.assign(parents.size(), 0);
+    check(mplx_edges_is_free(ctx_, in.data(), actions.data(), (int)parents.size(), free.data(), cost.data()));
+  }
+  /// the getLinkedNodes voxel walk for stored edges on the device (mplx_edges_cells)
+  void edge_cells(const vec_E<Waypoint<Dim>> &parents, const std::vector<int> &actions, std::vector<long long> &offset,
+                  std::vector<int> &cells) const override {
+    sync();
+    std::vector<mplx_waypoint> in(parents.size());
+    for (std::size_t i = 0; i < parents.size(); i++) in[i] = to_pod(parents[i]);
+    offset.assign(parents.size() + 1, 0);
+    int64_t total = 0;
+    cells.resize(std::max<std::size_t>(1, 16 * parents.size()) * Dim);
+    int rc = mplx_edges_cells(ctx_, in.data(), actions.data(), (int)parents.size(), (int64_t *)offset.data(), cells.data(),
+                              (int64_t)(cells.size() / Dim), &total);
+    if (rc != MPLX_OK && total > (int64_t)(cells.size() / Dim)) {  // sized from the reported total
+      cells.resize((std::size_t)total * Dim);
+      rc = mplx_edges_cells(ctx_, in.data(), actions.data(), (int)parents.size(), (int64_t *)offset.data(), cells.data(),
+                            total, &total);
+    }
+    check(rc);
+    cells.resize((std::size_t)total * Dim);
   }
 
   /// Packed batched expansion for lock-step drivers (mplx_expand_packed, +inf successors dropped
@@ -485,8 +529,16 @@ struct State {
     int action_id;
   };
   std::vector<Pred> pred;
+  /// succ_coord / succ_action_id / succ_action_cost (state_space.h:40-45), LPA* only.  The
+  /// successor is looked up again by its lattice key when the node is re-expanded (hm_[succ_coord],
+  /// graph_search.h:282), so a state pruned from the space in between is re-created, as there.
+  struct Succ {
+    State *node;
+    decimal_t action_cost;
+    int action_id;
+  };
+  std::vector<Succ> succ;
   int heap_idx = -1;
-  decimal_t fval = 0;
   decimal_t g = std::numeric_limits<decimal_t>::infinity();
   decimal_t rhs = std::numeric_limits<decimal_t>::infinity();
   decimal_t h = std::numeric_limits<decimal_t>::infinity();
@@ -495,33 +547,47 @@ struct State {
 };
 
 /// priorityQueue: boost::heap::d_ary_heap<pair<f, State*>, arity<2>, mutable_<true>,
-/// compare<compare_pair>> (state_space.h:16-34) restated: binary heap with position handles;
-/// push = append + sift up, pop = swap root with last + sift down, increase = sift up; a child
-/// replaces its parent unless it compares strictly lower.
+/// compare<compare_pair>> (state_space.h:16-34) restated: binary heap of (key, state) pairs with
+/// position handles; push = append + sift up, pop = swap root with last + sift down, increase =
+/// sift up, erase = move the element to the root, then pop; a child replaces its parent unless it
+/// compares strictly lower.
 template <int Dim>
 class PriorityQueue {
  public:
   using S = State<Dim>;
-  /// compare_pair (state_space.h:16-27): true when p1 has LOWER priority than p2
-  static bool lower(const S *p1, const S *p2) {
-    if (p1->fval == p2->fval) return std::min(p1->g, p1->rhs) > std::min(p2->g, p2->rhs);
-    return p1->fval > p2->fval;
+  using Item = std::pair<decimal_t, S *>;
+  /// compare_pair (state_space.h:16-27): true when p1 has LOWER priority than p2; ties on the key
+  /// are broken on the states' current min(g, rhs)
+  static bool lower(const Item &p1, const Item &p2) {
+    if (p1.first == p2.first) return std::min(p1.second->g, p1.second->rhs) > std::min(p2.second->g, p2.second->rhs);
+    return p1.first > p2.first;
   }
   bool empty() const { return q_.empty(); }
   std::size_t size() const { return q_.size(); }
-  S *top() const { return q_.front(); }
-  const std::vector<S *> &raw() const { return q_; }
-  void push(S *s) { s->heap_idx = (int)q_.size(); q_.push_back(s); siftup(s->heap_idx); }
+  const Item &top() const { return q_.front(); }
+  const std::vector<Item> &raw() const { return q_; }
+  void clear() { q_.clear(); }
+  void push(decimal_t key, S *s) { s->heap_idx = (int)q_.size(); q_.emplace_back(key, s); siftup(s->heap_idx); }
   void pop() {
     swap_at(0, (int)q_.size() - 1);
-    q_.back()->heap_idx = -1;
+    q_.back().second->heap_idx = -1;
     q_.pop_back();
     if (!q_.empty()) siftdown(0);
   }
-  void increase(S *s) { siftup(s->heap_idx); }
+  /// (*heapkey).first = key; pq_.increase(heapkey)  (graph_search.h:118-119)
+  void increase(S *s, decimal_t key) { q_[s->heap_idx].first = key; siftup(s->heap_idx); }
+  void erase(S *s) {
+    int i = s->heap_idx;
+    while (i != 0) {
+      const int p = (i - 1) / 2;
+      swap_at(p, i);
+      i = p;
+    }
+    pop();
+  }
 
  private:
-  void swap_at(int a, int b) { std::swap(q_[a], q_[b]); q_[a]->heap_idx = a; q_[b]->heap_idx = b; }
+  void swap_at(int a, int b) { std::swap(q_[a], q_[b]); q_[a].second->heap_idx = a; q_[b].second->heap_idx = b; }
   void siftup(int i) {
     while (i != 0) {
       int p = (i - 1) / 2;
@@ -536,25 +602,188 @@ class PriorityQueue {
       if (!lower(q_[c], q_[i])) { swap_at(c, i); i = c; } else return;
     }
   }
-  std::vector<S *> q_;
+  std::vector<Item> q_;
 };
 
-/// StateSpace: state_space.h:81-114 (A* part)
+/// StateSpace: include/mpl_planner/common/state_space.h:81-287
 template <int Dim>
 struct StateSpace {
+  using S = State<Dim>;
   PriorityQueue<Dim> pq_;
-  /// hashMap (state_space.h:77-79): key -> state; the states live in an arena owned by the space
-  std::unordered_map<std::size_t, State<Dim> *> hm_;
-  std::deque<State<Dim>> arena_;
-  State<Dim> *make_state(const Waypoint<Dim> &c, std::size_t k) {
+  /// hashMap (state_space.h:77-79): lattice key -> state.  The states live in an arena owned by the
+  /// space; order_ lists the states of hm_ in insertion order, which is the iteration order this
+  /// planner defines for `for (it : hm_)` (boost::unordered_map leaves it unspecified; the loops
+  /// of getSubStateSpace :184-192 and getLinkedNodes depend on it).
+  std::unordered_map<std::size_t, S *> hm_;
+  std::vector<S *> order_;
+  std::deque<S> arena_;
+  /// hm_[coord] of a key that is not in the map yet: create the state and enter it
+  S *make_state(const Waypoint<Dim> &c, std::size_t k) {
     arena_.emplace_back(c, k);
-    return &arena_.back();
+    S *n = &arena_.back();
+    hm_[k] = n;
+    order_.push_back(n);
+    return n;
+  }
+  S *find(std::size_t k) const {
+    auto it = hm_.find(k);
+    return it == hm_.end() ? nullptr : it->second;
+  }
+  /// `StatePtr &p = hm_[coord]; if (!p) p = make_shared<State>(coord)` (graph_search.h:84-87) with
+  /// one hash-map operation; coord() is only evaluated for a new state
+  template <typename MakeCoord>
+  S *get_or_make(std::size_t k, MakeCoord coord, bool &created) {
+    auto ins = hm_.try_emplace(k, nullptr);
+    created = ins.second;
+    if (created) {
+      arena_.emplace_back(coord(), k);
+      ins.first->second = &arena_.back();
+      order_.push_back(ins.first->second);
+    }
+    return ins.first->second;
   }
   decimal_t eps_;
   decimal_t dt_{1};
-  std::vector<State<Dim> *> best_child_;
+  std::vector<S *> best_child_;
   int expand_iteration_ = 0;
+  /// state_space.h:96-100
+  decimal_t start_t_{0}, start_g_{0}, start_rhs_{0};
   explicit StateSpace(decimal_t eps = 1) : eps_(eps) {}
+
+  /// state_space.h:106-111
+  decimal_t getInitTime() const { return best_child_.empty() ? 0 : best_child_.front()->coord.t; }
+
+  /// calculateKey: state_space.h:283-285
+  decimal_t calculateKey(const S *node) const { return std::min(node->g, node->rhs) + eps_ * node->h; }
+
+  /// updateNode: state_space.h:254-280
+  void updateNode(S *currNode_ptr) {
+    if (currNode_ptr->rhs != start_rhs_) {  // compares VALUES, as the reference does
+      currNode_ptr->rhs = std::numeric_limits<decimal_t>::infinity();
+      for (const auto &pr : currNode_ptr->pred)
+        if (currNode_ptr->rhs > pr.node->g + pr.action_cost) currNode_ptr->rhs = pr.node->g + pr.action_cost;
+    }
+    if (currNode_ptr->iterationopened && !currNode_ptr->iterationclosed) {
+      pq_.erase(currNode_ptr);
+      currNode_ptr->iterationclosed = true;
+    }
+    if (currNode_ptr->g != currNode_ptr->rhs) {
+      pq_.push(calculateKey(currNode_ptr), currNode_ptr);
+      currNode_ptr->iterationopened = true;
+      currNode_ptr->iterationclosed = false;
+    }
+  }
+
+  /// getSubStateSpace: state_space.h:116-197 — re-root the graph at best_child_[time_step]
+  void getSubStateSpace(int time_step) {
+    if (best_child_.empty()) return;
+    const decimal_t inf = std::numeric_limits<decimal_t>::infinity();
+    S *currNode_ptr = best_child_[time_step];
+    start_g_ = currNode_ptr->g;
+    start_rhs_ = currNode_ptr->rhs;
+    start_t_ = currNode_ptr->coord.t;
+    currNode_ptr->pred.clear();
+    for (S *it : order_) {
+      it->g = inf;
+      it->rhs = inf;
+      it->pred.clear();
+    }
+    currNode_ptr->g = start_g_;
+    currNode_ptr->rhs = start_rhs_;
+
+    std::unordered_map<std::size_t, S *> new_hm;
+    std::vector<S *> new_order;
+    PriorityQueue<Dim> epq;
+    epq.push(currNode_ptr->rhs, currNode_ptr);
+    new_hm[currNode_ptr->key] = currNode_ptr;
+    new_order.push_back(currNode_ptr);
+    while (!epq.empty()) {
+      currNode_ptr = epq.top().second;
+      epq.pop();
+      for (std::size_t i = 0; i < currNode_ptr->succ.size(); i++) {
+        const std::size_t skey = currNode_ptr->succ[i].node->key;
+        S *&slot = new_hm[skey];
+        if (!slot) {
+          slot = find(skey);  // hm_[succ_coord]; the reference reports a "critical bug" when absent
+          if (!slot) throw std::logic_error("getSubStateSpace: successor is not in the state space");
+          new_order.push_back(slot);
+        }
+        S *succNode_ptr = slot;
+        int id = -1;
+        for (std::size_t k = 0; k < succNode_ptr->pred.size(); k++)
+          if (succNode_ptr->pred[k].node->key == currNode_ptr->key) { id = (int)k; break; }
+        if (id == -1)
+          succNode_ptr->pred.push_back(typename S::Pred{currNode_ptr, currNode_ptr->succ[i].action_cost,
+                                                        currNode_ptr->succ[i].action_id});
+        const decimal_t tentative_rhs = currNode_ptr->rhs + currNode_ptr->succ[i].action_cost;
+        if (tentative_rhs < succNode_ptr->rhs) {
+          succNode_ptr->rhs = tentative_rhs;
+          if (succNode_ptr->iterationclosed) {
+            succNode_ptr->g = succNode_ptr->rhs;
+            epq.push(succNode_ptr->rhs, succNode_ptr);
+          }
+        }
+      }
+    }
+    hm_.swap(new_hm);
+    order_.swap(new_order);
+    pq_.clear();
+    for (S *it : order_)
+      if (it->iterationopened && !it->iterationclosed) pq_.push(calculateKey(it), it);
+  }
+
+  /// One (state, i-th predecessor) reference: std::pair<Coord, int> of the reference (state_space.h:200,225)
+  using EdgeRef = std::pair<S *, int>;
+
+  /// increaseCost: state_space.h:200-221
+  void increaseCost(const std::vector<EdgeRef> &states) {
+    const decimal_t inf = std::numeric_limits<decimal_t>::infinity();
+    for (const auto &affected_node : states) {
+      S *succNode_ptr = affected_node.first;
+      const int i = affected_node.second;
+      if (!std::isinf(succNode_ptr->pred[i].action_cost)) {
+        succNode_ptr->pred[i].action_cost = inf;
+        updateNode(succNode_ptr);
+        S *parent = succNode_ptr->pred[i].node;
+        const int succ_act_id = succNode_ptr->pred[i].action_id;
+        for (auto &sc : parent->succ)
+          if (succ_act_id == sc.action_id) { sc.action_cost = inf; break; }
+      }
+    }
+  }
+
+  /// decreaseCost: state_space.h:223-251.  is_free(pr) of every still-blocked edge is asked in ONE
+  /// batched query up front (the map does not change during the call, so the answers are the ones
+  /// the reference's per-edge calls would get); the updates are then applied in list order.
+  template <typename Env>
+  void decreaseCost(const std::vector<EdgeRef> &states, const Env &ENV) {
+    vec_E<Waypoint<Dim>> parents;
+    std::vector<int> actions;
+    std::vector<int> slot(states.size(), -1);
+    for (std::size_t k = 0; k < states.size(); k++) {
+      const auto &pr = states[k].first->pred[states[k].second];
+      if (std::isinf(pr.action_cost)) {
+        slot[k] = (int)parents.size();
+        parents.push_back(pr.node->coord);  // forward_action(parent_key, action_id): env_base.h:228-231
+        actions.push_back(pr.action_id);
+      }
+    }
+    std::vector<uint8_t> free;
+    std::vector<decimal_t> cost;
+    if (!parents.empty()) ENV.is_free_edges(parents, actions, free, cost);
+    for (std::size_t k = 0; k < states.size(); k++) {
+      S *succNode_ptr = states[k].first;
+      const int i = states[k].second;
+      if (std::isinf(succNode_ptr->pred[i].action_cost) && free[slot[k]]) {
+        succNode_ptr->pred[i].action_cost = cost[slot[k]];  // calculate_intrinsic_cost(pr)
+        updateNode(succNode_ptr);
+        S *parent = succNode_ptr->pred[i].node;
+        const int succ_act_id = succNode_ptr->pred[i].action_id;
+        for (auto &sc : parent->succ)
+          if (succ_act_id == sc.action_id) { sc.action_cost = succNode_ptr->pred[i].action_cost; break; }
+      }
+    }
+  }
 };
 
 /// One edge of the recovered trajectory (the reference stores Primitive<Dim>; a primitive built
@@ -562,6 +791,50 @@ struct StateSpace {
 /// env_base.h:228-231).
 template <int Dim>
 struct Edge { Waypoint<Dim> from; int action_id; };
+
+/// recoverTraj: graph_search.h:369-455 (shared by Astar and LPAstar)
+template <int Dim>
+bool recoverTraj(State<Dim> *currNode_ptr, StateSpace<Dim> &ss, std::size_t start_key, std::vector<Edge<Dim>> &traj) {
+  using S = State<Dim>;
+  const decimal_t inf = std::numeric_limits<decimal_t>::infinity();
+  ss.best_child_.clear();
+  bool find_traj = false;
+  std::vector<Edge<Dim>> prs;
+  while (!currNode_ptr->pred.empty()) {
+    ss.best_child_.push_back(currNode_ptr);
+    int min_id = -1;
+    decimal_t min_rhs = inf, min_g = inf;
+    for (unsigned int i = 0; i < currNode_ptr->pred.size(); i++) {
+      const S *pred = currNode_ptr->pred[i].node;
+      const decimal_t ac = currNode_ptr->pred[i].action_cost;
+      if (min_rhs > pred->g + ac) {
+        min_rhs = pred->g + ac;
+        min_g = pred->g;
+        min_id = i;
+      } else if (!std::isinf(ac) && min_rhs == pred->g + ac) {
+        if (min_g < pred->g) {
+          min_g = pred->g;
+          min_id = i;
+        }
+      }
+    }
+    if (min_id >= 0) {
+      int action_idx = currNode_ptr->pred[min_id].action_id;
+      currNode_ptr = currNode_ptr->pred[min_id].node;
+      prs.push_back(Edge<Dim>{currNode_ptr->coord, action_idx});  // forward_action(coord, action): env_base.h:228-231
+    } else
+      break;
+    if (currNode_ptr->key == start_key) {
+      ss.best_child_.push_back(currNode_ptr);
+      find_traj = true;
+      break;
+    }
+  }
+  std::reverse(prs.begin(), prs.end());
+  std::reverse(ss.best_child_.begin(), ss.best_child_.end());
+  traj = find_traj ? prs : std::vector<Edge<Dim>>();
+  return find_traj;
+}
 
 /// The A* loop of include/mpl_planner/common/graph_search.h:39-182 cut at the get_succ call, so
 /// that a driver can either run it to completion for one query (GraphSearch::Astar below) or
@@ -584,25 +857,22 @@ class AstarStepper {
       return;
     }
     if (ss_ptr->pq_.empty()) {
-      S *&slot = ss_ptr->hm_[start_key_];
-      slot = ss_ptr->make_state(start_coord, start_key_);
-      S *n = slot;
+      S *n = ss_ptr->make_state(start_coord, start_key_);
       n->g = 0;
       n->h = ss_ptr->eps_ == 0 ? 0 : ENV->get_heur(start_coord);
-      n->fval = n->g + ss_ptr->eps_ * n->h;
-      ss_ptr->pq_.push(n);
+      ss_ptr->pq_.push(n->g + ss_ptr->eps_ * n->h, n);
       n->iterationopened = true;
       n->iterationclosed = false;
     }
     status_ = RUNNING;
   }
   bool active() const { return status_ == RUNNING; }
-  const std::vector<S *> &open_heap() const { return ss_ptr->pq_.raw(); }
+  const std::vector<std::pair<decimal_t, S *>> &open_heap() const { return ss_ptr->pq_.raw(); }
 
   /// graph_search.h:64-68: the node this iteration expands
   const Waypoint<Dim> &pop() {
     expand_iteration_++;
-    curr_ = ss_ptr->pq_.top();
+    curr_ = ss_ptr->pq_.top().second;
     ss_ptr->pq_.pop();
     curr_->iterationclosed = true;
     return curr_->coord;
@@ -614,22 +884,18 @@ class AstarStepper {
     for (int s = 0; s < n_succ; ++s) {
       if (std::isinf(succ_cost[s])) continue;  // graph_search.h:81
       const std::size_t skey = key_at(s);
-      S *&slot = ss_ptr->hm_[skey];
-      if (!slot) {
-        slot = ss_ptr->make_state(succ_at(s), skey);
-        slot->h = ss_ptr->eps_ == 0 ? 0 : ENV->get_heur(slot->coord);
-      }
-      S *succNode_ptr = slot;
+      bool created;
+      S *succNode_ptr = ss_ptr->get_or_make(skey, [&] { return succ_at(s); }, created);
+      if (created) succNode_ptr->h = ss_ptr->eps_ == 0 ? 0 : ENV->get_heur(succNode_ptr->coord);
       succNode_ptr->pred.push_back(typename S::Pred{curr_, succ_cost[s], succ_act_id[s]});
       const decimal_t tentative_gval = curr_->g + succ_cost[s];
       if (tentative_gval < succNode_ptr->g) {
         succNode_ptr->g = tentative_gval;
         const decimal_t fval = succNode_ptr->g + (ss_ptr->eps_) * succNode_ptr->h;
-        succNode_ptr->fval = fval;
         if (succNode_ptr->iterationopened && !succNode_ptr->iterationclosed) {
-          ss_ptr->pq_.increase(succNode_ptr);
+          ss_ptr->pq_.increase(succNode_ptr, fval);
         } else {
-          ss_ptr->pq_.push(succNode_ptr);
+          ss_ptr->pq_.push(fval, succNode_ptr);
           succNode_ptr->iterationopened = true;
         }
       }
@@ -650,54 +916,12 @@ class AstarStepper {
     traj.clear();
     if (status_ == DONE_TRIVIAL) return 0;
     if (status_ != DONE_GOAL) return inf;
-    if (recoverTraj(curr_, traj)) return curr_->g;
+    if (recoverTraj<Dim>(curr_, *ss_ptr, start_key_, traj)) return curr_->g;
     return inf;
   }
   int expanded() const { return expand_iteration_; }
 
  private:
-  /// recoverTraj: graph_search.h:369-455
-  bool recoverTraj(S *currNode_ptr, std::vector<Edge<Dim>> &traj) {
-    const decimal_t inf = std::numeric_limits<decimal_t>::infinity();
-    ss_ptr->best_child_.clear();
-    bool find_traj = false;
-    std::vector<Edge<Dim>> prs;
-    while (!currNode_ptr->pred.empty()) {
-      ss_ptr->best_child_.push_back(currNode_ptr);
-      int min_id = -1;
-      decimal_t min_rhs = inf, min_g = inf;
-      for (unsigned int i = 0; i < currNode_ptr->pred.size(); i++) {
-        const S *pred = currNode_ptr->pred[i].node;
-        const decimal_t ac = currNode_ptr->pred[i].action_cost;
-        if (min_rhs > pred->g + ac) {
-          min_rhs = pred->g + ac;
-          min_g = pred->g;
-          min_id = i;
-        } else if (!std::isinf(ac) && min_rhs == pred->g + ac) {
-          if (min_g < pred->g) {
-            min_g = pred->g;
-            min_id = i;
-          }
-        }
-      }
-      if (min_id >= 0) {
-        int action_idx = currNode_ptr->pred[min_id].action_id;
-        currNode_ptr = currNode_ptr->pred[min_id].node;
-        prs.push_back(Edge<Dim>{currNode_ptr->coord, action_idx});  // forward_action(coord, action): env_base.h:228-231
-      } else
-        break;
-      if (currNode_ptr->key == start_key_) {
-        ss_ptr->best_child_.push_back(currNode_ptr);
-        find_traj = true;
-        break;
-      }
-    }
-    std::reverse(prs.begin(), prs.end());
-    std::reverse(ss_ptr->best_child_.begin(), ss_ptr->best_child_.end());
-    traj = find_traj ? prs : std::vector<Edge<Dim>>();
-    return find_traj;
-  }
-
   enum Status { IDLE, RUNNING, DONE_TRIVIAL, DONE_GOAL, FAILED };
   const env_base<Dim> *ENV;
   std::shared_ptr<StateSpace<Dim>> ss_ptr;
@@ -725,13 +949,13 @@ class GraphSearch {
     std::vector<std::size_t> cand_keys;
     while (st.active()) {
       const auto &raw = st.open_heap();
-      if (lookahead_ > 0 && !raw.empty() && ENV->wants_candidates(raw[0]->key)) {
+      if (lookahead_ > 0 && !raw.empty() && ENV->wants_candidates(raw[0].second->key)) {
         // hint: the open nodes nearest the root of the heap are the likeliest next pops
         cands.clear();
         cand_keys.clear();
         for (std::size_t i = 1; i < raw.size() && (int)cands.size() < lookahead_; i++) {
-          cands.push_back(raw[i]->coord);
-          cand_keys.push_back(raw[i]->key);
+          cands.push_back(raw[i].second->coord);
+          cand_keys.push_back(raw[i].second->key);
         }
         ENV->prefetch(cands, cand_keys);
       }
@@ -744,6 +968,106 @@ class GraphSearch {
     }
     if (verbose_ && std::isinf(st.finish(traj))) printf("[GraphSearch] no trajectory (max expansions or empty queue)\n");
     return st.finish(traj);
+  }
+
+  /// LPAstar: include/mpl_planner/common/graph_search.h:194-365.  +inf successors are kept (they
+  /// may be re-opened by decreaseCost).  An empty queue at entry reads as a +inf top key (the
+  /// reference dereferences pq_.top() there).
+  decimal_t LPAstar(const Waypoint<Dim> &start_coord, const std::shared_ptr<env_base<Dim>> &ENV,
+                    std::shared_ptr<StateSpace<Dim>> &ss_ptr, std::vector<Edge<Dim>> &traj, int max_expand = -1) {
+    using S = State<Dim>;
+    const decimal_t inf = std::numeric_limits<decimal_t>::infinity();
+    traj.clear();
+    if (ENV->is_goal(start_coord)) return 0;
+    const std::size_t start_key = hash_value(start_coord);
+    S *currNode_ptr = ss_ptr->find(start_key);
+    if (!currNode_ptr) {
+      currNode_ptr = ss_ptr->make_state(start_coord, start_key);
+      currNode_ptr->g = inf;
+      currNode_ptr->rhs = 0;
+      currNode_ptr->h = ss_ptr->eps_ == 0 ? 0 : ENV->get_heur(start_coord);
+      ss_ptr->pq_.push(ss_ptr->calculateKey(currNode_ptr), currNode_ptr);
+      currNode_ptr->iterationopened = true;
+      currNode_ptr->iterationclosed = false;
+    }
+    // goal node: the previous goal if it still is one, else a detached placeholder (:222-240)
+    S goal_placeholder{Waypoint<Dim>(), 0};
+    S *goalNode_ptr = &goal_placeholder;
+    if (!ss_ptr->best_child_.empty() && ENV->is_goal(ss_ptr->best_child_.back()->coord)) {
+      goalNode_ptr = ss_ptr->best_child_.back();
+    } else {
+      goalNode_ptr->g = inf;
+      goalNode_ptr->rhs = inf;
+      goalNode_ptr->h = 0;
+    }
+
+    int expand_iteration = 0;
+    vec_E<Waypoint<Dim>> succ_coord, cands;
+    std::vector<decimal_t> succ_cost;
+    std::vector<int> succ_act_id;
+    std::vector<std::size_t> succ_key, cand_keys;
+    auto top_key = [&] { return ss_ptr->pq_.empty() ? inf : ss_ptr->pq_.top().first; };
+    while (top_key() < ss_ptr->calculateKey(goalNode_ptr) || goalNode_ptr->rhs != goalNode_ptr->g) {
+      if (ss_ptr->pq_.empty()) return inf;
+      expand_iteration++;
+      const auto &raw = ss_ptr->pq_.raw();
+      if (lookahead_ > 0 && raw[0].second->succ.empty() && ENV->wants_candidates(raw[0].second->key)) {
+        cands.clear();
+        cand_keys.clear();
+        for (std::size_t i = 1; i < raw.size() && (int)cands.size() < lookahead_; i++)
+          if (raw[i].second->succ.empty()) {
+            cands.push_back(raw[i].second->coord);
+            cand_keys.push_back(raw[i].second->key);
+          }
+        ENV->prefetch(cands, cand_keys);
+      }
+      currNode_ptr = ss_ptr->pq_.top().second;
+      ss_ptr->pq_.pop();
+      currNode_ptr->iterationclosed = true;
+      if (currNode_ptr->g > currNode_ptr->rhs)
+        currNode_ptr->g = currNode_ptr->rhs;
+      else {
+        currNode_ptr->g = inf;
+        ss_ptr->updateNode(currNode_ptr);
+      }
+
+      // successors: stored ones if the node was explored before, else get_succ (:259-271)
+      const bool explored = !currNode_ptr->succ.empty();
+      succ_key.clear();
+      if (explored) {
+        succ_coord.clear(); succ_cost.clear(); succ_act_id.clear();
+        for (const auto &sc : currNode_ptr->succ) {
+          succ_coord.push_back(sc.node->coord);
+          succ_key.push_back(sc.node->key);
+          succ_cost.push_back(sc.action_cost);
+          succ_act_id.push_back(sc.action_id);
+        }
+      } else {
+        ENV->get_succ(currNode_ptr->coord, succ_coord, succ_cost, succ_act_id);
+        const std::size_t *keys = ENV->last_succ_keys();
+        for (std::size_t s = 0; s < succ_coord.size(); s++) succ_key.push_back(keys ? keys[s] : hash_value(succ_coord[s]));
+        currNode_ptr->succ.resize(succ_coord.size());
+      }
+
+      for (std::size_t s = 0; s < succ_coord.size(); ++s) {
+        bool created;
+        S *succNode_ptr = ss_ptr->get_or_make(succ_key[s], [&] { return succ_coord[s]; }, created);
+        if (created) succNode_ptr->h = ss_ptr->eps_ == 0 ? 0 : ENV->get_heur(succNode_ptr->coord);
+        currNode_ptr->succ[s] = typename S::Succ{succNode_ptr, succ_cost[s], succ_act_id[s]};
+        int id = -1;
+        for (std::size_t i = 0; i < succNode_ptr->pred.size(); i++)
+          if (succNode_ptr->pred[i].node->key == currNode_ptr->key) { id = (int)i; break; }
+        if (id == -1) succNode_ptr->pred.push_back(typename S::Pred{currNode_ptr, succ_cost[s], succ_act_id[s]});
+        ss_ptr->updateNode(succNode_ptr);
+      }
+
+      if (ENV->is_goal(currNode_ptr->coord)) goalNode_ptr = currNode_ptr;
+      if (max_expand > 0 && expand_iteration >= max_expand) return inf;
+      if (ss_ptr->pq_.empty()) return inf;
+    }
+    ss_ptr->expand_iteration_ = expand_iteration;
+    if (recoverTraj<Dim>(goalNode_ptr, *ss_ptr, start_key, traj)) return goalNode_ptr->g - ss_ptr->start_g_;
+    return inf;
   }
 
  private:
@@ -765,12 +1089,12 @@ class PlannerBase {
   /// getCloseSet (planner_base.h): states with iterationclosed
   std::vector<const State<Dim> *> getCloseSetStates() const {
     std::vector<const State<Dim> *> v;
-    for (const auto &st : ss_ptr_->arena_) if (st.iterationclosed) v.push_back(&st);
+    for (const auto *st : ss_ptr_->order_) if (st->iterationclosed) v.push_back(st);
     return v;
   }
   std::size_t getOpenSetSize() const {
     std::size_t n = 0;
-    for (const auto &st : ss_ptr_->arena_) if (st.iterationopened && !st.iterationclosed) n++;
+    for (const auto *st : ss_ptr_->order_) if (st->iterationopened && !st->iterationclosed) n++;
     return n;
   }
   void setVmax(decimal_t v) { ENV_->set_v_max(v); }
@@ -788,20 +1112,31 @@ class PlannerBase {
     ENV_->set_tol_pos(tol_pos); ENV_->set_tol_vel(tol_vel); ENV_->set_tol_acc(tol_acc);
   }
   void setLookahead(int k) { lookahead_ = k; }
+  /// planner_base.h:170-176
+  void setLPAstar(bool use_lpastar) { use_lpastar_ = use_lpastar; }
+  /// planner_base.h:155: prune the state space to the subtree under best_child_[time_step]
+  void getSubStateSpace(int time_step) { ss_ptr_->getSubStateSpace(time_step); }
+  /// planner_base.h:164-167
+  void reset() { ss_ptr_ = nullptr; traj_.clear(); }
+  const std::shared_ptr<StateSpace<Dim>> &stateSpace() const { return ss_ptr_; }
 
-  /// planner_base.h:275-325 (A* branch)
+  /// planner_base.h:275-325
   bool plan(const Waypoint<Dim> &start, const Waypoint<Dim> &goal) {
     if (!ENV_->is_free(start.pos)) {
       printf("[PlannerBase] start is not free!\n");
       return false;
     }
     GraphSearch<Dim> planner(planner_verbose_, lookahead_);
-    ss_ptr_.reset(new StateSpace<Dim>(epsilon_));
+    // A*: a fresh state space per plan; LPA*: only at the first plan (planner_base.h:293-303)
+    if (!use_lpastar_ || !initialized()) ss_ptr_.reset(new StateSpace<Dim>(epsilon_));
     ENV_->set_goal(goal);
     ENV_->expanded_nodes_.clear();
     ENV_->begin_plan();
     ss_ptr_->dt_ = ENV_->get_dt();
-    traj_cost_ = planner.Astar(start, ENV_, ss_ptr_, traj_, max_num_);
+    if (use_lpastar_)
+      traj_cost_ = planner.LPAstar(start, ENV_, ss_ptr_, traj_, max_num_);
+    else
+      traj_cost_ = planner.Astar(start, ENV_, ss_ptr_, traj_, max_num_);
     if (std::isinf(traj_cost_)) return false;
     return true;
   }
@@ -815,6 +1150,7 @@ class PlannerBase {
   int max_num_ = -1;
   int lookahead_ = 0;
   bool planner_verbose_;
+  bool use_lpastar_ = false;
 };
 
 template <int Dim>
@@ -828,7 +1164,11 @@ class MapPlanner : public PlannerBase<Dim> {
     map_util_ = map_util;
   }
   /// Any env_base implementation (the closed-set equality tests install a CPU checker env here).
-  void setEnv(const std::shared_ptr<env_base<Dim>> &env) { this->ENV_ = env; gpu_env_.reset(); }
+  void setEnv(const std::shared_ptr<env_base<Dim>> &env, const std::shared_ptr<MapUtil<Dim>> &map_util = nullptr) {
+    this->ENV_ = env;
+    gpu_env_.reset();
+    if (map_util) map_util_ = map_util;
+  }
   void setControl(int control) { if (gpu_env_) gpu_env_->set_control(control); }
   void setSpeculation(int k) { if (gpu_env_) gpu_env_->set_speculation(k); this->setLookahead(k > 1 ? 4 * k : 0); }
   /// map_planner.cpp:20-43
@@ -849,7 +1189,61 @@ class MapPlanner : public PlannerBase<Dim> {
   void setGradientWeight(decimal_t w) { this->ENV_->set_gradient_weight(w); }
   env_map_gpu<Dim> *gpu_env() { return gpu_env_.get(); }
 
+  /// getLinkedNodes: src/mpl_planner/map_planner.cpp:124-157.  Every stored edge (state, i-th
+  /// predecessor) is walked through the grid — on the device for the GPU env, all edges in one
+  /// batch — and entered into lhm_ under each voxel it touches; returns the voxel centres.
+  vec_E<Vecf<Dim>> getLinkedNodes() const {
+    using S = State<Dim>;
+    lhm_.clear();
+    vec_E<Vecf<Dim>> linked_pts;
+    vec_E<Waypoint<Dim>> parents;
+    std::vector<int> actions;
+    std::vector<std::pair<S *, int>> owner;
+    for (S *st : this->ss_ptr_->order_)
+      for (std::size_t i = 0; i < st->pred.size(); i++) {
+        parents.push_back(st->pred[i].node->coord);
+        actions.push_back(st->pred[i].action_id);
+        owner.emplace_back(st, (int)i);
+      }
+    std::vector<long long> offset;
+    std::vector<int> cells;
+    if (!parents.empty()) this->ENV_->edge_cells(parents, actions, offset, cells);
+    const decimal_t res = map_util_->getRes();
+    const Vecf<Dim> ori = map_util_->getOrigin();
+    for (std::size_t e = 0; e < parents.size(); e++)
+      for (long long c = offset[e]; c < offset[e + 1]; c++) {
+        Veci<Dim> pn;
+        for (int k = 0; k < Dim; k++) pn(k) = cells[c * Dim + k];
+        Vecf<Dim> pt;  // intToFloat: map_util.h:110-113
+        for (int k = 0; k < Dim; k++) pt(k) = (pn(k) + 0.5) * res + ori(k);
+        linked_pts.push_back(pt);
+        lhm_[map_util_->getIndex(pn)].push_back(owner[e]);
+      }
+    return linked_pts;
+  }
+  /// updateBlockedNodes: map_planner.cpp:159-171
+  void updateBlockedNodes(const vec_E<Veci<Dim>> &blocked_pns) {
+    std::vector<std::pair<State<Dim> *, int>> blocked_nodes;
+    for (const auto &it : blocked_pns) {
+      auto search = lhm_.find(map_util_->getIndex(it));
+      if (search != lhm_.end()) blocked_nodes.insert(blocked_nodes.end(), search->second.begin(), search->second.end());
+    }
+    this->ss_ptr_->increaseCost(blocked_nodes);
+  }
+  /// updateClearedNodes: map_planner.cpp:173-185; the is_free(pr) re-validation runs batched in the env
+  void updateClearedNodes(const vec_E<Veci<Dim>> &cleared_pns) {
+    std::vector<std::pair<State<Dim> *, int>> cleared_nodes;
+    for (const auto &it : cleared_pns) {
+      auto search = lhm_.find(map_util_->getIndex(it));
+      if (search != lhm_.end()) cleared_nodes.insert(cleared_nodes.end(), search->second.begin(), search->second.end());
+    }
+    this->ss_ptr_->decreaseCost(cleared_nodes, *this->ENV_);
+  }
+  const std::unordered_map<int, std::vector<std::pair<State<Dim> *, int>>> &linkedTable() const { return lhm_; }
+
  protected:
+  /// voxel index -> (state, i-th predecessor) edges through it (map_planner.h:15-16,101)
+  mutable std::unordered_map<int, std::vector<std::pair<State<Dim> *, int>>> lhm_;
   std::shared_ptr<MapUtil<Dim>> map_util_;
   std::shared_ptr<env_map_gpu<Dim>> gpu_env_;
   Vecf<Dim> potential_radius_, potential_map_range_, search_radius_;
@@ -1044,7 +1438,7 @@ class MultiQueryPlanner {
       res[q].valid = !std::isinf(res[q].cost);
       res[q].expanded = st[q]->expanded();
       for (const auto &e : traj) res[q].actions.push_back(e.action_id);
-      for (const auto &stt : ss[q]->arena_) if (stt.iterationclosed) res[q].n_closed++;
+      for (const auto *stt : ss[q]->order_) if (stt->iterationclosed) res[q].n_closed++;
     }
     return res;
   }

@@ -41,6 +41,32 @@ int mplh_plan(const mplh_plan_args *a, mplh_plan_result *r, uint64_t *closed_key
   }
 }
 
+/* A scripted LPA* session (plan_capi_types.h: PLAN / LINK / BLOCK / CLEAR / SUBTREE steps) on one
+ * MapPlanner with the GPU env: get_succ, the getLinkedNodes voxel walk and the is_free(pr)
+ * re-validation of decreaseCost all run on the device.  outs has n_steps entries; the action ids of
+ * the trajectory found by PLAN step k go to actions[k*cap_actions ...]. */
+int mplh_lpa_run(const mplh_plan_args *a, const mplh_lpa_step *steps, int n_steps, mplh_lpa_out *outs,
+                 int32_t *actions, int cap_actions) {
+  try {
+    auto go = [&](auto dimtag) {
+      constexpr int Dim = decltype(dimtag)::value;
+      MPL::MapPlanner<Dim> planner(false);
+      auto mu = mplh::make_map<Dim>(a);
+      planner.setMapUtil(mu, a->device);
+      planner.setControl(a->control);
+      planner.setSpeculation(a->speculate);
+      mplh::run_lpa<Dim>(planner, mu, a, steps, n_steps, outs, actions, cap_actions);
+    };
+    if (a->dim == 2) go(std::integral_constant<int, 2>());
+    else if (a->dim == 3) go(std::integral_constant<int, 3>());
+    else { g_err = "dim must be 2 or 3"; return 1; }
+    return 0;
+  } catch (const std::exception &e) {
+    g_err = e.what();
+    return 2;
+  }
+}
+
 /* Lock-step batched A* over n_q (start, goal) pairs on the map/params of `a` (a->start/goal are
  * ignored).  totals[0] = lock-step iterations (= device launches of the expansion kernel),
  * totals[1] = nodes expanded over all queries, totals[2] = wall seconds of the search,

@@ -50,4 +50,90 @@ void run(MPL::MapPlanner<Dim> &planner, const mplh_plan_args *a, mplh_plan_resul
   r->n_actions = (int)traj.size();
   for (int i = 0; i < (int)traj.size() && i < cap_actions; i++) actions[i] = traj[i].action_id;
 }
+
+inline void fnv(uint64_t &h, const void *p, size_t n) {
+  const unsigned char *b = (const unsigned char *)p;
+  for (size_t i = 0; i < n; i++) { h ^= b[i]; h *= 0x100000001b3ULL; }
+}
+
+// Snapshot of the search state after a step: counts + a hash of every state's (key, g, rhs, flags).
+template <int Dim>
+void snapshot(MPL::MapPlanner<Dim> &planner, mplh_lpa_out *o) {
+  struct Rec { uint64_t key; double g, rhs; uint64_t flags; };
+  std::vector<Rec> recs;
+  o->n_closed = o->n_open = 0;
+  if (planner.initialized())
+    for (const auto *s : planner.stateSpace()->order_) {
+      recs.push_back(Rec{(uint64_t)s->key, s->g, s->rhs, (uint64_t)((s->iterationopened ? 1 : 0) | (s->iterationclosed ? 2 : 0))});
+      if (s->iterationclosed) o->n_closed++;
+      else if (s->iterationopened) o->n_open++;
+    }
+  std::sort(recs.begin(), recs.end(), [](const Rec &a, const Rec &b) { return a.key < b.key; });
+  o->n_states = (int)recs.size();
+  uint64_t h = 0xcbf29ce484222325ULL;
+  for (const auto &r : recs) fnv(h, &r, sizeof r);
+  o->state_hash = h;
+}
+
+// Run a scripted LPA* session (plan_capi_types.h) on `planner`, whose env and map_util are installed.
+template <int Dim>
+void run_lpa(MPL::MapPlanner<Dim> &planner, const std::shared_ptr<MPL::MapUtil<Dim>> &mu, const mplh_plan_args *a,
+             const mplh_lpa_step *steps, int n_steps, mplh_lpa_out *outs, int32_t *actions, int cap_actions) {
+  vec_E<VecDf> U;
+  for (int i = 0; i < a->nU; i++) U.push_back(VecDf(a->U + (size_t)i * a->udim, a->U + (size_t)(i + 1) * a->udim));
+  planner.setU(U);
+  planner.setVmax(a->v_max); planner.setAmax(a->a_max); planner.setJmax(a->j_max); planner.setYawmax(a->yaw_max);
+  planner.setDt(a->T); planner.setW(a->w); planner.setWyaw(a->wyaw); planner.setEpsilon(a->eps);
+  planner.setTol(a->tol_pos, a->tol_vel, a->tol_acc);
+  planner.setMaxNum(a->max_num);
+  planner.setLPAstar(true);
+  Waypoint<Dim> start = wp_from<Dim>(a->start, a->control);
+  const Waypoint<Dim> goal = wp_from<Dim>(a->goal, a->control);
+  for (int k = 0; k < n_steps; k++) {
+    mplh_lpa_out *o = &outs[k];
+    *o = mplh_lpa_out{};
+    const mplh_lpa_step &st = steps[k];
+    auto t0 = std::chrono::steady_clock::now();
+    if (st.op == MPLH_OP_PLAN) {
+      o->valid = planner.plan(start, goal) ? 1 : 0;
+      o->cost = planner.getTrajCost();
+      o->expanded = planner.getExpandedNum();
+      const auto traj = planner.getTraj();
+      o->n_actions = o->valid ? (int)traj.size() : 0;
+      for (int i = 0; i < o->n_actions && i < cap_actions; i++) actions[(size_t)k * cap_actions + i] = traj[i].action_id;
+    } else if (st.op == MPLH_OP_LINK) {
+      o->n_linked = (int64_t)planner.getLinkedNodes().size();
+      struct Rec { int64_t cell; uint64_t key; int64_t i; };
+      std::vector<Rec> recs;
+      for (const auto &it : planner.linkedTable())
+        for (const auto &e : it.second) recs.push_back(Rec{it.first, (uint64_t)e.first->key, e.second});
+      std::sort(recs.begin(), recs.end(), [](const Rec &x, const Rec &y) {
+        return x.cell != y.cell ? x.cell < y.cell : (x.key != y.key ? x.key < y.key : x.i < y.i);
+      });
+      uint64_t h = 0xcbf29ce484222325ULL;
+      for (const auto &r : recs) fnv(h, &r, sizeof r);
+      o->linked_hash = h;
+    } else if (st.op == MPLH_OP_BLOCK || st.op == MPLH_OP_CLEAR) {
+      MPL::Tmap m = mu->getMap();
+      vec_E<Veci<Dim>> pns;
+      for (int i = 0; i < st.n; i++) {
+        Veci<Dim> pn;
+        for (int d = 0; d < Dim; d++) pn(d) = st.cells[(size_t)i * Dim + d];
+        pns.push_back(pn);
+        if (!mu->isOutside(pn)) m[mu->getIndex(pn)] = st.op == MPLH_OP_BLOCK ? 100 : 0;
+      }
+      mu->setMap(mu->getOrigin(), mu->getDim(), m, mu->getRes());
+      if (st.op == MPLH_OP_BLOCK) planner.updateBlockedNodes(pns);
+      else planner.updateClearedNodes(pns);
+    } else if (st.op == MPLH_OP_SUBTREE) {
+      const auto &bc = planner.stateSpace()->best_child_;
+      if (st.n >= 0 && st.n < (int)bc.size()) {
+        start = bc[st.n]->coord;
+        planner.getSubStateSpace(st.n);
+      }
+    }
+    o->seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    snapshot<Dim>(planner, o);
+  }
+}
 }  // namespace mplh

@@ -40,6 +40,32 @@ typedef struct {
 }
 
 extern "C" {
+/* A scripted incremental-planning (LPA*) session on one planner: the steps run in order.
+ *   PLAN     plan(start, goal) with setLPAstar(true); start is args->start until a SUBTREE step
+ *   LINK     getLinkedNodes(): rebuild the voxel -> edges table from the current graph
+ *   BLOCK    mark n cells occupied in the map, then updateBlockedNodes(cells)
+ *   CLEAR    mark n cells free in the map, then updateClearedNodes(cells)
+ *   SUBTREE  start := best_child_[n]; getSubStateSpace(n)   (re-root at the n-th trajectory node) */
+enum { MPLH_OP_PLAN = 0, MPLH_OP_LINK = 1, MPLH_OP_BLOCK = 2, MPLH_OP_CLEAR = 3, MPLH_OP_SUBTREE = 4 };
+typedef struct {
+  int32_t op;
+  int32_t n;            /* BLOCK/CLEAR: number of cells; SUBTREE: time step */
+  const int32_t *cells; /* BLOCK/CLEAR: n * dim cell coordinates */
+} mplh_lpa_step;
+typedef struct {
+  int32_t valid;        /* PLAN: plan() return value */
+  double cost;          /* PLAN: getTrajCost() */
+  int32_t expanded;     /* PLAN: expand iterations of this call */
+  int32_t n_actions;    /* PLAN: edges of the recovered trajectory */
+  int32_t n_states, n_closed, n_open; /* after the step: states in the space / closed / in the queue */
+  uint64_t state_hash;  /* after the step: FNV-1a over (key, g, rhs, opened, closed) of all states by key */
+  int64_t n_linked;     /* LINK: voxel centres returned */
+  uint64_t linked_hash; /* LINK: FNV-1a over the sorted (voxel index, state key, pred index) table */
+  double seconds;
+} mplh_lpa_out;
+}
+
+extern "C" {
 /* Batched queries (config 5): shares every field of mplh_plan_args except start/goal. */
 typedef struct {
   int32_t valid;

@@ -37,6 +37,18 @@ class QueryResult(C.Structure):
                 ("n_actions", C.c_int32)]
 
 
+class LpaStep(C.Structure):
+    _fields_ = [("op", C.c_int32), ("n", C.c_int32), ("cells", C.c_void_p)]
+
+
+class LpaOut(C.Structure):
+    _fields_ = [("valid", C.c_int32), ("cost", C.c_double), ("expanded", C.c_int32), ("n_actions", C.c_int32),
+                ("n_states", C.c_int32), ("n_closed", C.c_int32), ("n_open", C.c_int32), ("state_hash", C.c_uint64),
+                ("n_linked", C.c_int64), ("linked_hash", C.c_uint64), ("seconds", C.c_double)]
+
+
+OP_PLAN, OP_LINK, OP_BLOCK, OP_CLEAR, OP_SUBTREE = range(5)
+
 WAYPOINT_DTYPE = np.dtype(
     [("pos", "<f8", 3), ("vel", "<f8", 3), ("acc", "<f8", 3), ("jrk", "<f8", 3), ("yaw", "<f8"), ("t", "<f8")]
 )
@@ -94,6 +106,56 @@ def run_plan(fn, lib, args, cap=1 << 21):
     out["closed"] = closed[: min(r.n_closed, cap)].copy()
     out["actions"] = actions[: r.n_actions].copy()
     return out
+
+
+def run_lpa(fn, lib, args, script, cap_actions=4096):
+    """Run a scripted LPA* session.  script: list of ("plan",), ("link",), ("block", cells[n, dim]),
+    ("clear", cells[n, dim]), ("subtree", k).  Returns one dict per step (fields of mplh_lpa_out, plus
+    the action ids of the trajectory for plan steps)."""
+    ops = dict(plan=OP_PLAN, link=OP_LINK, block=OP_BLOCK, clear=OP_CLEAR, subtree=OP_SUBTREE)
+    steps = (LpaStep * len(script))()
+    keep = []
+    for k, st in enumerate(script):
+        steps[k].op = ops[st[0]]
+        if st[0] in ("block", "clear"):
+            cells = np.ascontiguousarray(st[1], dtype=np.int32).reshape(-1, args.dim)
+            keep.append(cells)
+            steps[k].n = len(cells)
+            steps[k].cells = cells.ctypes.data
+        elif st[0] == "subtree":
+            steps[k].n = int(st[1])
+    outs = (LpaOut * len(script))()
+    actions = np.full((len(script), cap_actions), -1, dtype=np.int32)
+    rc = fn(C.byref(args), steps, len(script), outs, actions.ctypes.data, cap_actions)
+    if rc != 0:
+        err = getattr(lib, "mplh_last_error", None)
+        raise RuntimeError(err().decode() if err else f"lpa session failed rc={rc}")
+    res = []
+    for k in range(len(script)):
+        d = {name: getattr(outs[k], name) for name, _ in LpaOut._fields_}
+        d["op"] = script[k][0]
+        d["actions"] = actions[k, : min(d["n_actions"], cap_actions)].copy()
+        res.append(d)
+    return res
+
+
+def load_lpa_fn(path, fn):
+    L = C.CDLL(str(path))
+    f = getattr(L, fn)
+    f.argtypes = [C.POINTER(PlanArgs), C.POINTER(LpaStep), C.c_int, C.POINTER(LpaOut), C.c_void_p, C.c_int]
+    f.restype = C.c_int
+    return L, f
+
+
+def lpa_session(args, script):
+    """MPL::MapPlanner with setLPAstar(true) and the GPU env: plan / getLinkedNodes / updateBlockedNodes /
+    updateClearedNodes / getSubStateSpace as scripted; expansion, the linked-voxel walk and the
+    is_free(pr) re-validation run on the device."""
+    if not LIB.exists():
+        raise ImportError(f"{LIB} not built (python -c 'import __graft_entry__ as g; g.build()')")
+    lib, fn = load_lpa_fn(LIB, "mplh_lpa_run")
+    lib.mplh_last_error.restype = C.c_char_p
+    return run_lpa(fn, lib, args, script)
 
 
 def _host():

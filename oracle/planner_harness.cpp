@@ -14,16 +14,8 @@ class env_map_oracle : public MPL::env_map_host<Dim> {
                 std::vector<int> &action_idx) const override {
     succ.clear(); succ_cost.clear(); action_idx.clear();
     this->expanded_nodes_.push_back(curr.pos);
-    orc_env e{};
-    e.dim = Dim; e.control = a_->control; e.T = this->dt_; e.w = this->w_; e.wyaw = this->wyaw_;
-    e.v_max = this->v_max_; e.a_max = this->a_max_; e.j_max = this->j_max_; e.yaw_max = this->yaw_max_;
-    e.nU = a_->nU; e.udim = a_->udim; e.U = a_->U;
-    for (int k = 0; k < 3; k++) { e.mdim[k] = k < Dim ? a_->mdim[k] : 1; e.origin[k] = k < Dim ? a_->origin[k] : 0; }
-    e.res = a_->res; e.map = a_->map; e.potential = a_->potential;
-    e.potential_weight = a_->potential_weight; e.gradient_weight = a_->gradient_weight; e.region = nullptr;
-    orc_waypoint c{};
-    for (int d = 0; d < Dim; d++) { c.pos[d] = curr.pos(d); c.vel[d] = curr.vel(d); c.acc[d] = curr.acc(d); c.jrk[d] = curr.jrk(d); }
-    c.yaw = curr.yaw; c.t = curr.t;
+    const orc_env e = env();
+    const orc_waypoint c = pod(curr);
     std::vector<orc_waypoint> s(e.nU); std::vector<double> cost(e.nU); std::vector<int32_t> act(e.nU);
     const int n = orc_get_succ(&e, &c, s.data(), cost.data(), act.data(), nullptr, nullptr);
     for (int j = 0; j < n; j++) {
@@ -33,10 +25,61 @@ class env_map_oracle : public MPL::env_map_host<Dim> {
       succ.push_back(w); succ_cost.push_back(cost[j]); action_idx.push_back(act[j]);
     }
   }
+  void is_free_edges(const vec_E<Waypoint<Dim>> &parents, const std::vector<int> &actions, std::vector<uint8_t> &free,
+                     std::vector<decimal_t> &cost) const override {
+    const orc_env e = env();
+    std::vector<orc_waypoint> in(parents.size());
+    for (std::size_t i = 0; i < parents.size(); i++) in[i] = pod(parents[i]);
+    free.assign(parents.size(), 0);
+    cost.assign(parents.size(), 0);
+    orc_edges_is_free(&e, in.data(), actions.data(), (int)parents.size(), free.data(), cost.data());
+  }
+  void edge_cells(const vec_E<Waypoint<Dim>> &parents, const std::vector<int> &actions, std::vector<long long> &offset,
+                  std::vector<int> &cells) const override {
+    const orc_env e = env();
+    std::vector<orc_waypoint> in(parents.size());
+    for (std::size_t i = 0; i < parents.size(); i++) in[i] = pod(parents[i]);
+    offset.assign(parents.size() + 1, 0);
+    const int64_t total = orc_edges_cells(&e, in.data(), actions.data(), (int)parents.size(), (int64_t *)offset.data(), nullptr, 0);
+    cells.assign((std::size_t)total * Dim, 0);
+    orc_edges_cells(&e, in.data(), actions.data(), (int)parents.size(), (int64_t *)offset.data(), cells.data(), total);
+  }
+
  private:
+  static orc_waypoint pod(const Waypoint<Dim> &w) {
+    orc_waypoint c{};
+    for (int d = 0; d < Dim; d++) { c.pos[d] = w.pos(d); c.vel[d] = w.vel(d); c.acc[d] = w.acc(d); c.jrk[d] = w.jrk(d); }
+    c.yaw = w.yaw; c.t = w.t;
+    return c;
+  }
+  // the env reads the planner's CURRENT map (it changes between the steps of an LPA* session)
+  orc_env env() const {
+    orc_env e{};
+    e.dim = Dim; e.control = a_->control; e.T = this->dt_; e.w = this->w_; e.wyaw = this->wyaw_;
+    e.v_max = this->v_max_; e.a_max = this->a_max_; e.j_max = this->j_max_; e.yaw_max = this->yaw_max_;
+    e.nU = a_->nU; e.udim = a_->udim; e.U = a_->U;
+    for (int k = 0; k < 3; k++) { e.mdim[k] = k < Dim ? a_->mdim[k] : 1; e.origin[k] = k < Dim ? a_->origin[k] : 0; }
+    e.res = a_->res; e.map = (const int8_t *)this->map_util_->map().data(); e.potential = a_->potential;
+    e.potential_weight = a_->potential_weight; e.gradient_weight = a_->gradient_weight; e.region = nullptr;
+    return e;
+  }
   const mplh_plan_args *a_;
 };
 }  // namespace
+
+extern "C" int orcp_lpa_run(const mplh_plan_args *a, const mplh_lpa_step *steps, int n_steps, mplh_lpa_out *outs,
+                            int32_t *actions, int cap_actions) {
+  auto go = [&](auto dimtag) {
+    constexpr int Dim = decltype(dimtag)::value;
+    MPL::MapPlanner<Dim> planner(false);
+    auto mu = mplh::make_map<Dim>(a);
+    planner.setEnv(std::make_shared<env_map_oracle<Dim>>(mu, a), mu);
+    mplh::run_lpa<Dim>(planner, mu, a, steps, n_steps, outs, actions, cap_actions);
+  };
+  if (a->dim == 2) go(std::integral_constant<int, 2>());
+  else go(std::integral_constant<int, 3>());
+  return 0;
+}
 
 extern "C" int orcp_plan(const mplh_plan_args *a, mplh_plan_result *r, uint64_t *closed_keys, int cap_closed,
                          int32_t *actions, int cap_actions) {

@@ -44,6 +44,7 @@ struct Planner : MPL::MapPlanner<Dim> {
   explicit Planner(bool v) : MPL::MapPlanner<Dim>(v) {}
   using MPL::MapPlanner<Dim>::ss_ptr_;
   using MPL::MapPlanner<Dim>::ENV_;
+  using MPL::MapPlanner<Dim>::lhm_;
 };
 
 template <int Dim>
@@ -141,9 +142,145 @@ int region(const mplh_plan_args *a, const double *path, int n_path, const double
   for (size_t i = 0; i < reg.size(); i++) out[i] = reg[i] ? 1 : 0;
   return 0;
 }
+inline void fnv(uint64_t &h, const void *p, size_t n) {
+  const unsigned char *b = (const unsigned char *)p;
+  for (size_t i = 0; i < n; i++) {
+    h ^= b[i];
+    h *= 0x100000001b3ULL;
+  }
+}
+
+template <int Dim>
+void snapshot(Planner<Dim> &planner, mplh_lpa_out *o) {
+  struct Rec {
+    uint64_t key;
+    double g, rhs;
+    uint64_t flags;
+  };
+  std::vector<Rec> recs;
+  o->n_closed = o->n_open = 0;
+  if (planner.initialized())
+    for (const auto &it : planner.ss_ptr_->hm_) {
+      if (!it.second) continue;
+      const auto &s = it.second;
+      Rec r = {(uint64_t)hash_value(s->coord), s->g, s->rhs,
+               (uint64_t)((s->iterationopened ? 1 : 0) | (s->iterationclosed ? 2 : 0))};
+      recs.push_back(r);
+      if (s->iterationclosed)
+        o->n_closed++;
+      else if (s->iterationopened)
+        o->n_open++;
+    }
+  std::sort(recs.begin(), recs.end(), [](const Rec &a, const Rec &b) { return a.key < b.key; });
+  o->n_states = (int)recs.size();
+  uint64_t h = 0xcbf29ce484222325ULL;
+  for (const auto &r : recs) fnv(h, &r, sizeof r);
+  o->state_hash = h;
+}
+
+// The scripted LPA* session of plan_capi_types.h through the reference's own planner API:
+// setLPAstar / plan / getLinkedNodes / setMap + updateBlockedNodes / updateClearedNodes / getSubStateSpace.
+template <int Dim>
+int lpa_run(const mplh_plan_args *a, const mplh_lpa_step *steps, int n_steps, mplh_lpa_out *outs, int32_t *actions,
+            int cap_actions) {
+  Planner<Dim> planner(false);
+  auto mu = make_map<Dim>(a);
+  planner.setMapUtil(mu);
+  vec_E<VecDf> U;
+  for (int i = 0; i < a->nU; i++) {
+    VecDf u(a->udim);
+    for (int k = 0; k < a->udim; k++) u(k) = a->U[(size_t)i * a->udim + k];
+    U.push_back(u);
+  }
+  planner.setU(U);
+  planner.setVmax(a->v_max);
+  planner.setAmax(a->a_max);
+  planner.setJmax(a->j_max);
+  planner.setYawmax(a->yaw_max);
+  planner.setDt(a->T);
+  planner.setW(a->w);
+  planner.setWyaw(a->wyaw);
+  planner.setEpsilon(a->eps);
+  planner.setTol(a->tol_pos, a->tol_vel, a->tol_acc);
+  planner.setMaxNum(a->max_num);
+  planner.setLPAstar(true);
+  Waypoint<Dim> start = wp_from<Dim>(a->start, a->control);
+  const Waypoint<Dim> goal = wp_from<Dim>(a->goal, a->control);
+  const int order = __builtin_popcount(a->control & 15);
+  for (int k = 0; k < n_steps; k++) {
+    mplh_lpa_out *o = &outs[k];
+    *o = mplh_lpa_out{};
+    const mplh_lpa_step &st = steps[k];
+    auto t0 = std::chrono::steady_clock::now();
+    if (st.op == MPLH_OP_PLAN) {
+      o->valid = planner.plan(start, goal) ? 1 : 0;
+      o->cost = planner.getTrajCost();
+      o->expanded = planner.getExpandedNum();
+      const auto prs = planner.getTraj().getPrimitives();
+      o->n_actions = o->valid ? (int)prs.size() : 0;
+      for (int i = 0; i < o->n_actions && i < cap_actions; i++) {
+        int found = -1;
+        for (int u = 0; u < a->nU && found < 0; u++) {
+          bool same = true;
+          for (int d = 0; d < Dim; d++) same = same && prs[i].pr(d).coeff()(5 - order) == a->U[(size_t)u * a->udim + d];
+          if (same && (a->control & 16)) same = prs[i].pr_yaw().coeff()(4) == a->U[(size_t)u * a->udim + Dim];
+          if (same) found = u;
+        }
+        actions[(size_t)k * cap_actions + i] = found;
+      }
+    } else if (st.op == MPLH_OP_LINK) {
+      o->n_linked = (int64_t)planner.getLinkedNodes().size();
+      struct Rec {
+        int64_t cell;
+        uint64_t key;
+        int64_t i;
+      };
+      std::vector<Rec> recs;
+      for (const auto &it : planner.lhm_)
+        for (const auto &e : it.second) {
+          Rec r = {it.first, (uint64_t)hash_value(e.first), e.second};
+          recs.push_back(r);
+        }
+      std::sort(recs.begin(), recs.end(), [](const Rec &x, const Rec &y) {
+        return x.cell != y.cell ? x.cell < y.cell : (x.key != y.key ? x.key < y.key : x.i < y.i);
+      });
+      uint64_t h = 0xcbf29ce484222325ULL;
+      for (const auto &r : recs) fnv(h, &r, sizeof r);
+      o->linked_hash = h;
+    } else if (st.op == MPLH_OP_BLOCK || st.op == MPLH_OP_CLEAR) {
+      MPL::Tmap m = mu->getMap();
+      vec_Veci<Dim> pns;
+      for (int i = 0; i < st.n; i++) {
+        Veci<Dim> pn;
+        for (int d = 0; d < Dim; d++) pn(d) = st.cells[(size_t)i * Dim + d];
+        pns.push_back(pn);
+        if (!mu->isOutside(pn)) m[mu->getIndex(pn)] = st.op == MPLH_OP_BLOCK ? 100 : 0;
+      }
+      mu->setMap(mu->getOrigin(), mu->getDim(), m, mu->getRes());
+      if (st.op == MPLH_OP_BLOCK)
+        planner.updateBlockedNodes(pns);
+      else
+        planner.updateClearedNodes(pns);
+    } else if (st.op == MPLH_OP_SUBTREE) {
+      const auto &bc = planner.ss_ptr_->best_child_;
+      if (st.n >= 0 && st.n < (int)bc.size()) {
+        start = bc[st.n]->coord;
+        planner.getSubStateSpace(st.n);
+      }
+    }
+    o->seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    snapshot<Dim>(planner, o);
+  }
+  return 0;
+}
 }  // namespace
 
 extern "C" {
+int refp_lpa_run(const mplh_plan_args *a, const mplh_lpa_step *steps, int n_steps, mplh_lpa_out *outs,
+                 int32_t *actions, int cap_actions) {
+  return a->dim == 2 ? lpa_run<2>(a, steps, n_steps, outs, actions, cap_actions)
+                     : lpa_run<3>(a, steps, n_steps, outs, actions, cap_actions);
+}
 int refp_plan(const mplh_plan_args *a, mplh_plan_result *r, uint64_t *closed_keys, int cap_closed, int32_t *actions,
               int cap_actions) {
   *r = mplh_plan_result{};

@@ -2,7 +2,7 @@
 // Written from the documented semantics of boost::heap::d_ary_heap<T, mutable_<true>, arity<D>,
 // compare<Cmp>>: an array D-ary max-heap w.r.t. Cmp whose elements keep stable handles;
 // push appends and sifts up, pop swaps the root with the last element and sifts down,
-// increase(handle) sifts up, erase(handle) removes an arbitrary element; a child replaces its
+// increase(handle) sifts up, erase(handle) moves the element to the root and pops; a child replaces its
 // parent unless it compares strictly lower, and among equal children the first one is taken.
 // Tie-breaking between fully equal keys may differ from a given Boost release (unpinned in the
 // reference); the host planner of this repository implements the same rules.
@@ -92,7 +92,16 @@ class d_ary_heap {
     else
       siftdown(i);
   }
-  void erase(handle_type h) { erase_at(h.it_->index); }
+  // erase = move the element to the root without comparisons, then pop (as boost's d_ary_heap does)
+  void erase(handle_type h) {
+    std::size_t i = h.it_->index;
+    while (i != 0) {
+      const std::size_t p = (i - 1) / D;
+      swap_at(p, i);
+      i = p;
+    }
+    pop();
+  }
 
  private:
   void swap_at(std::size_t a, std::size_t b) {

@@ -4,7 +4,8 @@ import subprocess
 from pathlib import Path
 
 from motion_primitive_library_b200.planner import (PlanArgs, PlanResult, QueryResult, Waypoint, load_fn,  # noqa: F401
-                                                   make_args, plan, plan_batch, run_plan)
+                                                   load_lpa_fn, lpa_session, make_args, plan, plan_batch, run_lpa,
+                                                   run_plan)
 
 ROOT = Path(__file__).resolve().parent.parent
 
@@ -22,6 +23,20 @@ def plan_oracle(args):
 
 
 REF_PLANNER = ROOT / "oracle" / "_ref" / "libmplref_planner.so"
+
+
+def lpa_oracle(args, script):
+    """The product's host LPA* driven by the CPU-oracle env (TEST-ONLY harness)."""
+    p = ROOT / "oracle" / "liboracle_planner.so"
+    lib, fn = load_lpa_fn(p, "orcp_lpa_run")
+    return run_lpa(fn, lib, args, script)
+
+
+def lpa_reference(args, script):
+    """The REFERENCE's LPA* (setLPAstar / plan / getLinkedNodes / updateBlockedNodes / updateClearedNodes /
+    getSubStateSpace, unmodified sources + Eigen/Boost stand-ins) on the same script."""
+    lib, fn = load_lpa_fn(REF_PLANNER, "refp_lpa_run")
+    return run_lpa(fn, lib, args, script)
 
 
 def ref_planner_available():
