@@ -188,9 +188,14 @@ int mplx_edges_is_free(mplx_ctx *ctx, const mplx_waypoint *parents, const int32_
  * whenever getIndex differs from the previous sample's.  Edge e owns entries
  * [out_offset[e], out_offset[e+1]) of out_cells, ctx-dim int32 each; out_offset has n_edges+1
  * entries and *out_total = out_offset[n_edges].  If capacity (entries) is too small the call fails
- * with MPLX_ERR_ARG after filling out_offset and *out_total, so the caller can size and retry. */
+ * with MPLX_ERR_ARG after filling out_offset and *out_total, so the caller can size and retry.
+ * out_table_voxel / out_table_edge (both NULL, or capacity int32 each) receive the inverted table
+ * the reference keeps in lhm_ (map_planner.h:15-16,101): entry k says edge out_table_edge[k] passes
+ * through voxel getIndex = out_table_voxel[k]; sorted by voxel index, the edges of one voxel in
+ * emission order (edge index, then position along the edge) as lhm_[id] lists them. */
 int mplx_edges_cells(mplx_ctx *ctx, const mplx_waypoint *parents, const int32_t *actions, int n_edges,
-                     int64_t *out_offset, int32_t *out_cells, int64_t capacity, int64_t *out_total);
+                     int64_t *out_offset, int32_t *out_cells, int64_t capacity, int64_t *out_total,
+                     int32_t *out_table_voxel, int32_t *out_table_edge);
 
 /* Kernel selection (diagnostics): 0 = auto (the register kernel whenever |U| <= 256),
  * 1 = the sequential kernel that keeps traverse_primitive's literal per-primitive loop

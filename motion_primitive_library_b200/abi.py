@@ -135,7 +135,7 @@ def load() -> C.CDLL:
     lib.mplx_expand_packed.restype = i32
     lib.mplx_edges_is_free.argtypes = [vp, vp, vp, i32, vp, vp]
     lib.mplx_edges_is_free.restype = i32
-    lib.mplx_edges_cells.argtypes = [vp, vp, vp, i32, vp, vp, C.c_int64, C.POINTER(C.c_int64)]
+    lib.mplx_edges_cells.argtypes = [vp, vp, vp, i32, vp, vp, C.c_int64, C.POINTER(C.c_int64), vp, vp]
     lib.mplx_edges_cells.restype = i32
     lib.mplx_set_kernel.argtypes = [vp, i32]
     lib.mplx_set_kernel.restype = i32

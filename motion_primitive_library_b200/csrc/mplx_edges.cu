@@ -14,6 +14,7 @@
 // WITHOUT the max(5, .) of traverse_primitive, n+1 samples at t = i*(T/n) (a product, not the
 // running sum of env_map.h:99).  One thread per edge: these are maintenance queries (thousands to a
 // few million edges per map update), bandwidth is the occupancy bit grid in L2.
+#include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
 #include <cuda_runtime.h>
 #include <limits.h>
@@ -107,7 +108,8 @@ template <int DIM, int ORD, bool WRITE>
 __global__ void __launch_bounds__(128)
 edges_cells_kernel(const __grid_constant__ EnvParams P, const mplx_waypoint *__restrict__ parents,
                    const int32_t *__restrict__ actions, int n_edges, long long *__restrict__ count,
-                   const long long *__restrict__ offset, int32_t *__restrict__ cells) {
+                   const long long *__restrict__ offset, int32_t *__restrict__ cells, int32_t *__restrict__ ids,
+                   int32_t *__restrict__ owner) {
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= n_edges) return;
   EdgePrim<DIM, ORD> ep;
@@ -129,6 +131,10 @@ edges_cells_kernel(const __grid_constant__ EnvParams P, const mplx_waypoint *__r
       if (WRITE) {
 #pragma unroll
         for (int k = 0; k < DIM; k++) dst[k_out * DIM + k] = pn[k];
+        if (ids) {  // (voxel index, edge) pairs in emission order, for the inverted table
+          ids[offset[e] + k_out] = (int)id;
+          owner[offset[e] + k_out] = e;
+        }
       }
       k_out++;
       prev_id = (int)id;
@@ -152,13 +158,14 @@ static cudaError_t launch_free(const EnvParams &P, const mplx_waypoint *parents,
 
 template <int DIM, bool WRITE>
 static cudaError_t launch_cells(const EnvParams &P, const mplx_waypoint *parents, const int32_t *actions, int n,
-                                long long *count, const long long *offset, int32_t *cells, cudaStream_t st) {
+                                long long *count, const long long *offset, int32_t *cells, int32_t *ids, int32_t *owner,
+                                cudaStream_t st) {
   const int grid = (n + 127) / 128;
   switch (__builtin_popcount(P.control & 15)) {
-    case 1: edges_cells_kernel<DIM, 1, WRITE><<<grid, 128, 0, st>>>(P, parents, actions, n, count, offset, cells); break;
-    case 2: edges_cells_kernel<DIM, 2, WRITE><<<grid, 128, 0, st>>>(P, parents, actions, n, count, offset, cells); break;
-    case 3: edges_cells_kernel<DIM, 3, WRITE><<<grid, 128, 0, st>>>(P, parents, actions, n, count, offset, cells); break;
-    default: edges_cells_kernel<DIM, 4, WRITE><<<grid, 128, 0, st>>>(P, parents, actions, n, count, offset, cells); break;
+    case 1: edges_cells_kernel<DIM, 1, WRITE><<<grid, 128, 0, st>>>(P, parents, actions, n, count, offset, cells, ids, owner); break;
+    case 2: edges_cells_kernel<DIM, 2, WRITE><<<grid, 128, 0, st>>>(P, parents, actions, n, count, offset, cells, ids, owner); break;
+    case 3: edges_cells_kernel<DIM, 3, WRITE><<<grid, 128, 0, st>>>(P, parents, actions, n, count, offset, cells, ids, owner); break;
+    default: edges_cells_kernel<DIM, 4, WRITE><<<grid, 128, 0, st>>>(P, parents, actions, n, count, offset, cells, ids, owner); break;
   }
   return cudaGetLastError();
 }
@@ -198,9 +205,13 @@ extern "C" int mplx_edges_is_free(mplx_ctx *c, const mplx_waypoint *parents, con
 }
 
 extern "C" int mplx_edges_cells(mplx_ctx *c, const mplx_waypoint *parents, const int32_t *actions, int n_edges,
-                                int64_t *out_offset, int32_t *out_cells, int64_t capacity, int64_t *out_total) {
+                                int64_t *out_offset, int32_t *out_cells, int64_t capacity, int64_t *out_total,
+                                int32_t *out_table_voxel, int32_t *out_table_edge) {
   if (int r = check_edges(c, parents, actions, n_edges)) return r;
   if (!out_offset || !out_total) return fail(MPLX_ERR_ARG, "out_offset and out_total are required");
+  if ((out_table_voxel == nullptr) != (out_table_edge == nullptr))
+    return fail(MPLX_ERR_ARG, "out_table_voxel and out_table_edge go together");
+  const bool table = out_table_voxel != nullptr;
   *out_total = 0;
   out_offset[0] = 0;
   if (n_edges == 0) return MPLX_OK;
@@ -213,9 +224,9 @@ extern "C" int mplx_edges_cells(mplx_ctx *c, const mplx_waypoint *parents, const
   CU(cudaMemcpyAsync(B.actions.p, actions, sizeof(int32_t) * n_edges, cudaMemcpyHostToDevice, st));
   CU(cudaMemsetAsync(B.count.p + n_edges, 0, sizeof(long long), st));
   if (dim == 2)
-    CU((mplx::launch_cells<2, false>(c->P, B.parents.p, B.actions.p, n_edges, B.count.p, nullptr, nullptr, st)));
+    CU((mplx::launch_cells<2, false>(c->P, B.parents.p, B.actions.p, n_edges, B.count.p, nullptr, nullptr, nullptr, nullptr, st)));
   else
-    CU((mplx::launch_cells<3, false>(c->P, B.parents.p, B.actions.p, n_edges, B.count.p, nullptr, nullptr, st)));
+    CU((mplx::launch_cells<3, false>(c->P, B.parents.p, B.actions.p, n_edges, B.count.p, nullptr, nullptr, nullptr, nullptr, st)));
   // exclusive scan over n_edges+1 counts: offset[n_edges] = total
   size_t tmp_bytes = 0;
   CU(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, B.count.p, B.offset.p, n_edges + 1, st));
@@ -231,13 +242,30 @@ extern "C" int mplx_edges_cells(mplx_ctx *c, const mplx_waypoint *parents, const
     return fail(MPLX_ERR_ARG, "out_cells capacity %lld too small (need %lld entries)", (long long)capacity,
                 (long long)total);
   if (total == 0) return MPLX_OK;
+  if (total >= ((int64_t)1 << 31)) return fail(MPLX_ERR_ARG, "more than 2^31 linked voxels in one query");
   CU(B.cells.reserve((size_t)total * dim));
+  if (table) {
+    CU(B.ids.reserve(total)); CU(B.owner.reserve(total)); CU(B.ids_sorted.reserve(total)); CU(B.owner_sorted.reserve(total));
+  }
+  int32_t *ids = table ? B.ids.p : nullptr, *own = table ? B.owner.p : nullptr;
   if (dim == 2)
-    CU((mplx::launch_cells<2, true>(c->P, B.parents.p, B.actions.p, n_edges, nullptr, B.offset.p, B.cells.p, st)));
+    CU((mplx::launch_cells<2, true>(c->P, B.parents.p, B.actions.p, n_edges, nullptr, B.offset.p, B.cells.p, ids, own, st)));
   else
-    CU((mplx::launch_cells<3, true>(c->P, B.parents.p, B.actions.p, n_edges, nullptr, B.offset.p, B.cells.p, st)));
+    CU((mplx::launch_cells<3, true>(c->P, B.parents.p, B.actions.p, n_edges, nullptr, B.offset.p, B.cells.p, ids, own, st)));
   c->launches += 1;
   CU(cudaMemcpyAsync(out_cells, B.cells.p, sizeof(int32_t) * (size_t)total * dim, cudaMemcpyDeviceToHost, st));
+  if (table) {
+    // voxel -> edges table: the pairs sorted by voxel index; the radix sort is stable, so the
+    // edges of one voxel stay in emission order (the push_back order of lhm_[id], map_planner.cpp:149)
+    size_t sort_bytes = 0;
+    CU(cub::DeviceRadixSort::SortPairs(nullptr, sort_bytes, B.ids.p, B.ids_sorted.p, B.owner.p, B.owner_sorted.p, (int)total,
+                                       0, 32, st));
+    CU(B.scan_tmp.reserve(sort_bytes));
+    CU(cub::DeviceRadixSort::SortPairs(B.scan_tmp.p, sort_bytes, B.ids.p, B.ids_sorted.p, B.owner.p, B.owner_sorted.p,
+                                       (int)total, 0, 32, st));
+    CU(cudaMemcpyAsync(out_table_voxel, B.ids_sorted.p, sizeof(int32_t) * (size_t)total, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(out_table_edge, B.owner_sorted.p, sizeof(int32_t) * (size_t)total, cudaMemcpyDeviceToHost, st));
+  }
   CU(cudaStreamSynchronize(st));
   return MPLX_OK;
 }

@@ -104,13 +104,13 @@ struct ChunkBufs {
 // staging of the edge re-validation queries (mplx_edges.cu)
 struct EdgeBufs {
   DevBuf<mplx_waypoint> parents;
-  DevBuf<int32_t> actions, cells;
+  DevBuf<int32_t> actions, cells, ids, owner, ids_sorted, owner_sorted;
   DevBuf<uint8_t> free_, scan_tmp;
   DevBuf<double> cost;
   DevBuf<long long> count, offset;
   void release() {
     parents.release(); actions.release(); cells.release(); free_.release(); scan_tmp.release(); cost.release();
-    count.release(); offset.release();
+    count.release(); offset.release(); ids.release(); owner.release(); ids_sorted.release(); owner_sorted.release();
   }
 };
 

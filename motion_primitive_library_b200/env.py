@@ -300,10 +300,12 @@ class env_map:
                                                free.ctypes.data, cost.ctypes.data))
         return free, cost
 
-    def edge_cells(self, parents: np.ndarray, actions: np.ndarray):
+    def edge_cells(self, parents: np.ndarray, actions: np.ndarray, table: bool = False):
         """The voxel walk of MapPlanner::getLinkedNodes (map_planner.cpp:135-151) for stored edges:
         returns (offset int64[n+1], cells int32[total, Dim]); edge i passes through
-        cells[offset[i]:offset[i+1]] (consecutive repeats removed)."""
+        cells[offset[i]:offset[i+1]] (consecutive repeats removed).  With table=True also the
+        inverted voxel -> edges table (the reference's lhm_) as (voxel int32[total], edge int32[total]),
+        sorted by voxel index, edges of one voxel in emission order."""
         self._sync_params()
         parents = np.ascontiguousarray(parents, dtype=WAYPOINT_DTYPE).reshape(-1)
         actions = np.ascontiguousarray(actions, dtype=np.int32).reshape(-1)
@@ -315,10 +317,13 @@ class env_map:
         cap = max(1, 8 * n)
         for _ in range(2):
             cells = np.zeros((cap, self.Dim), dtype=np.int32)
+            tv = np.zeros(cap, dtype=np.int32) if table else None
+            te = np.zeros(cap, dtype=np.int32) if table else None
             rc = self._lib.mplx_edges_cells(self._h, parents.ctypes.data, actions.ctypes.data, n, off.ctypes.data,
-                                            cells.ctypes.data, cap, C.byref(total))
+                                            cells.ctypes.data, cap, C.byref(total), abi.ptr(tv), abi.ptr(te))
             if rc == 0:
-                return off, cells[: total.value]
+                t = total.value
+                return (off, cells[:t], tv[:t], te[:t]) if table else (off, cells[:t])
             if total.value <= cap:
                 abi.check(rc)
             cap = int(total.value)

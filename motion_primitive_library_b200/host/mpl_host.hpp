@@ -222,13 +222,15 @@ class env_base {
   ///  - is_free_edges: is_free(pr) (env_base.h:338-341, env_map.h:60-76) and
   ///    calculate_intrinsic_cost(pr) (env_base.h:343-345) per edge;
   ///  - edge_cells: the cells getLinkedNodes visits along each edge (map_planner.cpp:135-151),
-  ///    edge k owning cells[offset[k]*Dim .. offset[k+1]*Dim).
+  ///    edge k owning cells[offset[k]*Dim .. offset[k+1]*Dim); an env that can also returns the
+  ///    inverted table (table_voxel sorted, table_edge the edge of each entry, edges of one voxel in
+  ///    emission order), else leaves both empty and the planner sorts on the host.
   virtual void is_free_edges(const vec_E<Waypoint<Dim>> &, const std::vector<int> &, std::vector<uint8_t> &,
                              std::vector<decimal_t> &) const {
     throw std::runtime_error("this env does not serve edge re-validation");
   }
   virtual void edge_cells(const vec_E<Waypoint<Dim>> &, const std::vector<int> &, std::vector<long long> &,
-                          std::vector<int> &) const {
+                          std::vector<int> &, std::vector<int> &, std::vector<int> &) const {
     throw std::runtime_error("this env does not serve edge re-validation");
   }
   virtual bool wants_candidates(std::size_t) const { return false; }
@@ -369,22 +371,22 @@ class env_map_gpu : public env_map_host<Dim> {
   }
   /// the getLinkedNodes voxel walk for stored edges on the device (mplx_edges_cells)
   void edge_cells(const vec_E<Waypoint<Dim>> &parents, const std::vector<int> &actions, std::vector<long long> &offset,
-                  std::vector<int> &cells) const override {
+                  std::vector<int> &cells, std::vector<int> &table_voxel, std::vector<int> &table_edge) const override {
     sync();
     std::vector<mplx_waypoint> in(parents.size());
     for (std::size_t i = 0; i < parents.size(); i++) in[i] = to_pod(parents[i]);
     offset.assign(parents.size() + 1, 0);
     int64_t total = 0;
-    cells.resize(std::max<std::size_t>(1, 16 * parents.size()) * Dim);
-    int rc = mplx_edges_cells(ctx_, in.data(), actions.data(), (int)parents.size(), (int64_t *)offset.data(), cells.data(),
-                              (int64_t)(cells.size() / Dim), &total);
-    if (rc != MPLX_OK && total > (int64_t)(cells.size() / Dim)) {  // sized from the reported total
-      cells.resize((std::size_t)total * Dim);
-      rc = mplx_edges_cells(ctx_, in.data(), actions.data(), (int)parents.size(), (int64_t *)offset.data(), cells.data(),
-                            total, &total);
+    std::size_t cap = std::max<std::size_t>(1, 32 * parents.size());
+    for (int attempt = 0;; attempt++) {
+      cells.resize(cap * Dim); table_voxel.resize(cap); table_edge.resize(cap);
+      const int rc = mplx_edges_cells(ctx_, in.data(), actions.data(), (int)parents.size(), (int64_t *)offset.data(),
+                                      cells.data(), (int64_t)cap, &total, table_voxel.data(), table_edge.data());
+      if (rc == MPLX_OK) break;
+      if (attempt > 0 || total <= (int64_t)cap) check(rc);
+      cap = (std::size_t)total;  // sized from the reported total
     }
-    check(rc);
-    cells.resize((std::size_t)total * Dim);
+    cells.resize((std::size_t)total * Dim); table_voxel.resize((std::size_t)total); table_edge.resize((std::size_t)total);
   }
 
   /// Packed batched expansion for lock-step drivers (mplx_expand_packed, +inf successors dropped
@@ -1189,61 +1191,93 @@ class MapPlanner : public PlannerBase<Dim> {
   void setGradientWeight(decimal_t w) { this->ENV_->set_gradient_weight(w); }
   env_map_gpu<Dim> *gpu_env() { return gpu_env_.get(); }
 
+  /// The reference's lhm_ (map_planner.h:15-16,101: voxel index -> the (state, i-th predecessor)
+  /// edges through it) kept as a table sorted by voxel index; the edges of one voxel are in the
+  /// order getLinkedNodes' push_backs would have left them.
+  struct LinkedTable {
+    std::vector<int> voxel, edge;                          // sorted by voxel (stable)
+    std::vector<std::pair<State<Dim> *, int>> owner;       // edge -> (state, pred index)
+    void clear() { voxel.clear(); edge.clear(); owner.clear(); }
+    /// append the edges through voxel `id`, in lhm_[id] order
+    void collect(int id, std::vector<std::pair<State<Dim> *, int>> &out) const {
+      auto r = std::equal_range(voxel.begin(), voxel.end(), id);
+      for (auto it = r.first; it != r.second; ++it) out.push_back(owner[edge[it - voxel.begin()]]);
+    }
+  };
+
   /// getLinkedNodes: src/mpl_planner/map_planner.cpp:124-157.  Every stored edge (state, i-th
   /// predecessor) is walked through the grid — on the device for the GPU env, all edges in one
-  /// batch — and entered into lhm_ under each voxel it touches; returns the voxel centres.
+  /// batch, which also sorts the (voxel, edge) pairs into the table — and the voxel centres are
+  /// returned in the reference's order.
   vec_E<Vecf<Dim>> getLinkedNodes() const {
     using S = State<Dim>;
+    const auto t_begin = std::chrono::steady_clock::now();
     lhm_.clear();
     vec_E<Vecf<Dim>> linked_pts;
     vec_E<Waypoint<Dim>> parents;
     std::vector<int> actions;
-    std::vector<std::pair<S *, int>> owner;
+    std::size_t n_edges = 0;
+    for (const S *st : this->ss_ptr_->order_) n_edges += st->pred.size();
+    parents.reserve(n_edges); actions.reserve(n_edges); lhm_.owner.reserve(n_edges);
     for (S *st : this->ss_ptr_->order_)
       for (std::size_t i = 0; i < st->pred.size(); i++) {
         parents.push_back(st->pred[i].node->coord);
         actions.push_back(st->pred[i].action_id);
-        owner.emplace_back(st, (int)i);
+        lhm_.owner.emplace_back(st, (int)i);
       }
     std::vector<long long> offset;
     std::vector<int> cells;
-    if (!parents.empty()) this->ENV_->edge_cells(parents, actions, offset, cells);
+    if (parents.empty()) return linked_pts;
+    const auto t_env0 = std::chrono::steady_clock::now();
+    this->ENV_->edge_cells(parents, actions, offset, cells, lhm_.voxel, lhm_.edge);
+    const auto t_env1 = std::chrono::steady_clock::now();
+    const std::size_t total = cells.size() / Dim;
     const decimal_t res = map_util_->getRes();
     const Vecf<Dim> ori = map_util_->getOrigin();
-    for (std::size_t e = 0; e < parents.size(); e++)
-      for (long long c = offset[e]; c < offset[e + 1]; c++) {
-        Veci<Dim> pn;
-        for (int k = 0; k < Dim; k++) pn(k) = cells[c * Dim + k];
-        Vecf<Dim> pt;  // intToFloat: map_util.h:110-113
-        for (int k = 0; k < Dim; k++) pt(k) = (pn(k) + 0.5) * res + ori(k);
-        linked_pts.push_back(pt);
-        lhm_[map_util_->getIndex(pn)].push_back(owner[e]);
-      }
+    const bool host_table = lhm_.voxel.size() != total;
+    std::vector<int> ids;
+    if (host_table) ids.resize(total);
+    linked_pts.resize(total);
+    for (std::size_t c = 0; c < total; c++) {
+      Veci<Dim> pn;
+      for (int k = 0; k < Dim; k++) pn(k) = cells[c * Dim + k];
+      for (int k = 0; k < Dim; k++) linked_pts[c](k) = (pn(k) + 0.5) * res + ori(k);  // intToFloat: map_util.h:110-113
+      if (host_table) ids[c] = map_util_->getIndex(pn);
+    }
+    if (host_table) {  // an env without the device sort: stable sort of the (voxel, edge) pairs here
+      std::vector<int> owner_of(total), perm(total);
+      for (std::size_t e = 0; e < parents.size(); e++)
+        for (long long c = offset[e]; c < offset[e + 1]; c++) owner_of[c] = (int)e;
+      for (std::size_t c = 0; c < total; c++) perm[c] = (int)c;
+      std::stable_sort(perm.begin(), perm.end(), [&](int x, int y) { return ids[x] < ids[y]; });
+      lhm_.voxel.resize(total); lhm_.edge.resize(total);
+      for (std::size_t c = 0; c < total; c++) { lhm_.voxel[c] = ids[perm[c]]; lhm_.edge[c] = owner_of[perm[c]]; }
+    }
+    if (std::getenv("MPLH_TRACE")) {
+      auto ms = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) {
+        return std::chrono::duration<double, std::milli>(b - a).count();
+      };
+      std::fprintf(stderr, "[getLinkedNodes] %zu edges, %zu voxels: gather %.1f ms, env walk %.1f ms, points/table %.1f ms\n",
+                   parents.size(), total, ms(t_begin, t_env0), ms(t_env0, t_env1), ms(t_env1, std::chrono::steady_clock::now()));
+    }
     return linked_pts;
   }
   /// updateBlockedNodes: map_planner.cpp:159-171
   void updateBlockedNodes(const vec_E<Veci<Dim>> &blocked_pns) {
     std::vector<std::pair<State<Dim> *, int>> blocked_nodes;
-    for (const auto &it : blocked_pns) {
-      auto search = lhm_.find(map_util_->getIndex(it));
-      if (search != lhm_.end()) blocked_nodes.insert(blocked_nodes.end(), search->second.begin(), search->second.end());
-    }
+    for (const auto &it : blocked_pns) lhm_.collect(map_util_->getIndex(it), blocked_nodes);
     this->ss_ptr_->increaseCost(blocked_nodes);
   }
   /// updateClearedNodes: map_planner.cpp:173-185; the is_free(pr) re-validation runs batched in the env
   void updateClearedNodes(const vec_E<Veci<Dim>> &cleared_pns) {
     std::vector<std::pair<State<Dim> *, int>> cleared_nodes;
-    for (const auto &it : cleared_pns) {
-      auto search = lhm_.find(map_util_->getIndex(it));
-      if (search != lhm_.end()) cleared_nodes.insert(cleared_nodes.end(), search->second.begin(), search->second.end());
-    }
+    for (const auto &it : cleared_pns) lhm_.collect(map_util_->getIndex(it), cleared_nodes);
     this->ss_ptr_->decreaseCost(cleared_nodes, *this->ENV_);
   }
-  const std::unordered_map<int, std::vector<std::pair<State<Dim> *, int>>> &linkedTable() const { return lhm_; }
+  const LinkedTable &linkedTable() const { return lhm_; }
 
  protected:
-  /// voxel index -> (state, i-th predecessor) edges through it (map_planner.h:15-16,101)
-  mutable std::unordered_map<int, std::vector<std::pair<State<Dim> *, int>>> lhm_;
+  mutable LinkedTable lhm_;
   std::shared_ptr<MapUtil<Dim>> map_util_;
   std::shared_ptr<env_map_gpu<Dim>> gpu_env_;
   Vecf<Dim> potential_radius_, potential_map_range_, search_radius_;

@@ -35,7 +35,8 @@ class env_map_oracle : public MPL::env_map_host<Dim> {
     orc_edges_is_free(&e, in.data(), actions.data(), (int)parents.size(), free.data(), cost.data());
   }
   void edge_cells(const vec_E<Waypoint<Dim>> &parents, const std::vector<int> &actions, std::vector<long long> &offset,
-                  std::vector<int> &cells) const override {
+                  std::vector<int> &cells, std::vector<int> &table_voxel, std::vector<int> &table_edge) const override {
+    table_voxel.clear(); table_edge.clear();  // the planner sorts on the host
     const orc_env e = env();
     std::vector<orc_waypoint> in(parents.size());
     for (std::size_t i = 0; i < parents.size(); i++) in[i] = pod(parents[i]);

@@ -27,6 +27,16 @@ def check(sc, nodes, region=None, extra=500, seed=0):
     go, gc = env.edge_cells(parents, actions)
     np.testing.assert_array_equal(go, oo)
     np.testing.assert_array_equal(gc, oc)
+    # the inverted voxel -> edges table: a STABLE sort of the emitted (getIndex, edge) pairs by voxel
+    go2, gc2, tv, te = env.edge_cells(parents, actions, table=True)
+    np.testing.assert_array_equal(gc2, oc)
+    dims = np.asarray(sc.dim_cells, dtype=np.int64)
+    strides = np.concatenate([[1], np.cumprod(dims[:-1])])
+    ids = ((oc.astype(np.int64) * strides).sum(1)).astype(np.int32)      # int32 wrap-around as getIndex
+    owner = np.repeat(np.arange(parents.size, dtype=np.int32), np.diff(oo))
+    order = np.argsort(ids, kind="stable")
+    np.testing.assert_array_equal(tv, ids[order])
+    np.testing.assert_array_equal(te, owner[order])
     assert 0 < fo.sum() < fo.size and oc.shape[0] > parents.size
     return env, parents, actions
 
@@ -72,7 +82,7 @@ def test_capacity_retry_empty_and_errors():
     total = C.c_int64(0)
     small = np.zeros((4, 3), dtype=np.int32)
     rc = env._lib.mplx_edges_cells(env._h, parents.ctypes.data, actions.ctypes.data, n, off.ctypes.data,
-                                   small.ctypes.data, 4, C.byref(total))
+                                   small.ctypes.data, 4, C.byref(total), None, None)
     assert rc != 0 and total.value > 4 and off[-1] == total.value
     # an action id outside U
     bad = actions.copy()
