@@ -25,6 +25,9 @@
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
+#include <new>
+#include <type_traits>
 #include <deque>
 #include <limits>
 #include <memory>
@@ -182,8 +185,11 @@ class env_base {
     return goaled;
   }
   /// env_base.h:48-64 (heur_ignore_dynamics_ == true, the default: :368)
-  virtual decimal_t get_heur(const Waypoint<Dim> &state) const {
-    if (hash_value(goal_node_) == hash_value(state)) return 0;
+  virtual decimal_t get_heur(const Waypoint<Dim> &state) const { return get_heur(state, hash_value(state)); }
+  /// the same with the state's lattice key already known (the device returns it with the successor);
+  /// `goal_node_ == state` is hash equality (waypoint.h:133-135), the goal's hash is cached by set_goal
+  virtual decimal_t get_heur(const Waypoint<Dim> &state, std::size_t state_key) const {
+    if (goal_key_ == state_key) return 0;
     if (v_max_ > 0) return w_ * (state.pos - goal_node_.pos).lpNormInf() / v_max_;
     return w_ * (state.pos - goal_node_.pos).lpNormInf();
   }
@@ -200,7 +206,7 @@ class env_base {
   void set_w(decimal_t w) { w_ = w; touch(); }
   void set_wyaw(decimal_t wyaw) { wyaw_ = wyaw; touch(); }
   void set_t_max(int t) { t_max_ = t; }
-  bool set_goal(const Waypoint<Dim> &state) { goal_node_ = state; return true; }
+  bool set_goal(const Waypoint<Dim> &state) { goal_node_ = state; goal_key_ = hash_value(state); return true; }
   virtual void set_potential_weight(decimal_t) {}
   virtual void set_gradient_weight(decimal_t) {}
   virtual void set_potential_map(const std::vector<int8_t> &) {}
@@ -246,6 +252,7 @@ class env_base {
   decimal_t dt_{1.0};
   vec_E<VecDf> U_;
   Waypoint<Dim> goal_node_;
+  std::size_t goal_key_{hash_value(Waypoint<Dim>())};
   std::vector<bool> search_region_;
   mutable vec_E<Vecf<Dim>> expanded_nodes_;
 
@@ -518,6 +525,47 @@ class env_map_gpu : public env_map_host<Dim> {
   mutable long stats_nodes_ = 0, stats_calls_ = 0, stats_hits_ = 0;
 };
 
+/// A vector with room for N elements inside the object: most states have one or two predecessors,
+/// so the common case needs no heap allocation.  Only what the planner uses.
+template <typename T, int N>
+class SmallVec {
+ public:
+  SmallVec() {}
+  SmallVec(const SmallVec &) = delete;
+  SmallVec &operator=(const SmallVec &) = delete;
+  ~SmallVec() { if (heap_) std::free(heap_); }
+  std::size_t size() const { return n_; }
+  bool empty() const { return n_ == 0; }
+  void clear() { n_ = 0; }
+  T *begin() { return data(); }
+  T *end() { return data() + n_; }
+  const T *begin() const { return data(); }
+  const T *end() const { return data() + n_; }
+  T &operator[](std::size_t i) { return data()[i]; }
+  const T &operator[](std::size_t i) const { return data()[i]; }
+  void push_back(const T &v) {
+    if (n_ == cap_) grow();
+    data()[n_++] = v;
+  }
+
+ private:
+  static_assert(std::is_trivially_copyable<T>::value, "SmallVec holds plain records");
+  T *data() { return heap_ ? heap_ : inl_; }
+  const T *data() const { return heap_ ? heap_ : inl_; }
+  void grow() {
+    const unsigned nc = cap_ * 2;
+    T *p = (T *)std::malloc(sizeof(T) * nc);
+    if (!p) throw std::bad_alloc();
+    std::memcpy(p, data(), sizeof(T) * n_);
+    if (heap_) std::free(heap_);
+    heap_ = p;
+    cap_ = nc;
+  }
+  T inl_[N];
+  T *heap_ = nullptr;
+  unsigned n_ = 0, cap_ = N;
+};
+
 /// State: include/mpl_planner/common/state_space.h:36-74 (A* members)
 template <int Dim>
 struct State {
@@ -530,7 +578,7 @@ struct State {
     decimal_t action_cost;
     int action_id;
   };
-  std::vector<Pred> pred;
+  SmallVec<Pred, 1> pred;
   /// succ_coord / succ_action_id / succ_action_cost (state_space.h:40-45), LPA* only.  The
   /// successor is looked up again by its lattice key when the node is re-expanded (hm_[succ_coord],
   /// graph_search.h:282), so a state pruned from the space in between is re-created, as there.
@@ -618,11 +666,29 @@ struct StateSpace {
   /// of getSubStateSpace :184-192 and getLinkedNodes depend on it).
   std::unordered_map<std::size_t, S *> hm_;
   std::vector<S *> order_;
-  std::deque<S> arena_;
+  /// states are carved out of 256-state blocks: one allocation per block, addresses never move
+  struct Arena {
+    static constexpr std::size_t kBlock = 256;
+    std::vector<S *> blocks;
+    std::size_t used = kBlock;
+    S *emplace(const Waypoint<Dim> &c, std::size_t k) {
+      if (used == kBlock) {
+        blocks.push_back((S *)::operator new(sizeof(S) * kBlock));
+        used = 0;
+      }
+      return new (blocks.back() + used++) S(c, k);
+    }
+    ~Arena() {
+      for (std::size_t b = 0; b < blocks.size(); b++) {
+        const std::size_t n = b + 1 == blocks.size() ? used : kBlock;
+        for (std::size_t i = 0; i < n; i++) blocks[b][i].~S();
+        ::operator delete(blocks[b]);
+      }
+    }
+  } arena_;
   /// hm_[coord] of a key that is not in the map yet: create the state and enter it
   S *make_state(const Waypoint<Dim> &c, std::size_t k) {
-    arena_.emplace_back(c, k);
-    S *n = &arena_.back();
+    S *n = arena_.emplace(c, k);
     hm_[k] = n;
     order_.push_back(n);
     return n;
@@ -638,8 +704,7 @@ struct StateSpace {
     auto ins = hm_.try_emplace(k, nullptr);
     created = ins.second;
     if (created) {
-      arena_.emplace_back(coord(), k);
-      ins.first->second = &arena_.back();
+      ins.first->second = arena_.emplace(coord(), k);
       order_.push_back(ins.first->second);
     }
     return ins.first->second;
@@ -888,7 +953,7 @@ class AstarStepper {
       const std::size_t skey = key_at(s);
       bool created;
       S *succNode_ptr = ss_ptr->get_or_make(skey, [&] { return succ_at(s); }, created);
-      if (created) succNode_ptr->h = ss_ptr->eps_ == 0 ? 0 : ENV->get_heur(succNode_ptr->coord);
+      if (created) succNode_ptr->h = ss_ptr->eps_ == 0 ? 0 : ENV->get_heur(succNode_ptr->coord, skey);
       succNode_ptr->pred.push_back(typename S::Pred{curr_, succ_cost[s], succ_act_id[s]});
       const decimal_t tentative_gval = curr_->g + succ_cost[s];
       if (tentative_gval < succNode_ptr->g) {
@@ -1054,7 +1119,7 @@ class GraphSearch {
       for (std::size_t s = 0; s < succ_coord.size(); ++s) {
         bool created;
         S *succNode_ptr = ss_ptr->get_or_make(succ_key[s], [&] { return succ_coord[s]; }, created);
-        if (created) succNode_ptr->h = ss_ptr->eps_ == 0 ? 0 : ENV->get_heur(succNode_ptr->coord);
+        if (created) succNode_ptr->h = ss_ptr->eps_ == 0 ? 0 : ENV->get_heur(succNode_ptr->coord, succ_key[s]);
         currNode_ptr->succ[s] = typename S::Succ{succNode_ptr, succ_cost[s], succ_act_id[s]};
         int id = -1;
         for (std::size_t i = 0; i < succNode_ptr->pred.size(); i++)
@@ -1413,18 +1478,15 @@ class MultiQueryPlanner {
 
   std::vector<Result> plan(const vec_E<Waypoint<Dim>> &starts, const vec_E<Waypoint<Dim>> &goals, decimal_t eps,
                            int max_expand) {
+    release();
     WorkerPool pool(host_threads_ > 0 ? host_threads_ : effective_cpus());
-    // per-query host env: goal test + heuristic only (its get_succ is never called)
-    struct QueryEnv : env_map_host<Dim> {
-      using env_map_host<Dim>::env_map_host;
-      void get_succ(const Waypoint<Dim> &, vec_E<Waypoint<Dim>> &, std::vector<decimal_t> &, std::vector<int> &) const override {}
-    };
     const std::size_t Q = starts.size();
-    std::vector<std::unique_ptr<QueryEnv>> envs(Q);
-    std::vector<std::shared_ptr<StateSpace<Dim>>> ss(Q);
-    std::vector<std::unique_ptr<AstarStepper<Dim>>> st(Q);
+    auto &envs = envs_;
+    auto &ss = ss_;
+    auto &st = st_;
+    envs.resize(Q); ss.resize(Q); st.resize(Q);
     std::vector<Result> res(Q);
-    for (std::size_t q = 0; q < Q; q++) {
+    pool.run(Q, [&](std::size_t q) {
       envs[q].reset(new QueryEnv(map_util_));
       QueryEnv &e = *envs[q];
       e.w_ = gpu_->w_; e.v_max_ = gpu_->v_max_; e.dt_ = gpu_->dt_; e.t_max_ = gpu_->t_max_;
@@ -1433,7 +1495,7 @@ class MultiQueryPlanner {
       ss[q].reset(new StateSpace<Dim>(eps));
       st[q].reset(new AstarStepper<Dim>(&e, ss[q], max_expand));
       if (e.is_free(starts[q].pos)) st[q]->start(starts[q]);  // planner_base.h:283-287
-    }
+    });
     std::vector<mplx_waypoint> batch;
     std::vector<std::size_t> who;
     iterations_ = nodes_ = 0;
@@ -1466,18 +1528,40 @@ class MultiQueryPlanner {
       t_dev_ += std::chrono::duration<double>(t2 - t1).count();
       t_relax_ += std::chrono::duration<double>(t3 - t2).count();
     }
-    for (std::size_t q = 0; q < Q; q++) {
+    // trace back and count on the pool; the state spaces stay until release() / the next plan()
+    pool.run(Q, [&](std::size_t q) {
       std::vector<Edge<Dim>> traj;
       res[q].cost = st[q]->finish(traj);
       res[q].valid = !std::isinf(res[q].cost);
       res[q].expanded = st[q]->expanded();
       for (const auto &e : traj) res[q].actions.push_back(e.action_id);
       for (const auto *stt : ss[q]->order_) if (stt->iterationclosed) res[q].n_closed++;
-    }
+    });
     return res;
   }
+  /// Free the search states of the last plan() (tens of millions of states for a large batch), on
+  /// the host cores.  Called by the next plan() and the destructor.
+  void release() {
+    if (ss_.empty()) return;
+    WorkerPool pool(host_threads_ > 0 ? host_threads_ : effective_cpus());
+    pool.run(ss_.size(), [&](std::size_t q) {
+      st_[q].reset();
+      ss_[q].reset();
+      envs_[q].reset();
+    });
+    st_.clear(); ss_.clear(); envs_.clear();
+  }
+  ~MultiQueryPlanner() { release(); }
 
  private:
+  // per-query host env: goal test + heuristic only (its get_succ is never called)
+  struct QueryEnv : env_map_host<Dim> {
+    using env_map_host<Dim>::env_map_host;
+    void get_succ(const Waypoint<Dim> &, vec_E<Waypoint<Dim>> &, std::vector<decimal_t> &, std::vector<int> &) const override {}
+  };
+  std::vector<std::unique_ptr<QueryEnv>> envs_;
+  std::vector<std::shared_ptr<StateSpace<Dim>>> ss_;
+  std::vector<std::unique_ptr<AstarStepper<Dim>>> st_;
   std::shared_ptr<MapUtil<Dim>> map_util_;
   std::unique_ptr<env_map_gpu<Dim>> gpu_;
   long iterations_ = 0, nodes_ = 0;

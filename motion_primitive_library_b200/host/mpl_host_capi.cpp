@@ -70,7 +70,8 @@ int mplh_lpa_run(const mplh_plan_args *a, const mplh_lpa_step *steps, int n_step
 /* Lock-step batched A* over n_q (start, goal) pairs on the map/params of `a` (a->start/goal are
  * ignored).  totals[0] = lock-step iterations (= device launches of the expansion kernel),
  * totals[1] = nodes expanded over all queries, totals[2] = wall seconds of the search,
- * totals[3..5] = seconds in the pop / device expansion (incl. PCIe) / relax phases. */
+ * totals[3..5] = seconds in the pop / device expansion (incl. PCIe) / relax phases,
+ * totals[6] = seconds spent freeing the search states afterwards (7 doubles). */
 int mplh_plan_batch(const mplh_plan_args *a, const mplx_waypoint *starts, const mplx_waypoint *goals, int n_q,
                     mplh_query_result *out, double *totals) {
   try {
@@ -107,9 +108,12 @@ int mplh_plan_batch(const mplh_plan_args *a, const mplx_waypoint *starts, const 
         out[q].n_closed = (int)res[q].n_closed;
         out[q].n_actions = (int)res[q].actions.size();
       }
+      auto t1 = std::chrono::steady_clock::now();
+      mq.release();
+      const double secs_release = std::chrono::duration<double>(std::chrono::steady_clock::now() - t1).count();
       if (totals) {
         totals[0] = (double)mq.iterations(); totals[1] = (double)mq.nodes_expanded(); totals[2] = secs;
-        totals[3] = mq.t_pop(); totals[4] = mq.t_device(); totals[5] = mq.t_relax();
+        totals[3] = mq.t_pop(); totals[4] = mq.t_device(); totals[5] = mq.t_relax(); totals[6] = secs_release;
       }
     };
     if (a->dim == 2) go(std::integral_constant<int, 2>());

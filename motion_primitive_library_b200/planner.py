@@ -182,7 +182,7 @@ def plan_batch(args, starts, goals):
     goals = np.ascontiguousarray(goals, dtype=WAYPOINT_DTYPE)
     nq = len(starts)
     out = (QueryResult * max(nq, 1))()
-    totals = np.zeros(6)
+    totals = np.zeros(7)
     rc = lib.mplh_plan_batch(C.byref(args), starts.ctypes.data, goals.ctypes.data, nq, out, totals.ctypes.data)
     if rc != 0:
         raise RuntimeError(lib.mplh_last_error().decode())
@@ -190,4 +190,4 @@ def plan_batch(args, starts, goals):
     for q in range(nq):
         res[q] = (out[q].valid, out[q].cost, out[q].expanded, out[q].n_closed, out[q].n_actions)
     return res, dict(iterations=int(totals[0]), nodes=int(totals[1]), seconds=float(totals[2]), t_pop=float(totals[3]),
-                     t_device=float(totals[4]), t_relax=float(totals[5]))
+                     t_device=float(totals[4]), t_relax=float(totals[5]), t_release=float(totals[6]))
