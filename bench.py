@@ -44,7 +44,7 @@ def parse():
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--kernel", type=int, default=0, help="0 = auto (register kernel), 1 = literal loop, 2 = register, 3 = flat")
+    ap.add_argument("--kernel", type=int, default=0, help="0 = auto, 1 = literal loop, 2 = register, 3 = flat, 4 = dealing")
     return ap.parse_args()
 
 
@@ -230,6 +230,15 @@ def run_reference(args, sc, rank, world):
     print(json.dumps(line), flush=True)
 
 
+def kernel_name(which, sc):
+    """The kernel mplx_set_kernel(which) launches for this workload (auto rule: mplx_kernels.cu launch_expand)."""
+    names = {1: "mplx::expand_seq_kernel", 2: "mplx::expand_reg_kernel", 3: "mplx::expand_flat_kernel", 4: "mplx::expand_deal_kernel"}
+    if which in names:
+        return names[which]
+    heavy = (sc.control & 15) >= 7 or (sc.control & 16) != 0 or sc.potential() is not None
+    return "mplx::expand_deal_kernel" if heavy else "mplx::expand_reg_kernel"
+
+
 def main():
     args = parse()
     rank = int(os.environ.get("RANK", "0"))
@@ -400,7 +409,7 @@ def main():
     achieved = bytes_per_exp * n / (k_ms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s", "frac": achieved / peak_gbs,
                 "traffic": None, "peak_source": "measured" if pk.exists() else "fallback",
-                "kernel": "mplx::expand_reg_kernel" if args.kernel in (0, 2) else f"kernel {args.kernel}", "kernel_ms": k_ms,
+                "kernel": kernel_name(args.kernel, sc), "kernel_ms": k_ms,
                 "algorithmic_bytes_per_expansion": bytes_per_exp,
                 "mean_samples_per_expansion": mean_samples, "mean_successors_per_expansion": mean_succ}
     prof = ROOT / "profiles" / "traffic.json"

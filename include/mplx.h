@@ -197,10 +197,12 @@ int mplx_edges_cells(mplx_ctx *ctx, const mplx_waypoint *parents, const int32_t 
                      int64_t *out_offset, int32_t *out_cells, int64_t capacity, int64_t *out_total,
                      int32_t *out_table_voxel, int32_t *out_table_edge);
 
-/* Kernel selection (diagnostics): 0 = auto (the register kernel whenever |U| <= 256),
+/* Kernel selection (diagnostics): 0 = auto (the dealing kernel for JRK/SNP controls, yaw controls
+ * and potential-field planning once a batch fills the GPU, else the register kernel),
  * 1 = the sequential kernel that keeps traverse_primitive's literal per-primitive loop
  * (env_map.h:99-130), 2 = the register kernel, 3 = the flat (sample-parallel, shared-memory
- * staged) kernel.  All produce identical results. */
+ * staged) kernel, 4 = the dealing kernel (sampling pulled from a CTA-wide ticket queue).  All
+ * produce identical results. */
 int mplx_set_kernel(mplx_ctx *ctx, int which);
 
 /* Synchronise the ctx stream. */

@@ -340,7 +340,8 @@ int mplx_expand(mplx_ctx *c, const mplx_waypoint *nodes, int n_nodes, const mplx
 
 int mplx_set_kernel(mplx_ctx *c, int which) {
   if (!c) return fail(MPLX_ERR_ARG, "null ctx");
-  if (which < 0 || which > 3) return fail(MPLX_ERR_ARG, "which must be 0 (auto: register), 1 (sequential), 2 (register) or 3 (flat)");
+  if (which < 0 || which > 4)
+    return fail(MPLX_ERR_ARG, "which must be 0 (auto), 1 (sequential), 2 (register), 3 (flat) or 4 (dealing)");
   c->force_seq = which;
   return MPLX_OK;
 }

@@ -1,0 +1,267 @@
+// mplx_deal.cu — expand_deal_kernel: the expansion with phase C dealt from a CTA-wide queue.
+//
+// In the register kernel (mplx_kernels.cu) a thread keeps the primitive it built through the
+// sample loop, so a warp runs until its longest primitive is done while lanes whose primitive was
+// rejected, is short or hit an obstacle early idle: on the 512^3 ACC-27 workload only ~54 % of the
+// lane-steps of the sample loop do work, ~37 % with JRK-125 where half the primitives fail the
+// dynamic limits.  Here a CTA runs phases A/B for `rounds` batches of 256 (node, control) items
+// first; every primitive that needs sampling leaves a 16-byte ticket {slot, node, action, n} in a
+// shared-memory queue.  Then all 256 lanes pull tickets: a lane rebuilds the primitive's quotients
+// from the node (L1/L2 hit) and U[action] — the same code path as phase A, so the same bits —
+// walks the reference's loop four samples at a time, writes the cost, and pulls the next ticket
+// while its neighbours are still busy.  Results are identical to the other kernels (the order in
+// which primitives are sampled does not enter any result).
+#include "mplx_expand.cuh"
+
+namespace mplx {
+
+struct Ticket {
+  unsigned slot;  // output slot of the successor: node * nU + rank  (< 2^31, mplx_check_ready)
+  int node;       // frontier index
+  int action;     // control index
+  int n;          // max(5, ceil(max_v*T/res)): env_map.h:95
+};
+
+// One group of UNR samples of the reference's loop `for (t = 0; t < T; t += dt)` (env_map.h:99),
+// the body of traverse_groups (mplx_kernels.cu) cut at the group boundary.
+// Returns 0 = continue with the next group, 1 = the loop ended (cost in c), 2 = blocked (inf).
+template <int DIM, int ORD, bool YAW, int UNR>
+__device__ __forceinline__ int sample_group(const EnvParams &P, const double (&cf)[CoefLayout<DIM, ORD, YAW>::NCMAX],
+                                            bool need_vel, double dt, double &t, double &c, unsigned &n_samples) {
+  using CL = CoefLayout<DIM, ORD, YAW>;
+  const double T = P.T;
+  const int NC = CL::ncoef(need_vel);
+  const bool plain = P.pot == nullptr && P.region_bits == nullptr && !YAW;
+  double ts[UNR];
+  int idx[UNR];
+  bool valid[UNR];
+#pragma unroll
+  for (int j = 0; j < UNR; j++) {
+    ts[j] = t;
+    valid[j] = t < T;
+    double pk[DIM];
+    eval_pos<DIM, ORD>(cf, t, pk);
+    idx[j] = sample_index<DIM>(P, pk);  // -1 when outside the map
+    t += dt;                            // the reference's running sum
+  }
+  bool blocked[UNR];
+  double term[UNR];
+  if (plain) {
+    unsigned word[UNR];
+#pragma unroll
+    for (int j = 0; j < UNR; j++) {
+      word[j] = 0;
+      if (valid[j] && idx[j] >= 0) word[j] = __ldg(P.occ_bits + (idx[j] >> 5));
+    }
+#pragma unroll
+    for (int j = 0; j < UNR; j++) {
+      blocked[j] = idx[j] < 0 || ((word[j] >> (idx[j] & 31)) & 1u);
+      term[j] = 0.0;
+    }
+  } else {
+    VoxelRaw raw[UNR];
+#pragma unroll
+    for (int j = 0; j < UNR; j++) {
+      raw[j] = kVoxelNone;
+      if (valid[j] && idx[j] >= 0) raw[j] = voxel_fetch(P, idx[j]);
+    }
+#pragma unroll
+    for (int j = 0; j < UNR; j++) {
+      term[j] = 0.0;
+      blocked[j] = idx[j] < 0;
+      if (valid[j] && !blocked[j]) {
+        double vel[DIM];
+        double gterm = 0.0;
+        if (need_vel) {
+          eval_vel<DIM, ORD>(cf + CL::NCP, ts[j], vel);
+          gterm = grad_term<DIM>(P, vel);
+        }
+        blocked[j] = voxel_classify(P, raw[j], dt, gterm, term[j]);
+        if (YAW) {
+          if (!blocked[j] && P.wyaw > 0)
+            term[j] += yaw_term(P, vel[0], vel[1], normalize_angle(cf[NC - 2] * ts[j] + cf[NC - 1]), dt);
+        }
+      }
+    }
+  }
+  bool any_blocked = false;
+#pragma unroll
+  for (int j = 0; j < UNR; j++) any_blocked = any_blocked || (valid[j] && blocked[j]);
+  if (P.stats) {
+    bool open = true;  // still before the first blocking sample
+#pragma unroll
+    for (int j = 0; j < UNR; j++) {
+      if (open && valid[j]) n_samples++;
+      open = open && !(valid[j] && blocked[j]);
+    }
+  }
+  if (any_blocked) return 2;
+  if (!plain) {
+#pragma unroll
+    for (int j = 0; j < UNR; j++)
+      if (valid[j]) c += term[j];
+  }
+  return valid[UNR - 1] ? 0 : 1;
+}
+
+template <int DIM, int ORD, bool YAW, bool VEL, int UNR, int MINB, bool LAT>
+__global__ void __launch_bounds__(kThreads, MINB)
+expand_deal_kernel(const __grid_constant__ EnvParams P, const mplx_waypoint *__restrict__ nodes, int n_nodes,
+                   int npb, const __grid_constant__ OutPtrs o, int rounds) {
+  extern __shared__ __align__(16) unsigned char dsm[];
+  Ticket *queue = reinterpret_cast<Ticket *>(dsm);  // rounds * kThreads tickets
+  __shared__ uint32_t vbits[9];
+  __shared__ unsigned long long s_stats[2];
+  __shared__ int q_count, q_head;
+  const int nU = P.nU;
+  const int items = npb * nU;  // <= 256
+  const int words = (items + 31) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (threadIdx.x < 2) s_stats[threadIdx.x] = 0;
+  if (threadIdx.x == 0) q_count = q_head = 0;
+  __syncthreads();
+  unsigned n_emitted = 0;
+
+  // ---- phases A/B for `rounds` batches of npb nodes; tickets for what needs sampling ----
+  for (int r = 0; r < rounds; r++) {
+    const int node0 = (blockIdx.x * rounds + r) * npb;
+    PrimState<DIM, ORD, YAW> pr;
+    bool emit, same;
+    double max_v;
+    size_t slot;
+    phase_ab<DIM, ORD, YAW, LAT>(P, nodes, n_nodes, threadIdx.x, items, nU, node0, vbits, words, o, pr, emit, same,
+                                 max_v, slot);
+    const bool push = emit && !same;
+    if (emit) {
+      n_emitted++;
+      // curr.pos == tn.pos: no collision check, cost 0 + intrinsic (env_map.h:163-165)
+      if (same && o.cost) o.cost[slot] = 0.0 + intrinsic_cost<DIM, ORD, YAW>(P, pr);
+    }
+    const unsigned m = __ballot_sync(0xffffffffu, push);
+    if (m) {
+      int base = 0;
+      const int leader = __ffs(m) - 1;
+      if (lane == leader) base = atomicAdd(&q_count, __popc(m));
+      base = __shfl_sync(0xffffffffu, base, leader);
+      if (push) {
+        double dt;
+        Ticket tk;
+        tk.slot = (unsigned)slot;
+        const int nl = threadIdx.x / nU;
+        tk.node = node0 + nl;
+        tk.action = threadIdx.x - nl * nU;
+        tk.n = sample_count_n(P, max_v, dt);
+        queue[base + __popc(m & ((1u << lane) - 1u))] = tk;
+      }
+    }
+    __syncthreads();  // vbits is reused by the next round; the queue is read after the last one
+  }
+
+  // ---- phase C: every lane pulls tickets until the queue is dry ----
+  const int total = q_count;
+  double cf[CoefLayout<DIM, ORD, YAW>::NCMAX];
+  double dt = 0.0, t = 0.0, c = 0.0, intrinsic = 0.0;
+  unsigned slot = 0, n_samples = 0;
+  bool have = false, dry = false;
+  for (;;) {
+    const unsigned need = dry ? 0u : __ballot_sync(0xffffffffu, !have);
+    if (need) {
+      int base = 0;
+      const int leader = __ffs(need) - 1;
+      if (lane == leader) base = atomicAdd(&q_head, __popc(need));
+      base = __shfl_sync(0xffffffffu, base, leader);
+      dry = base + __popc(need) > total;  // warp-uniform: this pull reached the end of the queue
+      if (!have) {
+        const int qi = base + __popc(need & ((1u << lane) - 1u));
+        if (qi < total) {
+          const Ticket tk = queue[qi];
+          // Primitive(curr, U[action], dt): primitive.h:220-256, as phase A builds it
+          PrimState<DIM, ORD, YAW> pr;
+          const mplx_waypoint *cp = nodes + tk.node;
+          const double *u = P.U + (size_t)tk.action * P.udim;
+#pragma unroll
+          for (int k = 0; k < DIM; k++) pr.ax[k].build(__ldg(u + k), cp->pos[k], cp->vel[k], cp->acc[k], cp->jrk[k]);
+          if (YAW) {
+            pr.yaw_u = __ldg(u + DIM);
+            pr.yaw0 = cp->yaw;
+          }
+          fill_coef<DIM, ORD, YAW>(pr, VEL, cf);
+          intrinsic = intrinsic_cost<DIM, ORD, YAW>(P, pr);
+          dt = tk.n <= kNMax ? __ldg(P.tdt + tk.n) : P.T / tk.n;  // T/n (env_map.h:98)
+          slot = tk.slot;
+          t = 0.0;
+          c = 0.0;
+          have = true;
+        }
+      }
+    }
+    if (!__any_sync(0xffffffffu, have)) break;
+    if (have) {
+      const int st = sample_group<DIM, ORD, YAW, UNR>(P, cf, VEL, dt, t, c, n_samples);
+      if (st != 0) {
+        if (o.cost) o.cost[slot] = st == 2 ? (double)INFINITY : c + intrinsic;
+        have = false;
+      }
+    }
+  }
+  if (P.stats) {
+    atomicAdd(&s_stats[0], (unsigned long long)n_samples);
+    atomicAdd(&s_stats[1], (unsigned long long)n_emitted);
+    __syncthreads();
+    if (threadIdx.x < 2) atomicAdd(&P.stats[threadIdx.x], s_stats[threadIdx.x]);
+  }
+}
+
+template <int DIM, int ORD, bool YAW>
+static cudaError_t launch_deal_t(const EnvParams &P, const mplx_waypoint *d_nodes, int n_nodes, const mplx_succ_out &so,
+                                 cudaStream_t st, int rounds) {
+  const OutPtrs o{so.count, so.succ, so.cost, so.action, so.key, so.lattice};
+  const int npb = kThreads / P.nU;
+  const int per_cta = npb * rounds;
+  const int grid = (n_nodes + per_cta - 1) / per_cta;
+  const size_t smem = (size_t)rounds * kThreads * sizeof(Ticket);
+  const bool nv = YAW || (P.pot != nullptr && P.grad_w != 0.0);
+  const bool short_loops = P.maxn <= 15;
+  const bool lat = o.lattice != nullptr;
+#define MPLX_LAUNCH_DEAL(VEL, UNR, LAT) \
+  expand_deal_kernel<DIM, ORD, YAW, VEL, UNR, 4, LAT><<<grid, kThreads, smem, st>>>(P, d_nodes, n_nodes, npb, o, rounds)
+  if (nv) {
+    if (short_loops) { if (lat) MPLX_LAUNCH_DEAL(true, 2, true); else MPLX_LAUNCH_DEAL(true, 2, false); }
+    else { if (lat) MPLX_LAUNCH_DEAL(true, 4, true); else MPLX_LAUNCH_DEAL(true, 4, false); }
+  } else {
+    if (short_loops) { if (lat) MPLX_LAUNCH_DEAL(YAW, 2, true); else MPLX_LAUNCH_DEAL(YAW, 2, false); }
+    else { if (lat) MPLX_LAUNCH_DEAL(YAW, 4, true); else MPLX_LAUNCH_DEAL(YAW, 4, false); }
+  }
+#undef MPLX_LAUNCH_DEAL
+  return cudaGetLastError();
+}
+
+template <int DIM>
+static cudaError_t launch_deal_d(const EnvParams &P, const mplx_waypoint *d_nodes, int n_nodes, const mplx_succ_out &o,
+                                 cudaStream_t st, int rounds) {
+  const bool yaw = (P.control & 16) != 0;
+  switch (P.control & 15) {
+    case MPLX_VEL: return yaw ? launch_deal_t<DIM, 1, true>(P, d_nodes, n_nodes, o, st, rounds) : launch_deal_t<DIM, 1, false>(P, d_nodes, n_nodes, o, st, rounds);
+    case MPLX_ACC: return yaw ? launch_deal_t<DIM, 2, true>(P, d_nodes, n_nodes, o, st, rounds) : launch_deal_t<DIM, 2, false>(P, d_nodes, n_nodes, o, st, rounds);
+    case MPLX_JRK: return yaw ? launch_deal_t<DIM, 3, true>(P, d_nodes, n_nodes, o, st, rounds) : launch_deal_t<DIM, 3, false>(P, d_nodes, n_nodes, o, st, rounds);
+    case MPLX_SNP: return yaw ? launch_deal_t<DIM, 4, true>(P, d_nodes, n_nodes, o, st, rounds) : launch_deal_t<DIM, 4, false>(P, d_nodes, n_nodes, o, st, rounds);
+  }
+  return cudaErrorInvalidValue;
+}
+
+// rounds: batches of 256 items per CTA.  More rounds = better lane use in phase C but fewer,
+// longer CTAs; keep at least ~8 CTAs per resident slot (148 SMs x 4 CTAs) so the grid tail stays small.
+cudaError_t launch_expand_deal(const EnvParams &P, const mplx_waypoint *d_nodes, int n_nodes, const mplx_succ_out &o,
+                               cudaStream_t st, int rounds) {
+  if (n_nodes <= 0) return cudaSuccess;
+  const int npb = kThreads / P.nU;
+  if (rounds <= 0) {
+    const long ctas1 = ((long)n_nodes + npb - 1) / npb;  // CTAs at one round each
+    rounds = (int)(ctas1 / (148 * 4 * 8));
+    rounds = rounds < 1 ? 1 : (rounds > kDealMaxRounds ? kDealMaxRounds : rounds);
+  }
+  if (rounds > kDealMaxRounds) rounds = kDealMaxRounds;
+  return P.dim == 2 ? launch_deal_d<2>(P, d_nodes, n_nodes, o, st, rounds) : launch_deal_d<3>(P, d_nodes, n_nodes, o, st, rounds);
+}
+
+}  // namespace mplx

@@ -14,6 +14,11 @@ constexpr int kMaxU = 1024;  // |U| upper bound (125 is the largest set the refe
 // the flat kernel; results are identical.
 cudaError_t launch_expand(const EnvParams &P, const mplx_waypoint *d_nodes, int n_nodes,
                           const mplx_succ_out &o, cudaStream_t st, int force_seq);
+// The dealing kernel (mplx_deal.cu): phases A/B for `rounds` batches of 256 items per CTA, then
+// phase C pulled from a CTA-wide ticket queue.  rounds <= 0 picks it from the batch size.  |U| <= 256.
+constexpr int kDealMaxRounds = 8;
+cudaError_t launch_expand_deal(const EnvParams &P, const mplx_waypoint *d_nodes, int n_nodes,
+                               const mplx_succ_out &o, cudaStream_t st, int rounds);
 // bytes -> 1 bit/voxel: occ ? (byte == 100) : (byte != 0)
 cudaError_t launch_pack_bits(const int8_t *d_bytes, size_t nvox, uint32_t *d_bits, bool occ, cudaStream_t st);
 // sample-time table of `for (t = 0; t < T; t += T/n)` for n = 0..kNMax

@@ -330,7 +330,7 @@ class env_map:
         abi.check(rc)
 
     def set_kernel(self, which: int):
-        """0 = auto (register kernel), 1 = literal sequential loop, 2 = register kernel, 3 = flat kernel."""
+        """0 = auto, 1 = literal sequential loop, 2 = register kernel, 3 = flat kernel, 4 = dealing kernel."""
         abi.check(self._lib.mplx_set_kernel(self._h, int(which)))
 
     def enable_stats(self, on=True):

@@ -40,8 +40,8 @@ def gpu_env(sc, region=None):
     return e
 
 
-def run_parity(sc, n, region=None, exact_cost=False, seed=7, kernels=(1, 2, 3)):
-    """All kernels (1 = literal sequential loop, 2 = register kernel [default], 3 = flat sample-parallel) vs the oracle."""
+def run_parity(sc, n, region=None, exact_cost=False, seed=7, kernels=(1, 2, 3, 4)):
+    """All kernels (1 = literal sequential loop, 2 = register kernel, 3 = flat sample-parallel, 4 = dealing) vs the oracle."""
     nodes = sc.frontier(n, seed=seed)
     orc = ob.OracleEnv.from_scenario(sc, region=region).expand(nodes, nthreads=8)
     env = gpu_env(sc, region)
@@ -175,7 +175,7 @@ def test_2d_vel_and_3d_snp_and_jrkyaw():
         nodes["t"] = rng.integers(0, 5, n) * 1.0
         orc = ob.OracleEnv.from_scenario(sc).expand(nodes, nthreads=8)
         env = gpu_env(sc)
-        for which in (1, 2, 3):
+        for which in (1, 2, 3, 4):
             env.set_kernel(which)
             g = env.expand(nodes, want=WANT)
             st = assert_expansion_equal(g, orc, exact_cost=(control & 16) == 0)
@@ -209,10 +209,12 @@ def test_setter_invalidation_and_stats():
     e = gpu_env(sc)
     nodes = sc.frontier(500, seed=2)
     e.enable_stats(True)
-    g = e.expand(nodes, want=WANT)
-    samples, succ = e.last_stats()
     t = ob.OracleEnv.from_scenario(sc).timed(nodes)
-    assert samples == t["samples"] and succ == t["successors"] == int(g.count.sum())
+    for which in (2, 4, 0):
+        e.set_kernel(which)
+        g = e.expand(nodes, want=WANT)
+        samples, succ = e.last_stats()
+        assert samples == t["samples"] and succ == t["successors"] == int(g.count.sum())
     e.enable_stats(False)
     # change a limit: results must follow (params re-uploaded)
     e.set_v_max(1.0)
