@@ -202,7 +202,7 @@ int mplx_edges_cells(mplx_ctx *ctx, const mplx_waypoint *parents, const int32_t 
  * 1 = the sequential kernel that keeps traverse_primitive's literal per-primitive loop
  * (env_map.h:99-130), 2 = the register kernel, 3 = the flat (sample-parallel, shared-memory
  * staged) kernel, 4 = the dealing kernel (sampling pulled from a CTA-wide ticket queue).  All
- * produce identical results. */
+ * produce identical results.  The environment variable MPLX_KERNEL sets the initial value of a new ctx. */
 int mplx_set_kernel(mplx_ctx *ctx, int which);
 
 /* Synchronise the ctx stream. */

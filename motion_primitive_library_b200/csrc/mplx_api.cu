@@ -80,6 +80,10 @@ int mplx_create(int dim, int device, mplx_ctx **out) {
   if (!c) return fail(MPLX_ERR_ALLOC, "host allocation failed");
   c->dim = dim;
   c->device = device;
+  if (const char *k = getenv("MPLX_KERNEL")) {  // diagnostics: initial mplx_set_kernel value
+    const int w = atoi(k);
+    if (w >= 0 && w <= 4) c->force_seq = w;
+  }
   memset(&c->P, 0, sizeof c->P);
   c->P.dim = dim;
   e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);

@@ -425,10 +425,12 @@ cudaError_t launch_expand(const EnvParams &P, const mplx_waypoint *d_nodes, int 
   if (n_nodes <= 0) return cudaSuccess;
   // auto (0): the dealing kernel where lanes of the register kernel idle most — controls whose
   // dynamic limits reject many primitives (JRK/SNP) and sample loops with per-sample work beyond the
-  // voxel bit (potential field, yaw) — once the batch fills the GPU; the register kernel otherwise
+  // voxel bit (potential field, yaw) — once the batch is large enough for multi-round CTAs; the register kernel otherwise
   // (measured: 512^3 JRK-125 +21 %, ACCxYAW-81 with potential +35 %, plain ACC-27 -3 %).
   const bool heavy = (P.control & 15) >= MPLX_JRK || (P.control & 16) != 0 || P.pot != nullptr;
-  const bool deal = force_seq == 4 || (force_seq == 0 && heavy && (long)n_nodes * P.nU >= 256L * 148 * 4);
+  // (at one round per CTA the dealing kernel only adds overhead: 4096-node JRK launches of the lock-step
+  // multi-query driver run 0.37 ms faster on the register kernel, so auto needs >= 2 rounds' worth of CTAs)
+  const bool deal = force_seq == 4 || (force_seq == 0 && heavy && (long)n_nodes * P.nU >= 2L * 256 * 148 * 4 * 8);
   if (deal && P.nU <= kThreads) {
     static const int rounds_env = [] {
       const char *e = getenv("MPLX_DEAL_ROUNDS");  // tuning override

@@ -404,7 +404,7 @@ class env_map_gpu : public env_map_host<Dim> {
     const int n = (int)nodes.size(), nU = (int)this->U_.size();
     const std::size_t cap = (std::size_t)n * nU;
     const int nstate = Dim * __builtin_popcount(control_ & 15) + ((control_ & 16) ? 1 : 0);
-    p_count.resize(n); p_offset.resize(n); p_state.resize(cap * nstate); p_cost.resize(cap); p_action.resize(cap); p_key.resize(cap);
+    p_count.reserve(n); p_offset.reserve(n); p_state.reserve(cap * nstate); p_cost.reserve(cap); p_action.reserve(cap); p_key.reserve(cap);
     mplx_packed_out out{p_count.data(), (int64_t *)p_offset.data(), p_state.data(), p_cost.data(), p_action.data(),
                         p_key.data(), (int64_t)cap, 0, 0};
     check(mplx_expand_packed(ctx_, nodes.data(), n, MPLX_PACK_DROP_INF, &out));
@@ -431,11 +431,30 @@ class env_map_gpu : public env_map_host<Dim> {
     w.t = curr.t + this->dt_;
     return w;
   }
-  mutable std::vector<int32_t> p_count;
-  mutable std::vector<long long> p_offset;
-  mutable std::vector<double> p_state, p_cost;
-  mutable std::vector<uint16_t> p_action;
-  mutable std::vector<uint64_t> p_key;
+  /// page-locked host array (mplx_host_alloc): the packed records cross PCIe by DMA straight into
+  /// it; grows, never shrinks
+  template <typename T>
+  struct Pinned {
+    T *p = nullptr;
+    std::size_t cap = 0;
+    Pinned() {}
+    Pinned(const Pinned &) = delete;
+    ~Pinned() { if (p) mplx_host_free(p); }
+    void reserve(std::size_t n) {
+      if (n <= cap) return;
+      if (p) mplx_host_free(p);
+      cap = n + n / 4;
+      p = (T *)mplx_host_alloc(cap * sizeof(T));
+      if (!p) { cap = 0; throw std::runtime_error(mplx_last_error()); }
+    }
+    T *data() const { return p; }
+    T &operator[](std::size_t i) const { return p[i]; }
+  };
+  mutable Pinned<int32_t> p_count;
+  mutable Pinned<long long> p_offset;
+  mutable Pinned<double> p_state, p_cost;
+  mutable Pinned<uint16_t> p_action;
+  mutable Pinned<uint64_t> p_key;
   mutable int p_nstate = 0;
   static mplx_waypoint pod(const Waypoint<Dim> &w) { return to_pod(w); }
   int control() const { return control_; }
