@@ -230,13 +230,14 @@ def run_reference(args, sc, rank, world):
     print(json.dumps(line), flush=True)
 
 
-def kernel_name(which, sc):
+def kernel_name(which, sc, n_nodes):
     """The kernel mplx_set_kernel(which) launches for this workload (auto rule: mplx_kernels.cu launch_expand)."""
     names = {1: "mplx::expand_seq_kernel", 2: "mplx::expand_reg_kernel", 3: "mplx::expand_flat_kernel", 4: "mplx::expand_deal_kernel"}
     if which in names:
         return names[which]
     heavy = (sc.control & 15) >= 7 or (sc.control & 16) != 0 or sc.potential() is not None
-    return "mplx::expand_deal_kernel" if heavy else "mplx::expand_reg_kernel"
+    big = n_nodes * sc.nU >= 2 * 256 * 148 * 4 * 8
+    return "mplx::expand_deal_kernel" if heavy and big else "mplx::expand_reg_kernel"
 
 
 def main():
@@ -409,7 +410,7 @@ def main():
     achieved = bytes_per_exp * n / (k_ms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s", "frac": achieved / peak_gbs,
                 "traffic": None, "peak_source": "measured" if pk.exists() else "fallback",
-                "kernel": kernel_name(args.kernel, sc), "kernel_ms": k_ms,
+                "kernel": kernel_name(args.kernel, sc, n), "kernel_ms": k_ms,
                 "algorithmic_bytes_per_expansion": bytes_per_exp,
                 "mean_samples_per_expansion": mean_samples, "mean_successors_per_expansion": mean_succ}
     prof = ROOT / "profiles" / "traffic.json"

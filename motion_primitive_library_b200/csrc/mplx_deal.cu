@@ -8,7 +8,7 @@
 // first; every primitive that needs sampling leaves a 16-byte ticket {slot, node, action, n} in a
 // shared-memory queue.  Then all 256 lanes pull tickets: a lane rebuilds the primitive's quotients
 // from the node (L1/L2 hit) and U[action] — the same code path as phase A, so the same bits —
-// walks the reference's loop four samples at a time, writes the cost, and pulls the next ticket
+// walks the reference's loop four samples at a time (sample_group), writes the cost, and pulls the next ticket
 // while its neighbours are still busy.  Results are identical to the other kernels (the order in
 // which primitives are sampled does not enter any result).
 #include "mplx_expand.cuh"
@@ -21,88 +21,6 @@ struct Ticket {
   int action;     // control index
   int n;          // max(5, ceil(max_v*T/res)): env_map.h:95
 };
-
-// One group of UNR samples of the reference's loop `for (t = 0; t < T; t += dt)` (env_map.h:99),
-// the body of traverse_groups (mplx_kernels.cu) cut at the group boundary.
-// Returns 0 = continue with the next group, 1 = the loop ended (cost in c), 2 = blocked (inf).
-template <int DIM, int ORD, bool YAW, int UNR>
-__device__ __forceinline__ int sample_group(const EnvParams &P, const double (&cf)[CoefLayout<DIM, ORD, YAW>::NCMAX],
-                                            bool need_vel, double dt, double &t, double &c, unsigned &n_samples) {
-  using CL = CoefLayout<DIM, ORD, YAW>;
-  const double T = P.T;
-  const int NC = CL::ncoef(need_vel);
-  const bool plain = P.pot == nullptr && P.region_bits == nullptr && !YAW;
-  double ts[UNR];
-  int idx[UNR];
-  bool valid[UNR];
-#pragma unroll
-  for (int j = 0; j < UNR; j++) {
-    ts[j] = t;
-    valid[j] = t < T;
-    double pk[DIM];
-    eval_pos<DIM, ORD>(cf, t, pk);
-    idx[j] = sample_index<DIM>(P, pk);  // -1 when outside the map
-    t += dt;                            // the reference's running sum
-  }
-  bool blocked[UNR];
-  double term[UNR];
-  if (plain) {
-    unsigned word[UNR];
-#pragma unroll
-    for (int j = 0; j < UNR; j++) {
-      word[j] = 0;
-      if (valid[j] && idx[j] >= 0) word[j] = __ldg(P.occ_bits + (idx[j] >> 5));
-    }
-#pragma unroll
-    for (int j = 0; j < UNR; j++) {
-      blocked[j] = idx[j] < 0 || ((word[j] >> (idx[j] & 31)) & 1u);
-      term[j] = 0.0;
-    }
-  } else {
-    VoxelRaw raw[UNR];
-#pragma unroll
-    for (int j = 0; j < UNR; j++) {
-      raw[j] = kVoxelNone;
-      if (valid[j] && idx[j] >= 0) raw[j] = voxel_fetch(P, idx[j]);
-    }
-#pragma unroll
-    for (int j = 0; j < UNR; j++) {
-      term[j] = 0.0;
-      blocked[j] = idx[j] < 0;
-      if (valid[j] && !blocked[j]) {
-        double vel[DIM];
-        double gterm = 0.0;
-        if (need_vel) {
-          eval_vel<DIM, ORD>(cf + CL::NCP, ts[j], vel);
-          gterm = grad_term<DIM>(P, vel);
-        }
-        blocked[j] = voxel_classify(P, raw[j], dt, gterm, term[j]);
-        if (YAW) {
-          if (!blocked[j] && P.wyaw > 0)
-            term[j] += yaw_term(P, vel[0], vel[1], normalize_angle(cf[NC - 2] * ts[j] + cf[NC - 1]), dt);
-        }
-      }
-    }
-  }
-  bool any_blocked = false;
-#pragma unroll
-  for (int j = 0; j < UNR; j++) any_blocked = any_blocked || (valid[j] && blocked[j]);
-  if (P.stats) {
-    bool open = true;  // still before the first blocking sample
-#pragma unroll
-    for (int j = 0; j < UNR; j++) {
-      if (open && valid[j]) n_samples++;
-      open = open && !(valid[j] && blocked[j]);
-    }
-  }
-  if (any_blocked) return 2;
-  if (!plain) {
-#pragma unroll
-    for (int j = 0; j < UNR; j++)
-      if (valid[j]) c += term[j];
-  }
-  return valid[UNR - 1] ? 0 : 1;
-}
 
 template <int DIM, int ORD, bool YAW, bool VEL, int UNR, int MINB, bool LAT>
 __global__ void __launch_bounds__(kThreads, MINB)
@@ -162,6 +80,7 @@ expand_deal_kernel(const __grid_constant__ EnvParams P, const mplx_waypoint *__r
   double cf[CoefLayout<DIM, ORD, YAW>::NCMAX];
   double dt = 0.0, t = 0.0, c = 0.0, intrinsic = 0.0;
   unsigned slot = 0, n_samples = 0;
+  int left = 0;  // iterations of the reference's sample loop still to visit
   bool have = false, dry = false;
   for (;;) {
     const unsigned need = dry ? 0u : __ballot_sync(0xffffffffu, !have);
@@ -188,6 +107,7 @@ expand_deal_kernel(const __grid_constant__ EnvParams P, const mplx_waypoint *__r
           fill_coef<DIM, ORD, YAW>(pr, VEL, cf);
           intrinsic = intrinsic_cost<DIM, ORD, YAW>(P, pr);
           dt = tk.n <= kNMax ? __ldg(P.tdt + tk.n) : P.T / tk.n;  // T/n (env_map.h:98)
+          left = sample_loop_count(P, tk.n, dt);
           slot = tk.slot;
           t = 0.0;
           c = 0.0;
@@ -197,7 +117,8 @@ expand_deal_kernel(const __grid_constant__ EnvParams P, const mplx_waypoint *__r
     }
     if (!__any_sync(0xffffffffu, have)) break;
     if (have) {
-      const int st = sample_group<DIM, ORD, YAW, UNR>(P, cf, VEL, dt, t, c, n_samples);
+      const int st = sample_group<DIM, ORD, YAW, UNR>(P, cf, VEL, dt, left, t, c, n_samples);
+      left -= UNR;
       if (st != 0) {
         if (o.cost) o.cost[slot] = st == 2 ? (double)INFINITY : c + intrinsic;
         have = false;

@@ -324,4 +324,127 @@ __device__ __forceinline__ int sample_count_n(const EnvParams &P, double max_v, 
   return n;
 }
 
+// The cell of one sample as (inside, index): the same rule as sample_index, with the verdict kept
+// as a predicate (the six comparisons chain into one predicate register; no index is forced to -1).
+template <int DIM>
+__device__ __forceinline__ bool sample_cell(const EnvParams &P, const double (&pk)[DIM], int &idx) {
+  int pn[DIM];
+  bool inside = true;
+#pragma unroll
+  for (int k = 0; k < DIM; k++) {
+    const double y = div_exact(pk[k] - P.origin[k], P.res, P.rinv);
+    pn[k] = __double2int_rd(y);  // floor; saturates for |y| >= 2^31, 0 for NaN: both fail a test below
+    inside = inside && (y > 0x1p-55) && ((unsigned)pn[k] < (unsigned)P.mdim[k]);
+  }
+  idx = pn[0] + P.mdim[0] * pn[1];
+  if (DIM == 3) idx += P.mdim[0] * P.mdim[1] * pn[DIM - 1];
+  return inside;
+}
+
+// Iterations of `for (t = 0; t < T; t += dt)` with dt = T/n (env_map.h:98-99): n or n+1 depending on
+// how the running sum rounds.  From the table (built by running that very loop, build_ttab_kernel)
+// for n <= kNMax, by running the loop beyond it.
+__device__ __forceinline__ int sample_loop_count(const EnvParams &P, int n, double dt) {
+  if (n <= kNMax) return __ldg(P.tcount + n);
+  int k = 0;
+  for (double t = 0; t < P.T; t += dt) k++;
+  return k;
+}
+
+// One group of UNR samples of the reference's loop `for (t = 0; t < T; t += dt)` (env_map.h:99).
+// `left` = iterations of that loop not yet visited (sample j of the group exists iff j < left: the
+// loop's own `t < T` test, counted instead of re-compared in FP64).  All UNR samples are evaluated
+// unconditionally (one past the end or outside the map just gets no load), their voxel loads are
+// issued back to back, and two decisions close the group:
+//   some existing sample blocks -> 2: the primitive's cost is inf (the reference returns at the
+//                                   first such sample; later ones cannot change an inf);
+//   the group held the loop's end -> 1: the accumulated cost is in c;
+// otherwise the terms of the group were added to c in sample order -> 0, call again with left - UNR.
+// n_samples counts what the reference's loop visits (up to and including the first blocking
+// sample) and is only maintained when the stats counters are on.
+template <int DIM, int ORD, bool YAW, int UNR>
+__device__ __forceinline__ int sample_group(const EnvParams &P, const double (&cf)[CoefLayout<DIM, ORD, YAW>::NCMAX],
+                                            bool need_vel, double dt, int left, double &t, double &c,
+                                            unsigned &n_samples) {
+  using CL = CoefLayout<DIM, ORD, YAW>;
+  const int NC = CL::ncoef(need_vel);
+  const bool plain = P.pot == nullptr && P.region_bits == nullptr && !YAW;
+  double ts[UNR];
+  int idx[UNR];
+  bool in[UNR];
+#pragma unroll
+  for (int j = 0; j < UNR; j++) {
+    ts[j] = t;
+    double pk[DIM];
+    eval_pos<DIM, ORD>(cf, t, pk);
+    in[j] = sample_cell<DIM>(P, pk, idx[j]);
+    t += dt;  // the reference's running sum
+  }
+  if (plain) {
+    // occupancy planning: the only question per sample is the voxel bit
+    unsigned word[UNR];
+#pragma unroll
+    for (int j = 0; j < UNR; j++) {
+      word[j] = 0;
+      if (j < left && in[j]) word[j] = __ldg(P.occ_bits + (idx[j] >> 5));
+    }
+    bool any_blocked = false;
+#pragma unroll
+    for (int j = 0; j < UNR; j++)
+      any_blocked = any_blocked || (j < left && (!in[j] || ((word[j] >> (idx[j] & 31)) & 1u)));
+    if (P.stats) {
+      bool open = true;  // still before the first blocking sample
+#pragma unroll
+      for (int j = 0; j < UNR; j++) {
+        if (open && j < left) n_samples++;
+        open = open && !(j < left && (!in[j] || ((word[j] >> (idx[j] & 31)) & 1u)));
+      }
+    }
+    if (any_blocked) return 2;
+    return left <= UNR ? 1 : 0;
+  }
+  VoxelRaw raw[UNR];
+#pragma unroll
+  for (int j = 0; j < UNR; j++) {
+    raw[j] = kVoxelNone;
+    if (j < left && in[j]) raw[j] = voxel_fetch(P, idx[j]);
+  }
+  bool blocked[UNR];
+  double term[UNR];
+#pragma unroll
+  for (int j = 0; j < UNR; j++) {
+    term[j] = 0.0;
+    blocked[j] = !in[j];
+    if (j < left && in[j]) {
+      double vel[DIM];
+      double gterm = 0.0;
+      if (need_vel) {
+        eval_vel<DIM, ORD>(cf + CL::NCP, ts[j], vel);
+        gterm = grad_term<DIM>(P, vel);
+      }
+      blocked[j] = voxel_classify(P, raw[j], dt, gterm, term[j]);
+      if (YAW) {
+        if (!blocked[j] && P.wyaw > 0)
+          term[j] += yaw_term(P, vel[0], vel[1], normalize_angle(cf[NC - 2] * ts[j] + cf[NC - 1]), dt);
+      }
+    }
+  }
+  bool any_blocked = false;
+#pragma unroll
+  for (int j = 0; j < UNR; j++) any_blocked = any_blocked || (j < left && blocked[j]);
+  if (P.stats) {
+    bool open = true;
+#pragma unroll
+    for (int j = 0; j < UNR; j++) {
+      if (open && j < left) n_samples++;
+      open = open && !(j < left && blocked[j]);
+    }
+  }
+  if (any_blocked) return 2;
+#pragma unroll
+  for (int j = 0; j < UNR; j++)
+    if (j < left) c += term[j];
+  return left <= UNR ? 1 : 0;
+}
+
 }  // namespace mplx

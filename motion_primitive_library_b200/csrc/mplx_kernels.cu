@@ -76,99 +76,19 @@ expand_seq_kernel(const __grid_constant__ EnvParams P, const mplx_waypoint *__re
 // are computed for nothing (they are bounds-checked like any other).  No shared-memory staging,
 // no atomics; lanes whose primitive is invalid or short idle while the longest one finishes.
 // Phase C of the register kernel: the reference's loop `for (t = 0; t < T; t += dt)`
-// (env_map.h:99) in groups of UNR samples with group-level control flow only.  All UNR samples of
-// a group are evaluated unconditionally (a sample past T or outside the map just gets no load),
-// their voxel loads are issued back to back, and two decisions close the group:
-//   some valid sample blocks  -> the primitive's cost is inf (the reference returns at the first
-//                                such sample; later ones cannot change an inf);
-//   the group reached t >= T  -> the loop has ended, return the accumulated cost;
-// otherwise the terms of the group are added in sample order and the next group starts.
-// n_samples counts what the reference's loop visits (up to and including the first blocking
-// sample) and is only maintained when the stats counters are on.
+// (env_map.h:99) in groups of UNR samples with group-level control flow only (sample_group,
+// mplx_expand.cuh).  count = iterations of that loop (sample_loop_count).
 template <int DIM, int ORD, bool YAW, int UNR>
 __device__ __forceinline__ double traverse_groups(const EnvParams &P, const double (&cf)[CoefLayout<DIM, ORD, YAW>::NCMAX],
-                                                 bool need_vel, double dt, unsigned &n_samples) {
-  using CL = CoefLayout<DIM, ORD, YAW>;
-  const double T = P.T;
-  const int NC = CL::ncoef(need_vel);
-  const bool plain = P.pot == nullptr && P.region_bits == nullptr && !YAW;
+                                                 bool need_vel, double dt, int count, unsigned &n_samples) {
   double c = 0;
   double t = 0;
-  for (;;) {
-    double ts[UNR];
-    int idx[UNR];
-    bool valid[UNR];
-#pragma unroll
-    for (int j = 0; j < UNR; j++) {
-      ts[j] = t;
-      valid[j] = t < T;
-      double pk[DIM];
-      eval_pos<DIM, ORD>(cf, t, pk);
-      idx[j] = sample_index<DIM>(P, pk);  // -1 when outside the map
-      t += dt;                            // the reference's running sum
-    }
-    bool blocked[UNR];
-    double term[UNR];
-    if (plain) {
-      // occupancy planning: the only question per sample is the voxel bit
-      unsigned word[UNR];
-#pragma unroll
-      for (int j = 0; j < UNR; j++) {
-        word[j] = 0;
-        if (valid[j] && idx[j] >= 0) word[j] = __ldg(P.occ_bits + (idx[j] >> 5));
-      }
-#pragma unroll
-      for (int j = 0; j < UNR; j++) {
-        blocked[j] = idx[j] < 0 || ((word[j] >> (idx[j] & 31)) & 1u);
-        term[j] = 0.0;
-      }
-    } else {
-      VoxelRaw raw[UNR];
-#pragma unroll
-      for (int j = 0; j < UNR; j++) {
-        raw[j] = kVoxelNone;
-        if (valid[j] && idx[j] >= 0) raw[j] = voxel_fetch(P, idx[j]);
-      }
-#pragma unroll
-      for (int j = 0; j < UNR; j++) {
-        term[j] = 0.0;
-        blocked[j] = idx[j] < 0;
-        if (valid[j] && !blocked[j]) {
-          double vel[DIM];
-          double gterm = 0.0;
-          if (need_vel) {
-            eval_vel<DIM, ORD>(cf + CL::NCP, ts[j], vel);
-            gterm = grad_term<DIM>(P, vel);
-          }
-          blocked[j] = voxel_classify(P, raw[j], dt, gterm, term[j]);
-          if (YAW) {
-            if (!blocked[j] && P.wyaw > 0)
-              term[j] += yaw_term(P, vel[0], vel[1], normalize_angle(cf[NC - 2] * ts[j] + cf[NC - 1]), dt);
-          }
-        }
-      }
-    }
-    bool any_blocked = false;
-#pragma unroll
-    for (int j = 0; j < UNR; j++) any_blocked = any_blocked || (valid[j] && blocked[j]);
-    if (P.stats) {
-      bool open = true;  // still before the first blocking sample
-#pragma unroll
-      for (int j = 0; j < UNR; j++) {
-        if (open && valid[j]) n_samples++;
-        open = open && !(valid[j] && blocked[j]);
-      }
-    }
-    if (any_blocked) return INFINITY;
-    if (!plain) {
-#pragma unroll
-      for (int j = 0; j < UNR; j++)
-        if (valid[j]) c += term[j];
-    }
-    if (!valid[UNR - 1]) return c;  // this group contained the end of the loop
+  for (int left = count;; left -= UNR) {
+    const int st = sample_group<DIM, ORD, YAW, UNR>(P, cf, need_vel, dt, left, t, c, n_samples);
+    if (st == 2) return INFINITY;
+    if (st == 1) return c;
   }
 }
-
 
 template <int DIM, int ORD, bool YAW, bool VEL, int UNR, int MINB, bool LAT>
 __global__ void __launch_bounds__(kThreads, MINB)
@@ -195,8 +115,8 @@ expand_reg_kernel(const __grid_constant__ EnvParams P, const mplx_waypoint *__re
       double cf[CoefLayout<DIM, ORD, YAW>::NCMAX];
       fill_coef<DIM, ORD, YAW>(pr, VEL, cf);
       double dt;
-      sample_count_n(P, max_v, dt);
-      cost = traverse_groups<DIM, ORD, YAW, UNR>(P, cf, VEL, dt, n_samples);
+      const int n = sample_count_n(P, max_v, dt);
+      cost = traverse_groups<DIM, ORD, YAW, UNR>(P, cf, VEL, dt, sample_loop_count(P, n, dt), n_samples);
     }
     if (!isinf(cost)) cost += intrinsic;
     if (o.cost) o.cost[slot] = cost;

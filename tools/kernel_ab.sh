@@ -1,8 +1,9 @@
-set -x
-timeout 900 python -m pytest tests/test_expand_parity_gpu.py -m gpu -x -q 2>&1 | tail -3
-for k in 0 4; do for r in 0; do echo "kernel $k"; MPLX_DEAL_ROUNDS=$r timeout 300 python bench.py --kernel $k --steps 20 --warmup 3 --no-cpu-baseline 2>/dev/null | python -c "
-import json,sys; d=json.loads(sys.stdin.readlines()[-1]); print(d['ms_per_step'], d['value'])"; done; done
-for r in 1 2 4 8; do echo "deal rounds $r"; MPLX_DEAL_ROUNDS=$r timeout 300 python bench.py --kernel 4 --steps 20 --warmup 3 --no-cpu-baseline 2>/dev/null | python -c "
-import json,sys; d=json.loads(sys.stdin.readlines()[-1]); print(d['ms_per_step'], d['value'])"; done
-for w in cfg3 cfg4; do for k in 0 4; do echo "$w kernel $k"; timeout 300 python bench.py --workload $w --kernel $k --steps 10 --warmup 3 --no-cpu-baseline 2>/dev/null | python -c "
-import json,sys; d=json.loads(sys.stdin.readlines()[-1]); print(d['ms_per_step'], d['value'])"; done; done
+#!/bin/bash
+# quick kernel check on the GPU box: parity of all kernels, then ms/step of the default and selected kernels
+timeout 900 python -m pytest tests/test_expand_parity_gpu.py -m gpu -x -q 2>&1 | tail -2
+run() { python bench.py "$@" --no-cpu-baseline 2>/dev/null | tail -1 | python -c "
+import json,sys; d=json.loads(sys.stdin.readline()); print(' ', d['roofline']['kernel'], d['ms_per_step'], round(d['value']/1e6,1), 'M/s')"; }
+echo "512c_acc27 auto"; run --steps 20 --warmup 3
+echo "512c_acc27 kernel 4"; run --steps 20 --warmup 3 --kernel 4
+for w in cfg2 cfg3 cfg4; do echo "$w auto"; run --workload $w --steps 10 --warmup 3; done
+echo "cfg3 kernel 2"; run --workload cfg3 --steps 10 --warmup 3 --kernel 2
