@@ -11,10 +11,6 @@ for w in cfg2 cfg3 cfg4; do
 done
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/${R}_launches_bench.csv \
   python bench.py --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/${R}_ncu_list.log 2>&1
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:expand_reg_kernel -c 1 -f -o gpurun_out/prof_${R}_reg \
-  python bench.py --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/${R}_ncu_reg.log 2>&1
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:expand_deal_kernel -c 1 -f -o gpurun_out/prof_${R}_deal_cfg3 \
-  python bench.py --workload cfg3 --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/${R}_ncu_deal.log 2>&1
 timeout 900 python tools/batch_queries.py --queries 4096 --max-expand 300 --ref-queries 128 2>/dev/null | tail -1 > gpurun_out/${R}_cfg5.json
 for f in gpurun_out/${R}_bench_line.json gpurun_out/${R}_bench_reference_line.json gpurun_out/${R}_bench_cfg*.json gpurun_out/${R}_cfg5.json; do
   python - "$f" <<'P'
