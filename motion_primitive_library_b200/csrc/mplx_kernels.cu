@@ -299,6 +299,9 @@ static cudaError_t launch_t(const EnvParams &P, const mplx_waypoint *d_nodes, in
     // (n <= 15: a group of 4 would mostly run past the end of the loop)
     const bool short_loops = P.maxn <= 15;
     const bool lat = o.lattice != nullptr;
+    // MPLX_UNR8=1: groups of 8 samples for plain long-loop planning (measured 0.810 vs 0.828 ms on
+    // 512^3 ACC-27, no change on 256^3; opt-in until the round's artefacts are re-taken with it)
+    static const bool unr8 = getenv("MPLX_UNR8") != nullptr;
 #define MPLX_LAUNCH_REG(VEL, UNR, LAT) \
   expand_reg_kernel<DIM, ORD, YAW, VEL, UNR, 4, LAT><<<grid, kThreads, 0, st>>>(P, d_nodes, n_nodes, npb, o)
     if (nv) {
@@ -306,7 +309,7 @@ static cudaError_t launch_t(const EnvParams &P, const mplx_waypoint *d_nodes, in
       else { if (lat) MPLX_LAUNCH_REG(true, 4, true); else MPLX_LAUNCH_REG(true, 4, false); }
     } else {
       if (short_loops) { if (lat) MPLX_LAUNCH_REG(YAW, 2, true); else MPLX_LAUNCH_REG(YAW, 2, false); }
-      else { if (lat) MPLX_LAUNCH_REG(YAW, 4, true); else MPLX_LAUNCH_REG(YAW, 4, false); }
+      else { if (lat) MPLX_LAUNCH_REG(YAW, 4, true); else if (unr8) MPLX_LAUNCH_REG(YAW, 8, false); else MPLX_LAUNCH_REG(YAW, 4, false); }
     }
 #undef MPLX_LAUNCH_REG
     return cudaGetLastError();
