@@ -133,3 +133,18 @@ def test_voxel_map_sessions(which, q):
     ref = pb.lpa_reference(a, script)
     assert ref[1]["n_linked"] > 100
     same_session(pb.lpa_oracle(a, script), ref)
+
+
+def test_degenerate_updates_match_reference():
+    """Cells outside the map (getIndex aliases them onto other voxels, as in the reference), repeated
+    cells, an empty list, LINK before any plan-changing step, and clearing cells that were never blocked."""
+    a, c = corridor_args()
+    first = pb.lpa_reference(a, [("plan",)])[0]
+    cells = trajectory_cells(c, first, every=1)
+    outside = np.array([[-3, 5], [int(c["dim"][0]) + 2, 7], [4, -1]], dtype=np.int32)
+    twice = np.concatenate([cells[8:10], cells[8:10]])
+    script = [("plan",), ("link",), ("block", outside), ("plan",), ("block", twice), ("plan",), ("link",),
+              ("clear", np.zeros((0, 2), dtype=np.int32)), ("clear", cells[20:22]), ("clear", twice), ("plan",)]
+    ref = pb.lpa_reference(a, script)
+    assert ref[10]["valid"] == 1
+    same_session(pb.lpa_oracle(a, script), ref)
