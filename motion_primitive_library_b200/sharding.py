@@ -1,7 +1,8 @@
 """Multi-GPU: the path shards over independent units (frontier batches, or whole start/goal queries
 — BASELINE.json config 5), one process per GPU, every rank holding a replica of the map.  There is
-no data-path collective: ranks exchange only the per-query results and the counters at the end
-(torch.distributed: NCCL on GPUs, gloo in the CPU tests)."""
+no data-path collective: the map is broadcast once at set-up (broadcast_array) and ranks exchange
+only the per-query results and the counters at the end (torch.distributed: NCCL on GPUs, gloo in
+the CPU tests)."""
 from __future__ import annotations
 
 import numpy as np
@@ -12,6 +13,46 @@ def shard_slice(n_items: int, rank: int, world: int) -> slice:
     if not (0 <= rank < world):
         raise ValueError("rank out of range")
     return slice(n_items * rank // world, n_items * (rank + 1) // world)
+
+
+def broadcast_array(arr, src: int = 0, group=None, device=None) -> np.ndarray:
+    """Set-up collective of the replicated design: the map (and potential / search-region arrays) exist
+    on rank `src` and every rank needs a copy before it uploads its replica (one
+    broadcast per map, 128 MiB at 512^3; NCCL over NVLink on GPUs, gloo in the CPU tests).
+    `arr` is the numpy array on rank src and ignored (may be None) elsewhere; returns the array on
+    every rank.  Without torch.distributed (world 1) it returns `arr` unchanged."""
+    import torch
+    import torch.distributed as dist
+
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return np.ascontiguousarray(arr)
+    rank = dist.get_rank(group)
+    dev = device if device is not None else (torch.device("cuda", torch.cuda.current_device())
+                                             if dist.get_backend(group) == "nccl" else torch.device("cpu"))
+    # header: dtype string (<= 16 bytes), ndim, shape (<= 8 dims)
+    hdr = torch.zeros(16 + 9, dtype=torch.int64, device=dev)
+    if rank == src:
+        a = np.ascontiguousarray(arr)
+        name = a.dtype.str.encode()
+        if len(name) > 16 or a.ndim > 8:
+            raise ValueError("unsupported array")
+        h = np.zeros(25, dtype=np.int64)
+        h[: len(name)] = np.frombuffer(name, dtype=np.uint8)
+        h[16] = a.ndim
+        h[17 : 17 + a.ndim] = a.shape
+        hdr.copy_(torch.from_numpy(h))
+    dist.broadcast(hdr, src=src, group=group)
+    h = hdr.cpu().numpy()
+    dtype = np.dtype(bytes(h[:16][h[:16] > 0].astype(np.uint8)).decode())
+    shape = tuple(int(x) for x in h[17 : 17 + int(h[16])])
+    nbytes = int(np.prod(shape, dtype=np.int64)) * dtype.itemsize
+    if rank == src:
+        payload = torch.from_numpy(a.view(np.uint8).reshape(-1)).to(dev)
+    else:
+        payload = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    if nbytes:
+        dist.broadcast(payload, src=src, group=group)
+    return payload.cpu().numpy().view(dtype).reshape(shape)
 
 
 def run_sharded(items: np.ndarray, fn, group=None, device=None):

@@ -63,6 +63,32 @@ def _worker(rank, world, port, n, outdir):
     dist.destroy_process_group()
 
 
+def _bcast_worker(rank, world, port, outdir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from motion_primitive_library_b200.sharding import broadcast_array
+
+    rng = np.random.default_rng(5)
+    grid = (rng.random((7, 9, 11)) < 0.1).astype(np.int8) * 100          # only rank 0's copy matters
+    pot = rng.integers(-1, 101, 50, dtype=np.int64).astype(np.float64)
+    got = broadcast_array(grid if rank == 0 else None, src=0)
+    got2 = broadcast_array(pot if rank == 0 else None, src=0)
+    empty = broadcast_array(np.zeros((0, 3), dtype=np.int32) if rank == 0 else None, src=0)
+    np.save(Path(outdir) / f"grid{rank}.npy", got)
+    np.save(Path(outdir) / f"pot{rank}.npy", got2)
+    assert empty.shape == (0, 3) and empty.dtype == np.int32
+    dist.destroy_process_group()
+
+
+def test_map_broadcast_two_ranks(tmp_path):
+    """The set-up collective: rank 0's map reaches every rank bit for bit (dtype and shape included)."""
+    mp.spawn(_bcast_worker, args=(2, _free_port(), str(tmp_path)), nprocs=2, join=True)
+    g0, g1 = np.load(tmp_path / "grid0.npy"), np.load(tmp_path / "grid1.npy")
+    assert g0.dtype == np.int8 and g0.shape == (7, 9, 11) and g0.sum() > 0
+    np.testing.assert_array_equal(g0, g1)
+    np.testing.assert_array_equal(np.load(tmp_path / "pot0.npy"), np.load(tmp_path / "pot1.npy"))
+
+
 def test_shard_slice_partitions():
     from motion_primitive_library_b200.sharding import shard_slice
 

@@ -43,7 +43,8 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     sc = S.cfg3() if args.cells == 512 else S.scaled(S.cfg3(), args.cells)
-    grid = sc.grid()
+    # rank 0 builds the map, every rank receives its replica (the only set-up collective: SURVEY.md §8e)
+    grid = sharding.broadcast_array(sc.grid() if rank == 0 else None, src=0)
     # start/goal pairs: free cell centres at rest, at least min_dist apart
     pts = sc.frontier(4 * args.queries, seed=11, max_steps=0)["pos"]
     rng = np.random.default_rng(5)
