@@ -6,7 +6,7 @@
 // lane-steps of the sample loop do work, ~37 % with JRK-125 where half the primitives fail the
 // dynamic limits.  Here a CTA runs phases A/B for `rounds` batches of 256 (node, control) items
 // first; every primitive that needs sampling leaves a 16-byte ticket {slot, node, action, n} in a
-// shared-memory queue.  Then all 256 lanes pull tickets: a lane rebuilds the primitive's quotients
+// shared-memory queue (long loops at the front, short ones at the back).  Then all 256 lanes pull tickets: a lane rebuilds the primitive's quotients
 // from the node (L1/L2 hit) and U[action] — the same code path as phase A, so the same bits —
 // walks the reference's loop four samples at a time (sample_group), writes the cost, and pulls the next ticket
 // while its neighbours are still busy.  Results are identical to the other kernels (the order in
@@ -30,13 +30,18 @@ expand_deal_kernel(const __grid_constant__ EnvParams P, const mplx_waypoint *__r
   Ticket *queue = reinterpret_cast<Ticket *>(dsm);  // rounds * kThreads tickets
   __shared__ uint32_t vbits[9];
   __shared__ unsigned long long s_stats[2];
-  __shared__ int q_count, q_head;
+  __shared__ int q_long, q_short, q_head;
   const int nU = P.nU;
   const int items = npb * nU;  // <= 256
   const int words = (items + 31) >> 5;
   const int lane = threadIdx.x & 31;
   if (threadIdx.x < 2) s_stats[threadIdx.x] = 0;
-  if (threadIdx.x == 0) q_count = q_head = 0;
+  if (threadIdx.x == 0) q_long = q_short = q_head = 0;
+  const int cap = rounds * kThreads;
+  // longest-first dealing in two classes: tickets of long loops fill the queue from the front,
+  // short ones from the back, and the queue is pulled front to back, so the primitives that are
+  // still running when the queue dries up are short ones
+  const int n_long = (5 + P.maxn) / 2;
   __syncthreads();
   unsigned n_emitted = 0;
 
@@ -55,28 +60,41 @@ expand_deal_kernel(const __grid_constant__ EnvParams P, const mplx_waypoint *__r
       // curr.pos == tn.pos: no collision check, cost 0 + intrinsic (env_map.h:163-165)
       if (same && o.cost) o.cost[slot] = 0.0 + intrinsic_cost<DIM, ORD, YAW>(P, pr);
     }
-    const unsigned m = __ballot_sync(0xffffffffu, push);
-    if (m) {
-      int base = 0;
-      const int leader = __ffs(m) - 1;
-      if (lane == leader) base = atomicAdd(&q_count, __popc(m));
-      base = __shfl_sync(0xffffffffu, base, leader);
+    double dt_unused;
+    const int n = push ? sample_count_n(P, max_v, dt_unused) : 0;
+    const bool is_long = push && n >= n_long;
+    const unsigned ml = __ballot_sync(0xffffffffu, is_long);
+    const unsigned ms = __ballot_sync(0xffffffffu, push && !is_long);
+    if (ml | ms) {
+      int base_l = 0, base_s = 0;
+      if (ml) {
+        const int leader = __ffs(ml) - 1;
+        if (lane == leader) base_l = atomicAdd(&q_long, __popc(ml));
+        base_l = __shfl_sync(0xffffffffu, base_l, leader);
+      }
+      if (ms) {
+        const int leader = __ffs(ms) - 1;
+        if (lane == leader) base_s = atomicAdd(&q_short, __popc(ms));
+        base_s = __shfl_sync(0xffffffffu, base_s, leader);
+      }
       if (push) {
-        double dt;
         Ticket tk;
         tk.slot = (unsigned)slot;
         const int nl = threadIdx.x / nU;
         tk.node = node0 + nl;
         tk.action = threadIdx.x - nl * nU;
-        tk.n = sample_count_n(P, max_v, dt);
-        queue[base + __popc(m & ((1u << lane) - 1u))] = tk;
+        tk.n = n;
+        const unsigned below = (1u << lane) - 1u;
+        const int qi = is_long ? base_l + __popc(ml & below) : cap - 1 - (base_s + __popc(ms & below));
+        queue[qi] = tk;
       }
     }
     __syncthreads();  // vbits is reused by the next round; the queue is read after the last one
   }
 
   // ---- phase C: every lane pulls tickets until the queue is dry ----
-  const int total = q_count;
+  const int n_front = q_long;
+  const int total = n_front + q_short;
   double cf[CoefLayout<DIM, ORD, YAW>::NCMAX];
   double dt = 0.0, t = 0.0, c = 0.0, intrinsic = 0.0;
   unsigned slot = 0, n_samples = 0;
@@ -93,7 +111,7 @@ expand_deal_kernel(const __grid_constant__ EnvParams P, const mplx_waypoint *__r
       if (!have) {
         const int qi = base + __popc(need & ((1u << lane) - 1u));
         if (qi < total) {
-          const Ticket tk = queue[qi];
+          const Ticket tk = queue[qi < n_front ? qi : cap - 1 - (qi - n_front)];
           // Primitive(curr, U[action], dt): primitive.h:220-256, as phase A builds it
           PrimState<DIM, ORD, YAW> pr;
           const mplx_waypoint *cp = nodes + tk.node;
