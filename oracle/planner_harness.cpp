@@ -14,10 +14,13 @@ class env_map_oracle : public MPL::env_map_host<Dim> {
                 std::vector<int> &action_idx) const override {
     succ.clear(); succ_cost.clear(); action_idx.clear();
     this->expanded_nodes_.push_back(curr.pos);
+    const auto t_in = std::chrono::steady_clock::now();
+    struct Acc { double &s; std::chrono::steady_clock::time_point t0; ~Acc() { s += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count(); } } acc{seconds_in_get_succ, t_in};
     const orc_env e = env();
     const orc_waypoint c = pod(curr);
     std::vector<orc_waypoint> s(e.nU); std::vector<double> cost(e.nU); std::vector<int32_t> act(e.nU);
-    const int n = orc_get_succ(&e, &c, s.data(), cost.data(), act.data(), nullptr, nullptr);
+    keys_.resize(e.nU);
+    const int n = orc_get_succ(&e, &c, s.data(), cost.data(), act.data(), (uint64_t *)keys_.data(), nullptr);
     for (int j = 0; j < n; j++) {
       Waypoint<Dim> w(curr.control);
       for (int d = 0; d < Dim; d++) { w.pos(d) = s[j].pos[d]; w.vel(d) = s[j].vel[d]; w.acc(d) = s[j].acc[d]; w.jrk(d) = s[j].jrk[d]; }
@@ -45,6 +48,12 @@ class env_map_oracle : public MPL::env_map_host<Dim> {
     cells.assign((std::size_t)total * Dim, 0);
     orc_edges_cells(&e, in.data(), actions.data(), (int)parents.size(), (int64_t *)offset.data(), cells.data(), total);
   }
+
+  /// like the GPU env, the oracle hands the successors' lattice keys back with them
+  const std::size_t *last_succ_keys() const override { return keys_.data(); }
+  mutable std::vector<std::size_t> keys_;
+  /// wall time spent inside get_succ (the oracle), so a caller can split plan() into env and bookkeeping
+  mutable double seconds_in_get_succ = 0;
 
  private:
   static orc_waypoint pod(const Waypoint<Dim> &w) {
@@ -88,8 +97,13 @@ extern "C" int orcp_plan(const mplh_plan_args *a, mplh_plan_result *r, uint64_t 
   auto go = [&](auto dimtag) {
     constexpr int Dim = decltype(dimtag)::value;
     MPL::MapPlanner<Dim> planner(false);
-    planner.setEnv(std::make_shared<env_map_oracle<Dim>>(mplh::make_map<Dim>(a), a));
+    auto env = std::make_shared<env_map_oracle<Dim>>(mplh::make_map<Dim>(a), a);
+    planner.setEnv(env);
     mplh::run<Dim>(planner, a, r, closed_keys, cap_closed, actions, cap_actions);
+    if (std::getenv("ORCP_TRACE"))
+      std::fprintf(stderr, "[orcp_plan] plan %.1f ms: get_succ (oracle) %.1f ms, host bookkeeping %.1f ms, %d expansions, %d closed + %d open states\n",
+                   r->seconds * 1e3, env->seconds_in_get_succ * 1e3, (r->seconds - env->seconds_in_get_succ) * 1e3, r->expanded,
+                   r->n_closed, r->n_open);
   };
   if (a->dim == 2) go(std::integral_constant<int, 2>());
   else go(std::integral_constant<int, 3>());
