@@ -674,6 +674,57 @@ class PriorityQueue {
   std::vector<Item> q_;
 };
 
+/// lattice key -> state, open addressing with linear probing (the keys are already well-mixed 64-bit
+/// hashes).  Only what the state space needs of the reference's hashMap (state_space.h:77-79):
+/// look-up, insert-if-absent, swap; iteration goes through StateSpace::order_.  A slot is empty
+/// while its value is null, so a key is only present once a state has been stored for it.
+template <typename V>
+class KeyMap {
+ public:
+  KeyMap() { rehash(64); }
+  V *find(std::size_t k) const {
+    for (std::size_t i = slot_of(k);; i = (i + 1) & mask_) {
+      if (!tab_[i].second) return nullptr;
+      if (tab_[i].first == k) return tab_[i].second;
+    }
+  }
+  /// the value slot of k, entered (null) if absent; the caller must store a non-null value before the
+  /// next call when `created`
+  V *&obtain(std::size_t k, bool &created) {
+    if ((size_ + 1) * 2 > tab_.size()) rehash(tab_.size() * 2);
+    for (std::size_t i = slot_of(k);; i = (i + 1) & mask_) {
+      if (!tab_[i].second) {
+        tab_[i].first = k;
+        size_++;
+        created = true;
+        return tab_[i].second;
+      }
+      if (tab_[i].first == k) {
+        created = false;
+        return tab_[i].second;
+      }
+    }
+  }
+  std::size_t size() const { return size_; }
+  void swap(KeyMap &o) { tab_.swap(o.tab_); std::swap(mask_, o.mask_); std::swap(size_, o.size_); }
+
+ private:
+  std::size_t slot_of(std::size_t k) const { return ((k * 0x9e3779b97f4a7c15ULL) >> 20) & mask_; }
+  void rehash(std::size_t n) {
+    std::vector<std::pair<std::size_t, V *>> old(n);
+    old.swap(tab_);
+    mask_ = n - 1;
+    for (const auto &e : old)
+      if (e.second) {
+        std::size_t i = slot_of(e.first);
+        while (tab_[i].second) i = (i + 1) & mask_;
+        tab_[i] = e;
+      }
+  }
+  std::vector<std::pair<std::size_t, V *>> tab_;
+  std::size_t mask_ = 0, size_ = 0;
+};
+
 /// StateSpace: include/mpl_planner/common/state_space.h:81-287
 template <int Dim>
 struct StateSpace {
@@ -683,7 +734,7 @@ struct StateSpace {
   /// space; order_ lists the states of hm_ in insertion order, which is the iteration order this
   /// planner defines for `for (it : hm_)` (boost::unordered_map leaves it unspecified; the loops
   /// of getSubStateSpace :184-192 and getLinkedNodes depend on it).
-  std::unordered_map<std::size_t, S *> hm_;
+  KeyMap<S> hm_;
   std::vector<S *> order_;
   /// states are carved out of 256-state blocks: one allocation per block, addresses never move
   struct Arena {
@@ -708,25 +759,22 @@ struct StateSpace {
   /// hm_[coord] of a key that is not in the map yet: create the state and enter it
   S *make_state(const Waypoint<Dim> &c, std::size_t k) {
     S *n = arena_.emplace(c, k);
-    hm_[k] = n;
+    bool created;
+    hm_.obtain(k, created) = n;
     order_.push_back(n);
     return n;
   }
-  S *find(std::size_t k) const {
-    auto it = hm_.find(k);
-    return it == hm_.end() ? nullptr : it->second;
-  }
+  S *find(std::size_t k) const { return hm_.find(k); }
   /// `StatePtr &p = hm_[coord]; if (!p) p = make_shared<State>(coord)` (graph_search.h:84-87) with
   /// one hash-map operation; coord() is only evaluated for a new state
   template <typename MakeCoord>
   S *get_or_make(std::size_t k, MakeCoord coord, bool &created) {
-    auto ins = hm_.try_emplace(k, nullptr);
-    created = ins.second;
+    S *&slot = hm_.obtain(k, created);
     if (created) {
-      ins.first->second = arena_.emplace(coord(), k);
-      order_.push_back(ins.first->second);
+      slot = arena_.emplace(coord(), k);
+      order_.push_back(slot);
     }
-    return ins.first->second;
+    return slot;
   }
   decimal_t eps_;
   decimal_t dt_{1};
@@ -777,19 +825,20 @@ struct StateSpace {
     currNode_ptr->g = start_g_;
     currNode_ptr->rhs = start_rhs_;
 
-    std::unordered_map<std::size_t, S *> new_hm;
+    KeyMap<S> new_hm;
     std::vector<S *> new_order;
     PriorityQueue<Dim> epq;
     epq.push(currNode_ptr->rhs, currNode_ptr);
-    new_hm[currNode_ptr->key] = currNode_ptr;
+    bool fresh;
+    new_hm.obtain(currNode_ptr->key, fresh) = currNode_ptr;
     new_order.push_back(currNode_ptr);
     while (!epq.empty()) {
       currNode_ptr = epq.top().second;
       epq.pop();
       for (std::size_t i = 0; i < currNode_ptr->succ.size(); i++) {
         const std::size_t skey = currNode_ptr->succ[i].node->key;
-        S *&slot = new_hm[skey];
-        if (!slot) {
+        S *&slot = new_hm.obtain(skey, fresh);
+        if (fresh) {
           slot = find(skey);  // hm_[succ_coord]; the reference reports a "critical bug" when absent
           if (!slot) throw std::logic_error("getSubStateSpace: successor is not in the state space");
           new_order.push_back(slot);
