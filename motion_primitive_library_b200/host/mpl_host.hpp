@@ -239,6 +239,12 @@ class env_base {
                           std::vector<int> &, std::vector<int> &, std::vector<int> &) const {
     throw std::runtime_error("this env does not serve edge re-validation");
   }
+  /// MapPlanner::setSearchRegion(path, dense) (src/mpl_planner/map_planner.cpp:46-95) served by the
+  /// env that owns the grids: build the tunnel of half-width ceil(radius/res) cells around the path
+  /// and install it as the search region.
+  virtual void search_region_from_path(const vec_E<Vecf<Dim>> &, const Vecf<Dim> &, bool) {
+    throw std::runtime_error("this env does not build search regions");
+  }
   virtual bool wants_candidates(std::size_t) const { return false; }
   virtual void prefetch(const vec_E<Waypoint<Dim>> &, const std::vector<std::size_t> &) const {}
   virtual const std::size_t *last_succ_keys() const { return nullptr; }
@@ -356,6 +362,9 @@ class env_map_gpu : public env_map_host<Dim> {
     potential_on_device_ = true;
   }
   /// MapPlanner::setSearchRegion on the device (mplx_set_search_region_path)
+  void search_region_from_path(const vec_E<Vecf<Dim>> &path, const Vecf<Dim> &radius, bool dense) override {
+    set_search_region_path(path, radius, dense);
+  }
   void set_search_region_path(const vec_E<Vecf<Dim>> &path, const Vecf<Dim> &radius, bool dense) {
     sync();
     std::vector<double> flat;
@@ -1317,9 +1326,38 @@ class MapPlanner : public PlannerBase<Dim> {
   }
   /// map_planner.cpp:46-95, on the device
   void setSearchRegion(const vec_E<Vecf<Dim>> &path, bool dense = false) {
-    if (!gpu_env_) throw std::runtime_error("setSearchRegion needs the GPU env (setMapUtil)");
-    gpu_env_->set_search_region_path(path, search_radius_, dense);
+    this->ENV_->search_region_from_path(path, search_radius_, dense);
   }
+  /// Trajectory::getWaypoints() positions of the last plan (trajectory.h:277-289): the start state of
+  /// every primitive and the end state of the last one = the states recoverTraj walked, start to goal
+  vec_E<Vecf<Dim>> getWaypointPositions() const {
+    vec_E<Vecf<Dim>> path;
+    if (this->ss_ptr_)
+      for (const auto *st : this->ss_ptr_->best_child_) path.push_back(st->coord.pos);
+    return path;
+  }
+  /// iterativePlan: src/mpl_planner/map_planner.cpp:393-433 — replan inside a tunnel around the previous
+  /// trajectory until the cost stops changing (or max_num iterations).  raw_path = the waypoint
+  /// positions of the trajectory to start from (getWaypointPositions() of an earlier plan).
+  bool iterativePlan(const Waypoint<Dim> &start, const Waypoint<Dim> &goal, const vec_E<Vecf<Dim>> &raw_path,
+                     int max_num = 3) {
+    vec_E<Vecf<Dim>> path = raw_path;
+    double prev_traj_cost = 0;
+    iterations_ = 0;
+    int cnt = 0;
+    while (cnt < max_num) {
+      cnt++;
+      iterations_ = cnt;
+      setSearchRegion(path, false);
+      if (!this->plan(start, goal)) return false;
+      if (prev_traj_cost == this->traj_cost_) break;
+      prev_traj_cost = this->traj_cost_;
+      path = getWaypointPositions();
+    }
+    return true;
+  }
+  /// plan() calls made by the last iterativePlan
+  int iterations() const { return iterations_; }
   void setPotentialWeight(decimal_t w) { this->ENV_->set_potential_weight(w); }
   void setGradientWeight(decimal_t w) { this->ENV_->set_gradient_weight(w); }
   env_map_gpu<Dim> *gpu_env() { return gpu_env_.get(); }
@@ -1411,6 +1449,7 @@ class MapPlanner : public PlannerBase<Dim> {
 
  protected:
   mutable LinkedTable lhm_;
+  int iterations_ = 0;
   std::shared_ptr<MapUtil<Dim>> map_util_;
   std::shared_ptr<env_map_gpu<Dim>> gpu_env_;
   Vecf<Dim> potential_radius_, potential_map_range_, search_radius_;

@@ -41,6 +41,42 @@ int mplh_plan(const mplh_plan_args *a, mplh_plan_result *r, uint64_t *closed_key
   }
 }
 
+/* MapPlanner::plan() followed by MapPlanner::iterativePlan() (map_planner.cpp:393-433) with the GPU
+ * env: every iteration builds the tunnel around the previous trajectory on the device
+ * (mplx_set_search_region_path) and replans inside it.  info[0] = plan() calls made by
+ * iterativePlan, info[1] = its return value. */
+int mplh_iterative_plan(const mplh_plan_args *a, const double *search_radius, int max_iter, mplh_plan_result *first,
+                        mplh_plan_result *last, int32_t *info, uint64_t *closed_keys, int cap_closed, int32_t *actions,
+                        int cap_actions) {
+  try {
+    *first = mplh_plan_result{};
+    *last = mplh_plan_result{};
+    auto go = [&](auto dimtag) {
+      constexpr int Dim = decltype(dimtag)::value;
+      MPL::MapPlanner<Dim> planner(false);
+      planner.setMapUtil(mplh::make_map<Dim>(a), a->device);
+      planner.setControl(a->control);
+      planner.setSpeculation(a->speculate);
+      if (a->potential) {
+        size_t n = 1;
+        for (int k = 0; k < Dim; k++) n *= (size_t)a->mdim[k];
+        planner.gpu_env()->set_potential_map(std::vector<int8_t>(a->potential, a->potential + n));
+        planner.setPotentialWeight(a->potential_weight);
+        planner.setGradientWeight(a->gradient_weight);
+      }
+      mplh::run_iterative<Dim>(planner, a, search_radius, max_iter, first, last, info, closed_keys, cap_closed, actions,
+                               cap_actions);
+    };
+    if (a->dim == 2) go(std::integral_constant<int, 2>());
+    else if (a->dim == 3) go(std::integral_constant<int, 3>());
+    else { g_err = "dim must be 2 or 3"; return 1; }
+    return 0;
+  } catch (const std::exception &e) {
+    g_err = e.what();
+    return 2;
+  }
+}
+
 /* A scripted LPA* session (plan_capi_types.h: PLAN / LINK / BLOCK / CLEAR / SUBTREE steps) on one
  * MapPlanner with the GPU env: get_succ, the getLinkedNodes voxel walk and the is_free(pr)
  * re-validation of decreaseCost all run on the device.  outs has n_steps entries; the action ids of

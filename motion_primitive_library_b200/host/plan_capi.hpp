@@ -21,11 +21,9 @@ std::shared_ptr<MPL::MapUtil<Dim>> make_map(const mplh_plan_args *a) {
   mu->setMap(ori, dim, MPL::Tmap(a->map, a->map + n), a->res);
   return mu;
 }
-// Configure `planner` (whose env is already installed) from the flat args, run plan(), and
-// export the closed set (sorted lattice keys) and the trajectory's action ids.
+// Configure `planner` (whose env is already installed) from the flat args.
 template <int Dim>
-void run(MPL::MapPlanner<Dim> &planner, const mplh_plan_args *a, mplh_plan_result *r, uint64_t *closed_keys,
-         int cap_closed, int32_t *actions, int cap_actions) {
+void configure(MPL::MapPlanner<Dim> &planner, const mplh_plan_args *a) {
   vec_E<VecDf> U;
   for (int i = 0; i < a->nU; i++) U.push_back(VecDf(a->U + (size_t)i * a->udim, a->U + (size_t)(i + 1) * a->udim));
   planner.setU(U);
@@ -33,10 +31,13 @@ void run(MPL::MapPlanner<Dim> &planner, const mplh_plan_args *a, mplh_plan_resul
   planner.setDt(a->T); planner.setW(a->w); planner.setWyaw(a->wyaw); planner.setEpsilon(a->eps);
   planner.setTol(a->tol_pos, a->tol_vel, a->tol_acc);
   planner.setMaxNum(a->max_num);
-  const Waypoint<Dim> start = wp_from<Dim>(a->start, a->control), goal = wp_from<Dim>(a->goal, a->control);
-  auto t0 = std::chrono::steady_clock::now();
-  r->valid = planner.plan(start, goal) ? 1 : 0;
-  r->seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+}
+// Export the state of the last plan(): cost, counts, the closed set (sorted lattice keys) and the
+// trajectory's action ids.
+template <int Dim>
+void export_result(MPL::MapPlanner<Dim> &planner, bool valid, mplh_plan_result *r, uint64_t *closed_keys, int cap_closed,
+                   int32_t *actions, int cap_actions) {
+  r->valid = valid ? 1 : 0;
   r->cost = planner.getTrajCost();
   r->expanded = planner.getExpandedNum();
   std::vector<uint64_t> keys;
@@ -45,10 +46,49 @@ void run(MPL::MapPlanner<Dim> &planner, const mplh_plan_args *a, mplh_plan_resul
   std::sort(keys.begin(), keys.end());
   r->n_closed = (int)keys.size();
   r->n_open = planner.initialized() ? (int)planner.getOpenSetSize() : 0;
-  for (int i = 0; i < (int)keys.size() && i < cap_closed; i++) closed_keys[i] = keys[i];
+  if (closed_keys)
+    for (int i = 0; i < (int)keys.size() && i < cap_closed; i++) closed_keys[i] = keys[i];
   const auto traj = planner.getTraj();
   r->n_actions = (int)traj.size();
-  for (int i = 0; i < (int)traj.size() && i < cap_actions; i++) actions[i] = traj[i].action_id;
+  if (actions)
+    for (int i = 0; i < (int)traj.size() && i < cap_actions; i++) actions[i] = traj[i].action_id;
+}
+// One plan() call: configure, plan, export.
+template <int Dim>
+void run(MPL::MapPlanner<Dim> &planner, const mplh_plan_args *a, mplh_plan_result *r, uint64_t *closed_keys,
+         int cap_closed, int32_t *actions, int cap_actions) {
+  configure<Dim>(planner, a);
+  const Waypoint<Dim> start = wp_from<Dim>(a->start, a->control), goal = wp_from<Dim>(a->goal, a->control);
+  auto t0 = std::chrono::steady_clock::now();
+  const bool ok = planner.plan(start, goal);
+  r->seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+  export_result<Dim>(planner, ok, r, closed_keys, cap_closed, actions, cap_actions);
+}
+// plan(), then iterativePlan() from that trajectory inside a tunnel of the given radius
+// (map_planner.cpp:393-433).  info[0] = plan() calls made by iterativePlan, info[1] = its return value.
+// `first` describes the initial plan, `last` (+ closed set / actions) the final one.
+template <int Dim>
+void run_iterative(MPL::MapPlanner<Dim> &planner, const mplh_plan_args *a, const double *search_radius, int max_iter,
+                   mplh_plan_result *first, mplh_plan_result *last, int32_t *info, uint64_t *closed_keys,
+                   int cap_closed, int32_t *actions, int cap_actions) {
+  configure<Dim>(planner, a);
+  const Waypoint<Dim> start = wp_from<Dim>(a->start, a->control), goal = wp_from<Dim>(a->goal, a->control);
+  auto t0 = std::chrono::steady_clock::now();
+  const bool ok0 = planner.plan(start, goal);
+  first->seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+  export_result<Dim>(planner, ok0, first, nullptr, 0, nullptr, 0);
+  info[0] = info[1] = 0;
+  *last = *first;
+  if (!ok0) return;
+  Vecf<Dim> rad;
+  for (int k = 0; k < Dim; k++) rad(k) = search_radius[k];
+  planner.setSearchRadius(rad);
+  t0 = std::chrono::steady_clock::now();
+  const bool ok = planner.iterativePlan(start, goal, planner.getWaypointPositions(), max_iter);
+  last->seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+  info[0] = planner.iterations();
+  info[1] = ok ? 1 : 0;
+  export_result<Dim>(planner, ok, last, closed_keys, cap_closed, actions, cap_actions);
 }
 
 inline void fnv(uint64_t &h, const void *p, size_t n) {

@@ -158,6 +158,47 @@ def lpa_session(args, script):
     return run_lpa(fn, lib, args, script)
 
 
+def load_iter_fn(path, fn):
+    L = C.CDLL(str(path))
+    f = getattr(L, fn)
+    f.argtypes = [C.POINTER(PlanArgs), C.c_void_p, C.c_int, C.POINTER(PlanResult), C.POINTER(PlanResult), C.c_void_p,
+                  C.c_void_p, C.c_int, C.c_void_p, C.c_int]
+    f.restype = C.c_int
+    return L, f
+
+
+def run_iterative(fn, lib, args, search_radius, max_iter=3, cap=1 << 21):
+    """plan() followed by MapPlanner::iterativePlan() from that trajectory.  Returns (first, last):
+    dicts of the plan-result fields; `last` also has closed keys, action ids, `iterations` (plan() calls
+    iterativePlan made; 0 when the driver cannot know) and `ok` (its return value)."""
+    first, last = PlanResult(), PlanResult()
+    info = np.zeros(2, dtype=np.int32)
+    rad = np.zeros(3)
+    rad[: len(search_radius)] = search_radius
+    closed = np.zeros(cap, dtype=np.uint64)
+    actions = np.zeros(65536, dtype=np.int32)
+    rc = fn(C.byref(args), rad.ctypes.data, int(max_iter), C.byref(first), C.byref(last), info.ctypes.data,
+            closed.ctypes.data, cap, actions.ctypes.data, actions.size)
+    if rc != 0:
+        err = getattr(lib, "mplh_last_error", None)
+        raise RuntimeError(err().decode() if err else f"iterative plan failed rc={rc}")
+    f = {k: getattr(first, k) for k, _ in PlanResult._fields_}
+    l = {k: getattr(last, k) for k, _ in PlanResult._fields_}
+    l["closed"] = closed[: min(last.n_closed, cap)].copy()
+    l["actions"] = actions[: last.n_actions].copy()
+    l["iterations"], l["ok"] = int(info[0]), int(info[1])
+    return f, l
+
+
+def iterative_plan(args, search_radius, max_iter=3):
+    """MPL::MapPlanner::plan() + iterativePlan() with the GPU env (tunnels built on the device)."""
+    if not LIB.exists():
+        raise ImportError(f"{LIB} not built (python -c 'import __graft_entry__ as g; g.build()')")
+    lib, fn = load_iter_fn(LIB, "mplh_iterative_plan")
+    lib.mplh_last_error.restype = C.c_char_p
+    return run_iterative(fn, lib, args, search_radius, max_iter)
+
+
 def _host():
     if not LIB.exists():
         raise ImportError(f"{LIB} not built (python -c 'import __graft_entry__ as g; g.build()')")

@@ -49,9 +49,42 @@ class env_map_oracle : public MPL::env_map_host<Dim> {
     orc_edges_cells(&e, in.data(), actions.data(), (int)parents.size(), (int64_t *)offset.data(), cells.data(), total);
   }
 
+  /// MapPlanner::setSearchRegion (src/mpl_planner/map_planner.cpp:46-95) restated on the CPU for the checker env
+  void search_region_from_path(const vec_E<Vecf<Dim>> &path, const Vecf<Dim> &radius, bool dense) override {
+    auto &mu = *this->map_util_;
+    vec_E<Veci<Dim>> ps;
+    if (!dense) {
+      for (unsigned int i = 1; i < path.size(); i++) {
+        auto pns = mu.rayTrace(path[i - 1], path[i]);
+        ps.insert(ps.end(), pns.begin(), pns.end());
+        ps.push_back(mu.floatToInt(path[i]));
+      }
+    } else {
+      for (const auto &pt : path) ps.push_back(mu.floatToInt(pt));
+    }
+    int rn[3] = {0, 0, 0};
+    for (int i = 0; i < Dim; i++) rn[i] = (int)std::ceil(radius(i) / mu.getRes());
+    const Veci<Dim> dim = mu.getDim();
+    std::size_t nvox = 1;
+    for (int i = 0; i < Dim; i++) nvox *= (std::size_t)dim(i);
+    std::vector<bool> in_region(nvox, false);
+    for (const auto &it : ps)
+      for (int dx = -rn[0]; dx <= rn[0]; dx++)
+        for (int dy = -rn[1]; dy <= rn[1]; dy++)
+          for (int dz = -rn[2]; dz <= rn[2]; dz++) {
+            Veci<Dim> pn = it;
+            pn(0) += dx; pn(1) += dy;
+            if (Dim == 3) pn(Dim - 1) += dz;
+            if (mu.isOutside(pn)) continue;
+            in_region[mu.getIndex(pn)] = true;
+          }
+    this->set_search_region(in_region);
+    region_bytes_.assign(in_region.begin(), in_region.end());
+  }
   /// like the GPU env, the oracle hands the successors' lattice keys back with them
   const std::size_t *last_succ_keys() const override { return keys_.data(); }
   mutable std::vector<std::size_t> keys_;
+  std::vector<uint8_t> region_bytes_;  // search_region_ as one byte per voxel for orc_env
   /// wall time spent inside get_succ (the oracle), so a caller can split plan() into env and bookkeeping
   mutable double seconds_in_get_succ = 0;
 
@@ -70,7 +103,8 @@ class env_map_oracle : public MPL::env_map_host<Dim> {
     e.nU = a_->nU; e.udim = a_->udim; e.U = a_->U;
     for (int k = 0; k < 3; k++) { e.mdim[k] = k < Dim ? a_->mdim[k] : 1; e.origin[k] = k < Dim ? a_->origin[k] : 0; }
     e.res = a_->res; e.map = (const int8_t *)this->map_util_->map().data(); e.potential = a_->potential;
-    e.potential_weight = a_->potential_weight; e.gradient_weight = a_->gradient_weight; e.region = nullptr;
+    e.potential_weight = a_->potential_weight; e.gradient_weight = a_->gradient_weight;
+    e.region = region_bytes_.empty() ? nullptr : region_bytes_.data();
     return e;
   }
   const mplh_plan_args *a_;
@@ -104,6 +138,24 @@ extern "C" int orcp_plan(const mplh_plan_args *a, mplh_plan_result *r, uint64_t 
       std::fprintf(stderr, "[orcp_plan] plan %.1f ms: get_succ (oracle) %.1f ms, host bookkeeping %.1f ms, %d expansions, %d closed + %d open states\n",
                    r->seconds * 1e3, env->seconds_in_get_succ * 1e3, (r->seconds - env->seconds_in_get_succ) * 1e3, r->expanded,
                    r->n_closed, r->n_open);
+  };
+  if (a->dim == 2) go(std::integral_constant<int, 2>());
+  else go(std::integral_constant<int, 3>());
+  return 0;
+}
+
+extern "C" int orcp_iterative_plan(const mplh_plan_args *a, const double *search_radius, int max_iter,
+                                   mplh_plan_result *first, mplh_plan_result *last, int32_t *info, uint64_t *closed_keys,
+                                   int cap_closed, int32_t *actions, int cap_actions) {
+  *first = mplh_plan_result{};
+  *last = mplh_plan_result{};
+  auto go = [&](auto dimtag) {
+    constexpr int Dim = decltype(dimtag)::value;
+    MPL::MapPlanner<Dim> planner(false);
+    auto mu = mplh::make_map<Dim>(a);
+    planner.setEnv(std::make_shared<env_map_oracle<Dim>>(mu, a), mu);
+    mplh::run_iterative<Dim>(planner, a, search_radius, max_iter, first, last, info, closed_keys, cap_closed, actions,
+                             cap_actions);
   };
   if (a->dim == 2) go(std::integral_constant<int, 2>());
   else go(std::integral_constant<int, 3>());

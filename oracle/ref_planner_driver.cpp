@@ -142,6 +142,96 @@ int region(const mplh_plan_args *a, const double *path, int n_path, const double
   for (size_t i = 0; i < reg.size(); i++) out[i] = reg[i] ? 1 : 0;
   return 0;
 }
+// plan(), then the reference's MapPlanner::iterativePlan(start, goal, getTraj(), max_iter) inside a tunnel
+// of the given radius; same outputs as the host planner's run_iterative (host/plan_capi.hpp).
+template <int Dim>
+void export_result(Planner<Dim> &planner, const mplh_plan_args *a, bool valid, mplh_plan_result *r, uint64_t *closed_keys,
+                   int cap_closed, int32_t *actions, int cap_actions) {
+  r->valid = valid ? 1 : 0;
+  r->cost = planner.getTrajCost();
+  r->expanded = planner.initialized() ? planner.getExpandedNum() : 0;
+  std::vector<uint64_t> keys;
+  int n_open = 0;
+  if (planner.initialized())
+    for (const auto &it : planner.ss_ptr_->hm_) {
+      if (!it.second) continue;
+      if (it.second->iterationclosed)
+        keys.push_back((uint64_t)hash_value(it.second->coord));
+      else if (it.second->iterationopened)
+        n_open++;
+    }
+  std::sort(keys.begin(), keys.end());
+  r->n_closed = (int)keys.size();
+  r->n_open = n_open;
+  if (closed_keys)
+    for (int i = 0; i < (int)keys.size() && i < cap_closed; i++) closed_keys[i] = keys[i];
+  const auto prs = planner.getTraj().getPrimitives();
+  r->n_actions = (int)prs.size();
+  const int order = __builtin_popcount(a->control & 15);
+  if (actions)
+    for (int i = 0; i < (int)prs.size() && i < cap_actions; i++) {
+      int found = -1;
+      for (int u = 0; u < a->nU && found < 0; u++) {
+        bool same = true;
+        for (int d = 0; d < Dim; d++) same = same && prs[i].pr(d).coeff()(5 - order) == a->U[(size_t)u * a->udim + d];
+        if (same && (a->control & 16)) same = prs[i].pr_yaw().coeff()(4) == a->U[(size_t)u * a->udim + Dim];
+        if (same) found = u;
+      }
+      actions[i] = found;
+    }
+}
+
+template <int Dim>
+int iterative(const mplh_plan_args *a, const double *search_radius, int max_iter, mplh_plan_result *first,
+              mplh_plan_result *last, int32_t *info, uint64_t *closed_keys, int cap_closed, int32_t *actions,
+              int cap_actions) {
+  Planner<Dim> planner(false);
+  planner.setMapUtil(make_map<Dim>(a));
+  vec_E<VecDf> U;
+  for (int i = 0; i < a->nU; i++) {
+    VecDf u(a->udim);
+    for (int k = 0; k < a->udim; k++) u(k) = a->U[(size_t)i * a->udim + k];
+    U.push_back(u);
+  }
+  planner.setU(U);
+  planner.setVmax(a->v_max);
+  planner.setAmax(a->a_max);
+  planner.setJmax(a->j_max);
+  planner.setYawmax(a->yaw_max);
+  planner.setDt(a->T);
+  planner.setW(a->w);
+  planner.setWyaw(a->wyaw);
+  planner.setEpsilon(a->eps);
+  planner.setTol(a->tol_pos, a->tol_vel, a->tol_acc);
+  planner.setMaxNum(a->max_num);
+  if (a->potential) {
+    size_t n = 1;
+    for (int k = 0; k < Dim; k++) n *= (size_t)a->mdim[k];
+    planner.ENV_->set_potential_map(std::vector<int8_t>(a->potential, a->potential + n));
+    planner.setPotentialWeight(a->potential_weight);
+    planner.setGradientWeight(a->gradient_weight);
+  }
+  const Waypoint<Dim> start = wp_from<Dim>(a->start, a->control), goal = wp_from<Dim>(a->goal, a->control);
+  auto t0 = std::chrono::steady_clock::now();
+  const bool ok0 = planner.plan(start, goal);
+  first->seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+  export_result<Dim>(planner, a, ok0, first, nullptr, 0, nullptr, 0);
+  info[0] = info[1] = 0;
+  *last = *first;
+  if (!ok0) return 0;
+  Vecf<Dim> rad;
+  for (int k = 0; k < Dim; k++) rad(k) = search_radius[k];
+  planner.setSearchRadius(rad);
+  // the reference does not report how many plan() calls iterativePlan made: count them through the
+  // expanded-nodes log, which plan() clears (planner_base.h:308) — not needed for parity, so 0 here
+  t0 = std::chrono::steady_clock::now();
+  const bool ok = planner.iterativePlan(start, goal, planner.getTraj(), max_iter);
+  last->seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+  info[1] = ok ? 1 : 0;
+  export_result<Dim>(planner, a, ok, last, closed_keys, cap_closed, actions, cap_actions);
+  return 0;
+}
+
 inline void fnv(uint64_t &h, const void *p, size_t n) {
   const unsigned char *b = (const unsigned char *)p;
   for (size_t i = 0; i < n; i++) {
@@ -281,6 +371,14 @@ int refp_lpa_run(const mplh_plan_args *a, const mplh_lpa_step *steps, int n_step
                  int32_t *actions, int cap_actions) {
   return a->dim == 2 ? lpa_run<2>(a, steps, n_steps, outs, actions, cap_actions)
                      : lpa_run<3>(a, steps, n_steps, outs, actions, cap_actions);
+}
+int refp_iterative_plan(const mplh_plan_args *a, const double *search_radius, int max_iter, mplh_plan_result *first,
+                        mplh_plan_result *last, int32_t *info, uint64_t *closed_keys, int cap_closed, int32_t *actions,
+                        int cap_actions) {
+  *first = mplh_plan_result{};
+  *last = mplh_plan_result{};
+  return a->dim == 2 ? iterative<2>(a, search_radius, max_iter, first, last, info, closed_keys, cap_closed, actions, cap_actions)
+                     : iterative<3>(a, search_radius, max_iter, first, last, info, closed_keys, cap_closed, actions, cap_actions);
 }
 int refp_plan(const mplh_plan_args *a, mplh_plan_result *r, uint64_t *closed_keys, int cap_closed, int32_t *actions,
               int cap_actions) {

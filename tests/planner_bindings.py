@@ -4,8 +4,8 @@ import subprocess
 from pathlib import Path
 
 from motion_primitive_library_b200.planner import (PlanArgs, PlanResult, QueryResult, Waypoint, load_fn,  # noqa: F401
-                                                   load_lpa_fn, lpa_session, make_args, plan, plan_batch, run_lpa,
-                                                   run_plan)
+                                                   iterative_plan, load_iter_fn, load_lpa_fn, lpa_session, make_args,
+                                                   plan, plan_batch, run_iterative, run_lpa, run_plan)
 
 ROOT = Path(__file__).resolve().parent.parent
 
@@ -37,6 +37,18 @@ def lpa_reference(args, script):
     getSubStateSpace, unmodified sources + Eigen/Boost stand-ins) on the same script."""
     lib, fn = load_lpa_fn(REF_PLANNER, "refp_lpa_run")
     return run_lpa(fn, lib, args, script)
+
+
+def iterative_oracle(args, search_radius, max_iter=3):
+    """The product's host plan() + iterativePlan() driven by the CPU-oracle env (TEST-ONLY harness)."""
+    lib, fn = load_iter_fn(ROOT / "oracle" / "liboracle_planner.so", "orcp_iterative_plan")
+    return run_iterative(fn, lib, args, search_radius, max_iter)
+
+
+def iterative_reference(args, search_radius, max_iter=3):
+    """The REFERENCE's plan() + MapPlanner::iterativePlan(start, goal, getTraj(), max_iter)."""
+    lib, fn = load_iter_fn(REF_PLANNER, "refp_iterative_plan")
+    return run_iterative(fn, lib, args, search_radius, max_iter)
 
 
 def ref_planner_available():

@@ -1,0 +1,42 @@
+"""MapPlanner::iterativePlan end to end on the GPU env (tunnels built by mplx_set_search_region_path,
+expansion by libmplx) against the same host planner with the CPU oracle env, which
+tests/test_iterative_plan_vs_ref.py pins to the reference's own iterativePlan.
+
+The GPU budget of the round in which this caller was added was spent before it could be run on a
+device: the pieces (device tunnel builder, expansion, host loop) are each parity-tested, but this
+composition executes on a GPU for the first time in the round-end run, so it is marked xfail
+(non-strict) until a passing run has been observed; it must be promoted to a hard test then."""
+import numpy as np
+import pytest
+
+import fixtures
+import planner_bindings as pb
+from test_iterative_plan_vs_ref import same
+
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.xfail(strict=False, reason="first GPU execution of this composition; promote once observed passing")]
+ACC = 0x03
+
+
+@pytest.mark.parametrize("radius,speculate", [((0.5, 0.5), 1), ((0.15, 0.15), 8)])
+def test_corridor_tunnel_replanning(radius, speculate):
+    c = fixtures.corridor()
+    a = pb.make_args(2, ACC, c["grid"], c["dim"], c["origin"], c["res"], fixtures.U_2d(), start=dict(pos=c["start"]),
+                     goal=dict(pos=c["goal"]), v_max=1.0, a_max=1.0, speculate=speculate)
+    orc = pb.iterative_oracle(a, radius, 3)
+    assert orc[0]["valid"] == 1 and orc[1]["ok"] == 1
+    got = pb.iterative_plan(a, radius, 3)
+    same(got, orc)
+    assert got[1]["iterations"] == orc[1]["iterations"]
+
+
+def test_voxel_map_tunnel():
+    from motion_primitive_library_b200 import scenarios as S
+
+    sc = S.scaled(S.cfg_headline(), 64)
+    nodes = sc.frontier(16, seed=4, max_steps=0)
+    a = pb.make_args(3, sc.control, sc.grid(), sc.dim_cells, sc.origin, sc.res, sc.U, start=dict(pos=nodes["pos"][0]),
+                     goal=dict(pos=nodes["pos"][1]), v_max=sc.v_max, a_max=sc.a_max, max_num=4000, speculate=16)
+    orc = pb.iterative_oracle(a, (0.6, 0.6, 0.4), 3)
+    assert orc[0]["valid"] == 1
+    same(pb.iterative_plan(a, (0.6, 0.6, 0.4), 3), orc)
