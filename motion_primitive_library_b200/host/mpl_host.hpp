@@ -22,6 +22,9 @@
 #include <mutex>
 #include <thread>
 #include <cmath>
+#ifndef M_PI
+#define M_PI 3.14159265358979323846
+#endif
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
@@ -105,6 +108,211 @@ std::size_t hash_value(const Waypoint<Dim> &key) {
   if (key.enable_t) { int id = std::round(key.t / 0.1); hash_combine(val, id); }
   return val;
 }
+
+/// power: include/mpl_basis/math.h:197-205
+inline decimal_t power(decimal_t t, int n) {
+  decimal_t tn = 1;
+  while (n > 0) { tn *= t; n--; }
+  return tn;
+}
+/// normalize_angle: include/mpl_basis/math.h:15-19
+inline decimal_t normalize_angle(decimal_t angle) {
+  while (angle > M_PI) angle -= 2.0 * M_PI;
+  while (angle < -M_PI) angle += 2.0 * M_PI;
+  return angle;
+}
+
+/// Primitive1D: include/mpl_basis/primitive.h:25-197 — the evaluators and the effort integral of one
+/// axis, with the reference's operand order (these run on the host, after planning: sampling a
+/// recovered trajectory is not on the expansion path).
+struct Primitive1D {
+  decimal_t c[6] = {0, 0, 0, 0, 0, 0};  // highest order first (primitive.h:34-50)
+  /// primitive.h:128-145
+  decimal_t p(decimal_t t) const {
+    return c[0] / 120 * power(t, 5) + c[1] / 24 * power(t, 4) + c[2] / 6 * power(t, 3) + c[3] / 2 * t * t + c[4] * t + c[5];
+  }
+  decimal_t v(decimal_t t) const { return c[0] / 24 * power(t, 4) + c[1] / 6 * power(t, 3) + c[2] / 2 * t * t + c[3] * t + c[4]; }
+  decimal_t a(decimal_t t) const { return c[0] / 6 * power(t, 3) + c[1] / 2 * t * t + c[2] * t + c[3]; }
+  decimal_t j(decimal_t t) const { return c[0] / 2 * t * t + c[1] * t + c[2]; }
+  /// primitive.h:92-122
+  decimal_t J(decimal_t t, int control) const {
+    const int o = control & 15;
+    if (o == Control::VEL)
+      return c[0] * c[0] / 5184 * power(t, 9) + c[0] * c[1] / 576 * power(t, 8) +
+             (c[1] * c[1] / 252 + c[0] * c[2] / 168) * power(t, 7) + (c[0] * c[3] / 72 + c[1] * c[2] / 36) * power(t, 6) +
+             (c[2] * c[2] / 20 + c[0] * c[4] / 60 + c[1] * c[3] / 15) * power(t, 5) +
+             (c[2] * c[3] / 4 + c[1] * c[4] / 12) * power(t, 4) + (c[3] * c[3] / 3 + c[2] * c[4] / 3) * power(t, 3) +
+             c[3] * c[4] * t * t + c[4] * c[4] * t;
+    else if (o == Control::ACC)
+      return c[0] * c[0] / 252 * power(t, 7) + c[0] * c[1] / 36 * power(t, 6) +
+             (c[1] * c[1] / 20 + c[0] * c[2] / 15) * power(t, 5) + (c[0] * c[3] / 12 + c[1] * c[2] / 4) * power(t, 4) +
+             (c[2] * c[2] / 3 + c[1] * c[3] / 3) * power(t, 3) + c[2] * c[3] * t * t + c[3] * c[3] * t;
+    else if (o == Control::JRK)
+      return c[0] * c[0] / 20 * power(t, 5) + c[0] * c[1] / 4 * power(t, 4) + (c[1] * c[1] + c[0] * c[2]) / 3 * power(t, 3) +
+             c[1] * c[2] * t * t + c[2] * c[2] * t;
+    else if (o == Control::SNP)
+      return c[0] * c[0] / 3 * power(t, 3) + c[0] * c[1] * t * t + c[1] * c[1] * t;
+    return 0;
+  }
+};
+
+/// Primitive<Dim> built from a state and a control input: include/mpl_basis/primitive.h:220-256
+template <int Dim>
+class Primitive {
+ public:
+  Primitive() {}
+  Primitive(const Waypoint<Dim> &p, const VecDf &u, decimal_t t) : t_(t), control_(p.control) {
+    const int o = control_ & 15;
+    for (int i = 0; i < Dim; i++) {
+      decimal_t *c = prs_[i].c;
+      if (o == Control::SNP) { c[1] = u[i]; c[2] = p.jrk(i); c[3] = p.acc(i); c[4] = p.vel(i); c[5] = p.pos(i); }
+      else if (o == Control::JRK) { c[2] = u[i]; c[3] = p.acc(i); c[4] = p.vel(i); c[5] = p.pos(i); }
+      else if (o == Control::ACC) { c[3] = u[i]; c[4] = p.vel(i); c[5] = p.pos(i); }
+      else if (o == Control::VEL) { c[4] = u[i]; c[5] = p.pos(i); }
+    }
+    if (control_ & 16) { pr_yaw_.c[4] = u[Dim]; pr_yaw_.c[5] = p.yaw; }
+  }
+  /// primitive.h:321-331
+  Waypoint<Dim> evaluate(decimal_t t) const {
+    Waypoint<Dim> p(control_);
+    for (int k = 0; k < Dim; k++) {
+      p.pos(k) = prs_[k].p(t);
+      p.vel(k) = prs_[k].v(t);
+      p.acc(k) = prs_[k].a(t);
+      p.jrk(k) = prs_[k].j(t);
+      if (p.use_yaw()) p.yaw = normalize_angle(pr_yaw_.p(t));
+    }
+    return p;
+  }
+  decimal_t t() const { return t_; }
+  int control() const { return control_; }
+  const Primitive1D &pr(int k) const { return prs_[k]; }
+  const Primitive1D &pr_yaw() const { return pr_yaw_; }
+  /// primitive.h:403-410
+  decimal_t J(int control) const {
+    decimal_t j = 0;
+    for (int k = 0; k < Dim; k++) j += prs_[k].J(t_, control);
+    return j;
+  }
+  decimal_t Jyaw() const { return pr_yaw_.J(t_, Control::VEL); }
+
+ private:
+  decimal_t t_{0};
+  int control_{Control::NONE};
+  Primitive1D prs_[Dim];
+  Primitive1D pr_yaw_;
+};
+
+/// Command<Dim>: include/mpl_basis/trajectory.h:19-28
+template <int Dim>
+struct Command {
+  Vecf<Dim> pos, vel, acc, jrk;
+  decimal_t yaw{0}, yaw_dot{0}, t{0};
+};
+
+/// Trajectory<Dim>: include/mpl_basis/trajectory.h:42-318 without the Lambda time scaling
+/// (scale / scale_down are not provided; lambda = 1, lambda_dot = 0 in the Command evaluation).
+template <int Dim>
+class Trajectory {
+ public:
+  Trajectory() {}
+  explicit Trajectory(const vec_E<Primitive<Dim>> &prs) : segs(prs) {
+    taus.push_back(0);
+    for (const auto &pr : prs) taus.push_back(pr.t() + taus.back());
+    Ts = taus;
+    total_t_ = taus.back();
+  }
+  /// trajectory.h:67-91
+  Waypoint<Dim> evaluate(decimal_t time) const {
+    decimal_t tau = time;
+    if (tau < 0) tau = 0;
+    if (tau > total_t_) tau = total_t_;
+    for (std::size_t id = 0; id < segs.size(); id++) {
+      if ((tau >= taus[id] && tau < taus[id + 1]) || id == segs.size() - 1) {
+        tau -= taus[id];
+        Waypoint<Dim> p(segs[id].control());
+        for (int j = 0; j < Dim; j++) {
+          const Primitive1D &pr = segs[id].pr(j);
+          p.pos(j) = pr.p(tau);
+          p.vel(j) = pr.v(tau);
+          p.acc(j) = pr.a(tau);
+          p.jrk(j) = pr.j(tau);
+          p.yaw = normalize_angle(segs[id].pr_yaw().p(tau));
+        }
+        return p;
+      }
+    }
+    return Waypoint<Dim>();
+  }
+  /// trajectory.h:100-137
+  bool evaluate(decimal_t time, Command<Dim> &p) const {
+    decimal_t tau = time;
+    if (tau < 0) tau = 0;
+    if (tau > total_t_) tau = total_t_;
+    const decimal_t lambda = 1, lambda_dot = 0;
+    for (std::size_t id = 0; id < segs.size(); id++) {
+      if (tau >= taus[id] && tau <= taus[id + 1]) {
+        tau -= taus[id];
+        for (int j = 0; j < Dim; j++) {
+          const Primitive1D &pr = segs[id].pr(j);
+          p.pos(j) = pr.p(tau);
+          p.vel(j) = pr.v(tau) / lambda;
+          p.acc(j) = pr.a(tau) / lambda / lambda - p.vel(j) * lambda_dot / lambda / lambda / lambda;
+          p.jrk(j) = pr.j(tau) / lambda / lambda - 3 / power(lambda, 3) * p.acc(j) * p.acc(j) * lambda_dot +
+                     3 / power(lambda, 4) * p.vel(j) * lambda_dot * lambda_dot;
+          p.yaw = normalize_angle(segs[id].pr_yaw().p(tau));
+          p.yaw_dot = normalize_angle(segs[id].pr_yaw().v(tau));
+          p.t = time;
+        }
+        return true;
+      }
+    }
+    return false;
+  }
+  /// trajectory.h:230-237
+  vec_E<Command<Dim>> sample(int N) const {
+    vec_E<Command<Dim>> ps(N + 1);
+    decimal_t dt = total_t_ / N;
+    for (int i = 0; i <= N; i++) evaluate(i * dt, ps[i]);
+    return ps;
+  }
+  /// trajectory.h:251-266
+  decimal_t J(int control) const {
+    decimal_t j = 0;
+    for (const auto &seg : segs) j += seg.J(control);
+    return j;
+  }
+  decimal_t Jyaw() const {
+    decimal_t j = 0;
+    for (const auto &seg : segs) j += seg.Jyaw();
+    return j;
+  }
+  /// trajectory.h:269-289
+  std::vector<decimal_t> getSegmentTimes() const {
+    std::vector<decimal_t> dts;
+    for (int i = 0; i < (int)Ts.size() - 1; i++) dts.push_back(Ts[i + 1] - Ts[i]);
+    return dts;
+  }
+  vec_E<Waypoint<Dim>> getWaypoints() const {
+    vec_E<Waypoint<Dim>> ws;
+    if (segs.empty()) return ws;
+    decimal_t t = 0;
+    for (const auto &seg : segs) {
+      ws.push_back(seg.evaluate(0));
+      ws.back().t = t;
+      t += seg.t();
+    }
+    ws.push_back(segs.back().evaluate(segs.back().t()));
+    ws.back().t = t;
+    return ws;
+  }
+  vec_E<Primitive<Dim>> getPrimitives() const { return segs; }
+  decimal_t getTotalTime() const { return total_t_; }
+
+  vec_E<Primitive<Dim>> segs;
+  std::vector<decimal_t> taus, Ts;
+  decimal_t total_t_{0};
+};
 
 namespace MPL {
 using Tmap = std::vector<signed char>;
@@ -192,6 +400,10 @@ class env_base {
     if (goal_key_ == state_key) return 0;
     if (v_max_ > 0) return w_ * (state.pos - goal_node_.pos).lpNormInf() / v_max_;
     return w_ * (state.pos - goal_node_.pos).lpNormInf();
+  }
+  /// env_base.h:228-231
+  void forward_action(const Waypoint<Dim> &curr, int action_id, Primitive<Dim> &pr) const {
+    pr = Primitive<Dim>(curr, U_[action_id], dt_);
   }
   void set_u(const vec_E<VecDf> &U) { U_ = U; touch(); }
   void set_v_max(decimal_t v) { v_max_ = v; touch(); }
@@ -1227,6 +1439,17 @@ class PlannerBase {
   virtual ~PlannerBase() {}
   bool initialized() { return !(ss_ptr_ == nullptr); }
   std::vector<Edge<Dim>> getTraj() const { return traj_; }
+  /// planner_base.h getTraj(): the recovered trajectory as piece-wise polynomials
+  /// (recoverTraj's forward_action per edge, graph_search.h:417-419)
+  Trajectory<Dim> getTrajectory() const {
+    vec_E<Primitive<Dim>> prs;
+    for (const auto &e : traj_) {
+      Primitive<Dim> pr;
+      ENV_->forward_action(e.from, e.action_id, pr);
+      prs.push_back(pr);
+    }
+    return Trajectory<Dim>(prs);
+  }
   decimal_t getTrajCost() const { return traj_cost_; }
   int getExpandedNum() const { return ss_ptr_ ? ss_ptr_->expand_iteration_ : 0; }
   vec_E<Vecf<Dim>> getExpandedNodes() const { return ENV_->expanded_nodes_; }

@@ -41,6 +41,30 @@ int mplh_plan(const mplh_plan_args *a, mplh_plan_result *r, uint64_t *closed_key
   }
 }
 
+/* MapPlanner::plan() with the GPU env, then the recovered Trajectory (include/mpl_basis/trajectory.h):
+ * sample(N), getTotalTime / J / Jyaw, getWaypoints and evaluate(t); layouts in plan_capi.hpp. */
+int mplh_plan_trajectory(const mplh_plan_args *a, int N, mplh_plan_result *r, double *samples, double *totals,
+                         double *waypoints, int cap_wp, int32_t *n_wp, double *mids) {
+  try {
+    *r = mplh_plan_result{};
+    auto go = [&](auto dimtag) {
+      constexpr int Dim = decltype(dimtag)::value;
+      MPL::MapPlanner<Dim> planner(false);
+      planner.setMapUtil(mplh::make_map<Dim>(a), a->device);
+      planner.setControl(a->control);
+      planner.setSpeculation(a->speculate);
+      mplh::run_trajectory<Dim>(planner, a, N, r, samples, totals, waypoints, cap_wp, n_wp, mids);
+    };
+    if (a->dim == 2) go(std::integral_constant<int, 2>());
+    else if (a->dim == 3) go(std::integral_constant<int, 3>());
+    else { g_err = "dim must be 2 or 3"; return 1; }
+    return 0;
+  } catch (const std::exception &e) {
+    g_err = e.what();
+    return 2;
+  }
+}
+
 /* MapPlanner::plan() followed by MapPlanner::iterativePlan() (map_planner.cpp:393-433) with the GPU
  * env: every iteration builds the tunnel around the previous trajectory on the device
  * (mplx_set_search_region_path) and replans inside it.  info[0] = plan() calls made by

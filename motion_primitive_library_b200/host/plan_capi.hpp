@@ -91,6 +91,41 @@ void run_iterative(MPL::MapPlanner<Dim> &planner, const mplh_plan_args *a, const
   export_result<Dim>(planner, ok, last, closed_keys, cap_closed, actions, cap_actions);
 }
 
+// plan(), then describe the recovered trajectory: samples = Trajectory::sample(N) as (N+1) rows of
+// {pos, vel, acc, jrk (Dim each), yaw, yaw_dot, t}; totals = {getTotalTime(), J(control), Jyaw(), #segments};
+// waypoints = getWaypoints() as rows of {pos, vel, acc, jrk (Dim each), yaw, t}; mids = evaluate(t) (the
+// Waypoint overload) at the N+1 sample times, same row layout as waypoints.
+template <int Dim>
+void run_trajectory(MPL::MapPlanner<Dim> &planner, const mplh_plan_args *a, int N, mplh_plan_result *r, double *samples,
+                    double *totals, double *waypoints, int cap_wp, int32_t *n_wp, double *mids) {
+  run<Dim>(planner, a, r, nullptr, 0, nullptr, 0);
+  *n_wp = 0;
+  totals[0] = totals[1] = totals[2] = totals[3] = 0;
+  if (!r->valid) return;
+  const Trajectory<Dim> traj = planner.getTrajectory();
+  totals[0] = traj.getTotalTime();
+  totals[1] = traj.J(a->control);
+  totals[2] = traj.Jyaw();
+  totals[3] = (double)traj.segs.size();
+  const auto cmds = traj.sample(N);
+  const int W = 4 * Dim + 3;
+  for (int i = 0; i <= N; i++) {
+    double *o = samples + (size_t)i * W;
+    for (int d = 0; d < Dim; d++) { o[d] = cmds[i].pos(d); o[Dim + d] = cmds[i].vel(d); o[2 * Dim + d] = cmds[i].acc(d); o[3 * Dim + d] = cmds[i].jrk(d); }
+    o[4 * Dim] = cmds[i].yaw; o[4 * Dim + 1] = cmds[i].yaw_dot; o[4 * Dim + 2] = cmds[i].t;
+  }
+  const int V = 4 * Dim + 2;
+  auto put = [&](double *o, const Waypoint<Dim> &w) {
+    for (int d = 0; d < Dim; d++) { o[d] = w.pos(d); o[Dim + d] = w.vel(d); o[2 * Dim + d] = w.acc(d); o[3 * Dim + d] = w.jrk(d); }
+    o[4 * Dim] = w.yaw; o[4 * Dim + 1] = w.t;
+  };
+  const auto ws = traj.getWaypoints();
+  *n_wp = (int)ws.size();
+  for (int i = 0; i < (int)ws.size() && i < cap_wp; i++) put(waypoints + (size_t)i * V, ws[i]);
+  const decimal_t dt = traj.getTotalTime() / N;
+  for (int i = 0; i <= N; i++) put(mids + (size_t)i * V, traj.evaluate(i * dt));
+}
+
 inline void fnv(uint64_t &h, const void *p, size_t n) {
   const unsigned char *b = (const unsigned char *)p;
   for (size_t i = 0; i < n; i++) { h ^= b[i]; h *= 0x100000001b3ULL; }

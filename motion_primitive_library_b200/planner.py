@@ -158,6 +158,46 @@ def lpa_session(args, script):
     return run_lpa(fn, lib, args, script)
 
 
+def load_traj_fn(path, fn):
+    L = C.CDLL(str(path))
+    f = getattr(L, fn)
+    f.argtypes = [C.POINTER(PlanArgs), C.c_int, C.POINTER(PlanResult), C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
+                  C.POINTER(C.c_int32), C.c_void_p]
+    f.restype = C.c_int
+    return L, f
+
+
+def run_trajectory(fn, lib, args, n_samples=50, cap_wp=4096):
+    """plan(), then the recovered Trajectory (trajectory.h): dict with `commands` = sample(N) rows
+    {pos, vel, acc, jrk, yaw, yaw_dot, t}, `total_time`, `J`, `Jyaw`, `segments`, `waypoints` =
+    getWaypoints() rows {pos, vel, acc, jrk, yaw, t} and `evaluated` = evaluate(t) at the sample times."""
+    dim = args.dim
+    r = PlanResult()
+    samples = np.zeros((n_samples + 1, 4 * dim + 3))
+    totals = np.zeros(4)
+    wps = np.zeros((cap_wp, 4 * dim + 2))
+    mids = np.zeros((n_samples + 1, 4 * dim + 2))
+    n_wp = C.c_int32(0)
+    rc = fn(C.byref(args), n_samples, C.byref(r), samples.ctypes.data, totals.ctypes.data, wps.ctypes.data, cap_wp,
+            C.byref(n_wp), mids.ctypes.data)
+    if rc != 0:
+        err = getattr(lib, "mplh_last_error", None)
+        raise RuntimeError(err().decode() if err else f"trajectory failed rc={rc}")
+    out = {k: getattr(r, k) for k, _ in PlanResult._fields_}
+    out.update(commands=samples, total_time=totals[0], J=totals[1], Jyaw=totals[2], segments=int(totals[3]),
+               waypoints=wps[: min(n_wp.value, cap_wp)].copy(), evaluated=mids)
+    return out
+
+
+def plan_trajectory(args, n_samples=50):
+    """MPL::MapPlanner::plan() with the GPU env + the recovered Trajectory (sample / waypoints / efforts)."""
+    if not LIB.exists():
+        raise ImportError(f"{LIB} not built (python -c 'import __graft_entry__ as g; g.build()')")
+    lib, fn = load_traj_fn(LIB, "mplh_plan_trajectory")
+    lib.mplh_last_error.restype = C.c_char_p
+    return run_trajectory(fn, lib, args, n_samples)
+
+
 def load_iter_fn(path, fn):
     L = C.CDLL(str(path))
     f = getattr(L, fn)

@@ -161,3 +161,18 @@ extern "C" int orcp_iterative_plan(const mplh_plan_args *a, const double *search
   else go(std::integral_constant<int, 3>());
   return 0;
 }
+
+extern "C" int orcp_plan_trajectory(const mplh_plan_args *a, int N, mplh_plan_result *r, double *samples, double *totals,
+                                    double *waypoints, int cap_wp, int32_t *n_wp, double *mids) {
+  *r = mplh_plan_result{};
+  auto go = [&](auto dimtag) {
+    constexpr int Dim = decltype(dimtag)::value;
+    MPL::MapPlanner<Dim> planner(false);
+    auto mu = mplh::make_map<Dim>(a);
+    planner.setEnv(std::make_shared<env_map_oracle<Dim>>(mu, a), mu);
+    mplh::run_trajectory<Dim>(planner, a, N, r, samples, totals, waypoints, cap_wp, n_wp, mids);
+  };
+  if (a->dim == 2) go(std::integral_constant<int, 2>());
+  else go(std::integral_constant<int, 3>());
+  return 0;
+}

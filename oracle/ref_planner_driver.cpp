@@ -232,6 +232,76 @@ int iterative(const mplh_plan_args *a, const double *search_radius, int max_iter
   return 0;
 }
 
+// plan(), then the reference's own Trajectory: sample(N), totals, getWaypoints, evaluate(t) — the layouts of
+// run_trajectory in host/plan_capi.hpp.
+template <int Dim>
+int trajectory(const mplh_plan_args *a, int N, mplh_plan_result *r, double *samples, double *totals, double *waypoints,
+               int cap_wp, int32_t *n_wp, double *mids) {
+  Planner<Dim> planner(false);
+  planner.setMapUtil(make_map<Dim>(a));
+  vec_E<VecDf> U;
+  for (int i = 0; i < a->nU; i++) {
+    VecDf u(a->udim);
+    for (int k = 0; k < a->udim; k++) u(k) = a->U[(size_t)i * a->udim + k];
+    U.push_back(u);
+  }
+  planner.setU(U);
+  planner.setVmax(a->v_max);
+  planner.setAmax(a->a_max);
+  planner.setJmax(a->j_max);
+  planner.setYawmax(a->yaw_max);
+  planner.setDt(a->T);
+  planner.setW(a->w);
+  planner.setWyaw(a->wyaw);
+  planner.setEpsilon(a->eps);
+  planner.setTol(a->tol_pos, a->tol_vel, a->tol_acc);
+  planner.setMaxNum(a->max_num);
+  const Waypoint<Dim> start = wp_from<Dim>(a->start, a->control), goal = wp_from<Dim>(a->goal, a->control);
+  const bool ok = planner.plan(start, goal);
+  export_result<Dim>(planner, a, ok, r, nullptr, 0, nullptr, 0);
+  *n_wp = 0;
+  totals[0] = totals[1] = totals[2] = totals[3] = 0;
+  if (!ok) return 0;
+  const Trajectory<Dim> traj = planner.getTraj();
+  totals[0] = traj.getTotalTime();
+  totals[1] = traj.J((Control::Control)a->control);
+  totals[2] = traj.Jyaw();
+  totals[3] = (double)traj.segs.size();
+  const auto cmds = traj.sample(N);
+  const int W = 4 * Dim + 3;
+  for (int i = 0; i <= N; i++) {
+    double *o = samples + (size_t)i * W;
+    for (int d = 0; d < Dim; d++) {
+      o[d] = cmds[i].pos(d);
+      o[Dim + d] = cmds[i].vel(d);
+      o[2 * Dim + d] = cmds[i].acc(d);
+      o[3 * Dim + d] = cmds[i].jrk(d);
+    }
+    o[4 * Dim] = cmds[i].yaw;
+    o[4 * Dim + 1] = cmds[i].yaw_dot;
+    o[4 * Dim + 2] = cmds[i].t;
+  }
+  const int V = 4 * Dim + 2;
+  const auto ws = traj.getWaypoints();
+  *n_wp = (int)ws.size();
+  for (int i = 0; i < (int)ws.size() + N + 1; i++) {
+    const bool wp = i < (int)ws.size();
+    if (wp && i >= cap_wp) continue;
+    const decimal_t dt = traj.getTotalTime() / N;
+    const Waypoint<Dim> w = wp ? ws[i] : traj.evaluate((i - (int)ws.size()) * dt);
+    double *o = wp ? waypoints + (size_t)i * V : mids + (size_t)(i - (int)ws.size()) * V;
+    for (int d = 0; d < Dim; d++) {
+      o[d] = w.pos(d);
+      o[Dim + d] = w.vel(d);
+      o[2 * Dim + d] = w.acc(d);
+      o[3 * Dim + d] = w.jrk(d);
+    }
+    o[4 * Dim] = w.yaw;
+    o[4 * Dim + 1] = w.t;
+  }
+  return 0;
+}
+
 inline void fnv(uint64_t &h, const void *p, size_t n) {
   const unsigned char *b = (const unsigned char *)p;
   for (size_t i = 0; i < n; i++) {
@@ -371,6 +441,12 @@ int refp_lpa_run(const mplh_plan_args *a, const mplh_lpa_step *steps, int n_step
                  int32_t *actions, int cap_actions) {
   return a->dim == 2 ? lpa_run<2>(a, steps, n_steps, outs, actions, cap_actions)
                      : lpa_run<3>(a, steps, n_steps, outs, actions, cap_actions);
+}
+int refp_plan_trajectory(const mplh_plan_args *a, int N, mplh_plan_result *r, double *samples, double *totals,
+                         double *waypoints, int cap_wp, int32_t *n_wp, double *mids) {
+  *r = mplh_plan_result{};
+  return a->dim == 2 ? trajectory<2>(a, N, r, samples, totals, waypoints, cap_wp, n_wp, mids)
+                     : trajectory<3>(a, N, r, samples, totals, waypoints, cap_wp, n_wp, mids);
 }
 int refp_iterative_plan(const mplh_plan_args *a, const double *search_radius, int max_iter, mplh_plan_result *first,
                         mplh_plan_result *last, int32_t *info, uint64_t *closed_keys, int cap_closed, int32_t *actions,

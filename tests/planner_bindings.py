@@ -4,8 +4,9 @@ import subprocess
 from pathlib import Path
 
 from motion_primitive_library_b200.planner import (PlanArgs, PlanResult, QueryResult, Waypoint, load_fn,  # noqa: F401
-                                                   iterative_plan, load_iter_fn, load_lpa_fn, lpa_session, make_args,
-                                                   plan, plan_batch, run_iterative, run_lpa, run_plan)
+                                                   iterative_plan, load_iter_fn, load_lpa_fn, load_traj_fn, lpa_session,
+                                                   make_args, plan, plan_batch, plan_trajectory, run_iterative, run_lpa,
+                                                   run_plan, run_trajectory)
 
 ROOT = Path(__file__).resolve().parent.parent
 
@@ -49,6 +50,17 @@ def iterative_reference(args, search_radius, max_iter=3):
     """The REFERENCE's plan() + MapPlanner::iterativePlan(start, goal, getTraj(), max_iter)."""
     lib, fn = load_iter_fn(REF_PLANNER, "refp_iterative_plan")
     return run_iterative(fn, lib, args, search_radius, max_iter)
+
+
+def trajectory_oracle(args, n_samples=50):
+    lib, fn = load_traj_fn(ROOT / "oracle" / "liboracle_planner.so", "orcp_plan_trajectory")
+    return run_trajectory(fn, lib, args, n_samples)
+
+
+def trajectory_reference(args, n_samples=50):
+    """The REFERENCE's plan() + its own Trajectory::sample / getWaypoints / evaluate / J."""
+    lib, fn = load_traj_fn(REF_PLANNER, "refp_plan_trajectory")
+    return run_trajectory(fn, lib, args, n_samples)
 
 
 def ref_planner_available():
