@@ -58,6 +58,12 @@ struct Vecf {
   Vecf operator*(decimal_t k) const { Vecf r; for (int i = 0; i < N; i++) r.d[i] = d[i] * k; return r; }
   Vecf operator/(decimal_t k) const { Vecf r; for (int i = 0; i < N; i++) r.d[i] = d[i] / k; return r; }
   decimal_t lpNormInf() const { decimal_t m = 0; for (int i = 0; i < N; i++) m = std::max(m, std::abs(d[i])); return m; }
+  /// Eigen's unrolled fixed-size reduction: a0 + a1 for two elements, a0 + (a1 + a2) for three
+  decimal_t dot(const Vecf &o) const {
+    if (N == 2) return d[0] * o.d[0] + d[1] * o.d[1];
+    return d[0] * o.d[0] + (d[1] * o.d[1] + d[N - 1] * o.d[N - 1]);
+  }
+  decimal_t norm() const { return std::sqrt(dot(*this)); }
 };
 template <int N>
 struct Veci {
@@ -120,6 +126,64 @@ inline decimal_t normalize_angle(decimal_t angle) {
   while (angle > M_PI) angle -= 2.0 * M_PI;
   while (angle < -M_PI) angle += 2.0 * M_PI;
   return angle;
+}
+
+/// Closed-form real roots, include/mpl_basis/math.h:22-96 (host side: the minimum-time heuristic).
+/// quad: b t^2 + c t + d;  cubic: a t^3 + b t^2 + c t + d;  quartic: a t^4 + ... + e.
+inline std::vector<decimal_t> quad(decimal_t b, decimal_t c, decimal_t d) {
+  std::vector<decimal_t> dts;
+  const decimal_t p = c * c - 4 * b * d;
+  if (p < 0) return dts;
+  dts.push_back((-c - sqrt(p)) / (2 * b));
+  dts.push_back((-c + sqrt(p)) / (2 * b));
+  return dts;
+}
+inline std::vector<decimal_t> cubic(decimal_t a, decimal_t b, decimal_t c, decimal_t d) {
+  std::vector<decimal_t> dts;
+  const decimal_t a2 = b / a, a1 = c / a, a0 = d / a;
+  const decimal_t Q = (3 * a1 - a2 * a2) / 9;
+  const decimal_t R = (9 * a1 * a2 - 27 * a0 - 2 * a2 * a2 * a2) / 54;
+  const decimal_t D = Q * Q * Q + R * R;
+  if (D > 0) {
+    const decimal_t S = std::cbrt(R + sqrt(D)), T = std::cbrt(R - sqrt(D));
+    dts.push_back(-a2 / 3 + (S + T));
+  } else if (D == 0) {
+    const decimal_t S = std::cbrt(R);
+    dts.push_back(-a2 / 3 + S + S);
+    dts.push_back(-a2 / 3 - S);
+  } else {
+    const decimal_t theta = acos(R / sqrt(-Q * Q * Q));
+    dts.push_back(2 * sqrt(-Q) * cos(theta / 3) - a2 / 3);
+    dts.push_back(2 * sqrt(-Q) * cos((theta + 2 * M_PI) / 3) - a2 / 3);
+    dts.push_back(2 * sqrt(-Q) * cos((theta + 4 * M_PI) / 3) - a2 / 3);
+  }
+  return dts;
+}
+inline std::vector<decimal_t> quartic(decimal_t a, decimal_t b, decimal_t c, decimal_t d, decimal_t e) {
+  std::vector<decimal_t> dts;
+  const decimal_t a3 = b / a, a2 = c / a, a1 = d / a, a0 = e / a;
+  const std::vector<decimal_t> ys = cubic(1, -a2, a1 * a3 - 4 * a0, 4 * a2 * a0 - a1 * a1 - a3 * a3 * a0);
+  const decimal_t y1 = ys.front();
+  const decimal_t r = a3 * a3 / 4 - a2 + y1;
+  if (r < 0) return dts;
+  const decimal_t R = sqrt(r);
+  decimal_t D, E;
+  if (R != 0) {
+    D = sqrt(0.75 * a3 * a3 - R * R - 2 * a2 + 0.25 * (4 * a3 * a2 - 8 * a1 - a3 * a3 * a3) / R);
+    E = sqrt(0.75 * a3 * a3 - R * R - 2 * a2 - 0.25 * (4 * a3 * a2 - 8 * a1 - a3 * a3 * a3) / R);
+  } else {
+    D = sqrt(0.75 * a3 * a3 - 2 * a2 + 2 * sqrt(y1 * y1 - 4 * a0));
+    E = sqrt(0.75 * a3 * a3 - 2 * a2 - 2 * sqrt(y1 * y1 - 4 * a0));
+  }
+  if (!std::isnan(D)) {
+    dts.push_back(-a3 / 4 + R / 2 + D / 2);
+    dts.push_back(-a3 / 4 + R / 2 - D / 2);
+  }
+  if (!std::isnan(E)) {
+    dts.push_back(-a3 / 4 - R / 2 + E / 2);
+    dts.push_back(-a3 / 4 - R / 2 - E / 2);
+  }
+  return dts;
 }
 
 /// Primitive1D: include/mpl_basis/primitive.h:25-197 — the evaluators and the effort integral of one
@@ -398,9 +462,43 @@ class env_base {
   /// `goal_node_ == state` is hash equality (waypoint.h:133-135), the goal's hash is cached by set_goal
   virtual decimal_t get_heur(const Waypoint<Dim> &state, std::size_t state_key) const {
     if (goal_key_ == state_key) return 0;
-    if (v_max_ > 0) return w_ * (state.pos - goal_node_.pos).lpNormInf() / v_max_;
-    return w_ * (state.pos - goal_node_.pos).lpNormInf();
+    return cal_heur(state, goal_node_);
   }
+  /// cal_heur: env_base.h:55-211.  With heur_ignore_dynamics_ (the default) the Linf distance over
+  /// v_max; otherwise the minimum of the closed-form time-optimal cost (ACC state: a quartic in t).
+  /// The JRK branches need the degree-6 companion-matrix solver of Eigen and are not provided.
+  virtual decimal_t cal_heur(const Waypoint<Dim> &state, const Waypoint<Dim> &goal) const {
+    if (heur_ignore_dynamics_) {
+      if (v_max_ > 0) return w_ * (state.pos - goal.pos).lpNormInf() / v_max_;
+      return w_ * (state.pos - goal.pos).lpNormInf();
+    }
+    if (state.control == Control::JRK)
+      throw std::runtime_error("cal_heur with dynamics for JRK states needs a degree-6 polynomial solver (not provided)");
+    const bool acc_acc = state.control == Control::ACC && goal.control == Control::ACC;
+    const bool acc_vel = state.control == Control::ACC && goal.control == Control::VEL;
+    if (acc_acc || acc_vel) {
+      const Vecf<Dim> dp = goal.pos - state.pos;
+      const Vecf<Dim> v0 = state.vel, v1 = goal.vel;
+      const decimal_t c1 = acc_acc ? -36 * dp.dot(dp) : -9 * dp.dot(dp);
+      const decimal_t c2 = acc_acc ? 24 * (v0 + v1).dot(dp) : 12 * v0.dot(dp);
+      const decimal_t c3 = acc_acc ? -4 * (v0.dot(v0) + v0.dot(v1) + v1.dot(v1)) : -3 * v0.dot(v0);
+      const decimal_t c4 = 0, c5 = w_;
+      std::vector<decimal_t> ts = quartic(c5, c4, c3, c2, c1);
+      const decimal_t t_bar = (state.pos - goal.pos).lpNormInf() / v_max_;
+      ts.push_back(t_bar);
+      decimal_t cost = std::numeric_limits<decimal_t>::max();
+      for (auto t : ts) {
+        if (t < t_bar) continue;
+        const decimal_t c = -c1 / 3 / t / t / t - c2 / 2 / t / t - c3 / t + w_ * t;
+        if (c < cost) cost = c;
+      }
+      return cost;
+    }
+    if (state.control == Control::VEL && goal.control == Control::VEL) return (w_ + 1) * (state.pos - goal.pos).norm();
+    return w_ * (state.pos - goal.pos).norm() / v_max_;
+  }
+  /// env_base.h:305-306
+  void set_heur_ignore_dynamics(bool ignore) { heur_ignore_dynamics_ = ignore; }
   /// env_base.h:228-231
   void forward_action(const Waypoint<Dim> &curr, int action_id, Primitive<Dim> &pr) const {
     pr = Primitive<Dim>(curr, U_[action_id], dt_);
@@ -1479,6 +1577,8 @@ class PlannerBase {
     ENV_->set_tol_pos(tol_pos); ENV_->set_tol_vel(tol_vel); ENV_->set_tol_acc(tol_acc);
   }
   void setLookahead(int k) { lookahead_ = k; }
+  /// planner_base.h:233-237
+  void setHeurIgnoreDynamics(bool ignore) { ENV_->set_heur_ignore_dynamics(ignore); }
   /// planner_base.h:170-176
   void setLPAstar(bool use_lpastar) { use_lpastar_ = use_lpastar; }
   /// planner_base.h:155: prune the state space to the subtree under best_child_[time_step]

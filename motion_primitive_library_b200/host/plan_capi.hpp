@@ -31,6 +31,7 @@ void configure(MPL::MapPlanner<Dim> &planner, const mplh_plan_args *a) {
   planner.setDt(a->T); planner.setW(a->w); planner.setWyaw(a->wyaw); planner.setEpsilon(a->eps);
   planner.setTol(a->tol_pos, a->tol_vel, a->tol_acc);
   planner.setMaxNum(a->max_num);
+  planner.setHeurIgnoreDynamics(a->heur_ignore_dynamics != 0);
 }
 // Export the state of the last plan(): cost, counts, the closed set (sorted lattice keys) and the
 // trajectory's action ids.
@@ -161,6 +162,7 @@ void run_lpa(MPL::MapPlanner<Dim> &planner, const std::shared_ptr<MPL::MapUtil<D
   planner.setDt(a->T); planner.setW(a->w); planner.setWyaw(a->wyaw); planner.setEpsilon(a->eps);
   planner.setTol(a->tol_pos, a->tol_vel, a->tol_acc);
   planner.setMaxNum(a->max_num);
+  planner.setHeurIgnoreDynamics(a->heur_ignore_dynamics != 0);
   planner.setLPAstar(true);
   Waypoint<Dim> start = wp_from<Dim>(a->start, a->control);
   const Waypoint<Dim> goal = wp_from<Dim>(a->goal, a->control);

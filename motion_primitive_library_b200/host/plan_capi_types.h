@@ -23,6 +23,7 @@ typedef struct {
   int32_t device;
   const int8_t *potential; /* optional */
   double potential_weight, gradient_weight;
+  int32_t heur_ignore_dynamics; /* PlannerBase::setHeurIgnoreDynamics; 1 = the reference's default */
 } mplh_plan_args;
 
 typedef struct {

@@ -22,7 +22,7 @@ class PlanArgs(C.Structure):
         ("tol_pos", C.c_double), ("tol_vel", C.c_double), ("tol_acc", C.c_double),
         ("start", Waypoint), ("goal", Waypoint), ("max_num", C.c_int32), ("speculate", C.c_int32),
         ("device", C.c_int32), ("potential", C.c_void_p), ("potential_weight", C.c_double),
-        ("gradient_weight", C.c_double),
+        ("gradient_weight", C.c_double), ("heur_ignore_dynamics", C.c_int32),
     ]
 
 
@@ -64,7 +64,7 @@ def load_fn(path, fn):
 
 def make_args(dim, control, grid, mdim, origin, res, U, start, goal, T=1.0, w=10.0, wyaw=1.0, eps=1.0, v_max=-1.0,
               a_max=-1.0, j_max=-1.0, yaw_max=-1.0, tol_pos=0.5, tol_vel=-1.0, tol_acc=-1.0, max_num=-1, speculate=1,
-              potential=None, potential_weight=0.1, gradient_weight=0.0):
+              potential=None, potential_weight=0.1, gradient_weight=0.0, heur_ignore_dynamics=True):
     keep = dict(grid=np.ascontiguousarray(grid, dtype=np.int8), U=np.ascontiguousarray(U, dtype=np.float64))
     a = PlanArgs()
     a.dim, a.control = dim, control
@@ -90,6 +90,7 @@ def make_args(dim, control, grid, mdim, origin, res, U, start, goal, T=1.0, w=10
         keep["pot"] = np.ascontiguousarray(potential, dtype=np.int8)
         a.potential = keep["pot"].ctypes.data
     a.potential_weight, a.gradient_weight = potential_weight, gradient_weight
+    a.heur_ignore_dynamics = 1 if heur_ignore_dynamics else 0
     a._keep = keep
     return a
 

@@ -69,6 +69,7 @@ int plan(const mplh_plan_args *a, mplh_plan_result *r, uint64_t *closed_keys, in
   planner.setEpsilon(a->eps);
   planner.setTol(a->tol_pos, a->tol_vel, a->tol_acc);
   planner.setMaxNum(a->max_num);
+  planner.setHeurIgnoreDynamics(a->heur_ignore_dynamics != 0);
   const Waypoint<Dim> start = wp_from<Dim>(a->start, a->control), goal = wp_from<Dim>(a->goal, a->control);
   auto t0 = std::chrono::steady_clock::now();
   r->valid = planner.plan(start, goal) ? 1 : 0;
@@ -204,6 +205,7 @@ int iterative(const mplh_plan_args *a, const double *search_radius, int max_iter
   planner.setEpsilon(a->eps);
   planner.setTol(a->tol_pos, a->tol_vel, a->tol_acc);
   planner.setMaxNum(a->max_num);
+  planner.setHeurIgnoreDynamics(a->heur_ignore_dynamics != 0);
   if (a->potential) {
     size_t n = 1;
     for (int k = 0; k < Dim; k++) n *= (size_t)a->mdim[k];
@@ -256,6 +258,7 @@ int trajectory(const mplh_plan_args *a, int N, mplh_plan_result *r, double *samp
   planner.setEpsilon(a->eps);
   planner.setTol(a->tol_pos, a->tol_vel, a->tol_acc);
   planner.setMaxNum(a->max_num);
+  planner.setHeurIgnoreDynamics(a->heur_ignore_dynamics != 0);
   const Waypoint<Dim> start = wp_from<Dim>(a->start, a->control), goal = wp_from<Dim>(a->goal, a->control);
   const bool ok = planner.plan(start, goal);
   export_result<Dim>(planner, a, ok, r, nullptr, 0, nullptr, 0);
@@ -363,6 +366,7 @@ int lpa_run(const mplh_plan_args *a, const mplh_lpa_step *steps, int n_steps, mp
   planner.setEpsilon(a->eps);
   planner.setTol(a->tol_pos, a->tol_vel, a->tol_acc);
   planner.setMaxNum(a->max_num);
+  planner.setHeurIgnoreDynamics(a->heur_ignore_dynamics != 0);
   planner.setLPAstar(true);
   Waypoint<Dim> start = wp_from<Dim>(a->start, a->control);
   const Waypoint<Dim> goal = wp_from<Dim>(a->goal, a->control);

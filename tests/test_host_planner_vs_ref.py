@@ -68,3 +68,31 @@ def test_potential_field_generator_vs_updatePotentialMap():
                          goal=dict(pos=(0, 0, 0)))
         ref = pb.reference_potential_map(a, rad, g.size)
         np.testing.assert_array_equal(S.potential_from_map(g, dims, res, rad), ref)
+
+
+def test_time_optimal_heuristic_with_dynamics():
+    """setHeurIgnoreDynamics(false): cal_heur's closed-form ACC branch (env_base.h:169-188, quartic of
+    math.h:68-113) steers A* differently from the Linf default; closed sets, costs and trajectories must
+    still match the reference exactly (same libm on both sides)."""
+    c = fixtures.corridor()
+    base = None
+    for eps in (1.0, 2.0):
+        a = pb.make_args(2, ACC, c["grid"], c["dim"], c["origin"], c["res"], fixtures.U_2d(), start=dict(pos=c["start"]),
+                         goal=dict(pos=c["goal"]), v_max=1.0, a_max=1.0, eps=eps, heur_ignore_dynamics=False)
+        ref = pb.plan_reference(a)
+        assert ref["valid"] == 1
+        same(pb.plan_oracle(a), ref)
+        if base is None:
+            a_def = pb.make_args(2, ACC, c["grid"], c["dim"], c["origin"], c["res"], fixtures.U_2d(),
+                                 start=dict(pos=c["start"]), goal=dict(pos=c["goal"]), v_max=1.0, a_max=1.0)
+            base = pb.plan_reference(a_def)
+            assert ref["n_closed"] != base["n_closed"]          # the heuristic really changed the search
+    from motion_primitive_library_b200 import scenarios as S
+
+    sc = S.scaled(S.cfg_headline(), 64)
+    nodes = sc.frontier(16, seed=4, max_steps=0)
+    for q in (0, 4):
+        a = pb.make_args(3, sc.control, sc.grid(), sc.dim_cells, sc.origin, sc.res, sc.U, start=dict(pos=nodes["pos"][q]),
+                         goal=dict(pos=nodes["pos"][q + 1]), v_max=sc.v_max, a_max=sc.a_max, max_num=1500,
+                         heur_ignore_dynamics=False)
+        same(pb.plan_oracle(a), pb.plan_reference(a))
