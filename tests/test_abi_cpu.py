@@ -47,6 +47,26 @@ def test_no_cpu_fallback_without_gpu():
         env_map(mu)
 
 
+def test_host_planner_entry_points_refuse_without_gpu():
+    """libmpl_host.so (C++ host planner with the GPU env): every entry point loads, resolves libmplx and
+    fails loudly — never plans on the CPU — when no device is present."""
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present; the refusal path is only reachable on a CPU-only host")
+    import fixtures
+    from motion_primitive_library_b200 import planner as P
+
+    c = fixtures.corridor()
+    a = P.make_args(2, 0x03, c["grid"], c["dim"], c["origin"], c["res"], fixtures.U_2d(), start=dict(pos=c["start"]),
+                    goal=dict(pos=c["goal"]), v_max=1.0, a_max=1.0)
+    q = np.zeros(2, dtype=P.WAYPOINT_DTYPE)
+    for call in (lambda: P.plan(a), lambda: P.lpa_session(a, [("plan",)]), lambda: P.iterative_plan(a, (0.5, 0.5), 2),
+                 lambda: P.plan_trajectory(a, 5), lambda: P.plan_batch(a, q, q)):
+        with pytest.raises(RuntimeError, match="no CUDA device|CPU fallback"):
+            call()
+
+
 def test_bad_arguments_rejected_before_cuda():
     from motion_primitive_library_b200 import abi
 
