@@ -44,7 +44,8 @@ def parse():
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--kernel", type=int, default=0, help="0 = auto, 1 = literal loop, 2 = register, 3 = flat, 4 = dealing")
+    ap.add_argument("--kernel", type=int, default=0,
+                    help="0 = auto, 1 = literal loop, 2 = register, 3 = flat, 4 = dealing, 5 = fixed-point")
     return ap.parse_args()
 
 
@@ -200,18 +201,26 @@ def host_threads():
     return effective_cpus()
 
 
+def config_dict(sc, n, world):
+    """The `config` object of the JSON line — identical for both arms (same workload, same step)."""
+    nU = sc.nU
+    slots = n * nU
+    return {"workload": sc.name, "map": "x".join(str(d) for d in sc.dim_cells) + f" @{sc.res} m int8",
+            "control": f"0x{sc.control:02x}", "primitives_per_node": nU, "nodes_per_step_per_gpu": n,
+            "frontier": "reachable lattice states (random free cell centres + <=6 random valid controls), seed 7+rank",
+            "parallelism": f"replicas x{world}, frontier sharded",
+            "l2": f"per-step working set {(n * 112 + slots * 132 + int(np.prod(sc.dim_cells))) / 1e6:.0f} MB "
+                  f"(frontier + successor records + map) exceeds the 126 MB L2"}
+
+
 def run_reference(args, sc, rank, world):
     if rank != 0:
         return
     threads = host_threads()
     arm = CpuArm(sc)
-    nodes = sc.frontier(max(4096, 64 * threads), seed=7)
-    # size a step at ~1.5 s of all-core CPU work
-    t = arm.timed(nodes[: 32 * threads], threads)
-    per_step = int(max(32 * threads, min(1 << 20, 1.5 * 32 * threads / max(t["seconds"], 1e-9))))
-    if per_step > len(nodes):
-        nodes = sc.frontier(per_step, seed=7)
-    batch = nodes[:per_step]
+    # the same step as the GPU arm: args.nodes frontier nodes of the same generator and seed (rank 0's slice)
+    per_step = args.nodes
+    batch = sc.frontier(per_step, seed=7)
     for _ in range(args.warmup):
         arm.timed(batch, threads)
     dt = 0.0
@@ -222,7 +231,7 @@ def run_reference(args, sc, rank, world):
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": sc.name, "nodes_per_step": per_step, "primitives_per_node": sc.nU},
+        "config": config_dict(sc, per_step, max(1, args.gpus)),
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": arm.kind,
                          "sample": f"{per_step} frontier nodes/step x {args.steps} steps; {arm.describe(threads)}"},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -230,12 +239,32 @@ def run_reference(args, sc, rank, world):
     print(json.dumps(line), flush=True)
 
 
+def parity_spot_check(env, sc, nodes):
+    """Expand `nodes` through the C ABI (the kernel the timed region uses) and compare with the CPU
+    checker: the reference itself (oracle/_ref) when present, else the restatement.  Counts, actions,
+    successor waypoints and keys bit-exact; costs exact for occupancy planning, 1e-6 relative otherwise.
+    Returns {"nodes": n, "successors": s, "against": ...}; raises on any mismatch."""
+    sys.path.insert(0, str(ROOT / "tests"))
+    import oracle_bindings as ob
+    from parity import assert_expansion_equal
+
+    orc_env = ob.OracleEnv.from_scenario(sc)
+    threads = host_threads()
+    against = "reference" if ob.ref_available() else "port"
+    o = ob.ref_expand(orc_env, nodes, nthreads=threads) if against == "reference" else orc_env.expand(nodes, nthreads=threads, lattice=False)
+    g = env.expand(nodes, want=("succ", "cost", "action", "key"))
+    st = assert_expansion_equal(g, o, exact_cost=sc.potential_radius is None and not (sc.control & 16))
+    return {"nodes": int(len(nodes)), "successors": st["successors"], "against": against}
+
+
 def kernel_name(which, sc, n_nodes):
     """The kernel mplx_set_kernel(which) launches for this workload (auto rule: mplx_kernels.cu launch_expand)."""
     names = {1: "mplx::expand_seq_kernel", 2: "mplx::expand_reg_kernel", 3: "mplx::expand_flat_kernel", 4: "mplx::expand_deal_kernel"}
     if which in names:
         return names[which]
-    heavy = (sc.control & 15) >= 7 or (sc.control & 16) != 0 or sc.potential() is not None
+    if (sc.control & 16) == 0 and sc.potential_radius is None and sc.nU <= 256:
+        return "mplx::expand_fx_kernel"  # occupancy planning: fixed-point sample loop (mplx_fx.cu)
+    heavy = (sc.control & 15) >= 7 or (sc.control & 16) != 0 or sc.potential_radius is not None
     big = n_nodes * sc.nU >= 2 * 256 * 148 * 4 * 8
     return "mplx::expand_deal_kernel" if heavy and big else "mplx::expand_reg_kernel"
 
@@ -298,6 +327,9 @@ def main():
     env.enable_stats(False)
     mean_samples, mean_succ = samples / n, succ_total / n
     bytes_per_exp = algorithmic_bytes(nU, mean_samples, mean_succ, False)
+
+    # ---- untimed spot check: a slice of the very frontier that is timed, against the CPU checker ----
+    parity_checked = parity_spot_check(env, sc, nodes_np[: min(n, 4096)])
 
     launches0 = env.launch_count()
     for _ in range(args.warmup):
@@ -433,11 +465,7 @@ def main():
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": sc.name, "map": "x".join(str(d) for d in sc.dim_cells) + f" @{sc.res} m int8",
-                   "control": f"0x{sc.control:02x}", "primitives_per_node": nU, "nodes_per_step_per_gpu": n,
-                   "primitives_per_sec": value * nU, "parallelism": f"replicas x{world}, frontier sharded",
-                   "l2": f"per-step working set {(n * 112 + slots * 132 + int(np.prod(sc.dim_cells))) / 1e6:.0f} MB "
-                         f"(frontier + successor records + map) exceeds the 126 MB L2"},
+        "config": config_dict(sc, n, world), "primitives_per_sec": value * nU, "parity_checked": parity_checked,
         "clocks": clocks, "e2e": e2e, "e2e_full_contract": e2e_full, "gpu_launches": int(gpu_launches),
         "roofline": roofline,
         "cpu_baseline": cpu_baseline,

@@ -40,6 +40,7 @@ static void refresh_params(mplx_ctx *c) {
   c->P.U = c->U.p;
   c->P.stats = c->stats_on ? c->stats.p : nullptr;
   c->P.occ_bits = c->has_map ? c->occ.p : nullptr;
+  c->P.occ2 = c->has_map ? c->occ2.p : nullptr;
   c->P.ttab = c->ttab.p;
   c->P.tcount = c->tcount.p;
   c->P.tdt = c->tdt.p;
@@ -82,7 +83,7 @@ int mplx_create(int dim, int device, mplx_ctx **out) {
   c->device = device;
   if (const char *k = getenv("MPLX_KERNEL")) {  // diagnostics: initial mplx_set_kernel value
     const int w = atoi(k);
-    if (w >= 0 && w <= 4) c->force_seq = w;
+    if (w >= 0 && w <= 5) c->force_seq = w;
   }
   memset(&c->P, 0, sizeof c->P);
   c->P.dim = dim;
@@ -106,7 +107,7 @@ int mplx_destroy(mplx_ctx *c) {
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
   c->map.release(); c->pot.release(); c->region.release(); c->U.release(); c->stats.release();
-  c->occ.release(); c->ttab.release(); c->tcount.release(); c->tdt.release();
+  c->occ.release(); c->occ2.release(); c->ttab.release(); c->tcount.release(); c->tdt.release();
   c->cb[0].release(); c->cb[1].release(); c->eb.release();
   c->d_nodes.release(); c->d_succ.release(); c->d_count.release(); c->d_action.release();
   c->d_lattice.release(); c->d_cost.release(); c->d_key.release();
@@ -132,7 +133,9 @@ int mplx_set_map(mplx_ctx *c, const int8_t *data, const int32_t *dim, const doub
   CU(cudaMemcpyAsync(c->map.p, data, nvox, cudaMemcpyHostToDevice, c->stream));
   CU(c->occ.reserve((nvox + 31) / 32));
   CU(mplx::launch_pack_bits(c->map.p, nvox, c->occ.p, true, c->stream));
-  c->launches++;
+  CU(c->occ2.reserve((nvox + 31) / 32));
+  CU(mplx::launch_pack_occ2(c->occ.p, nvox, c->dim, dim[0], dim[1], c->occ2.p, c->stream));
+  c->launches += 2;
   CU(cudaStreamSynchronize(c->stream));
   c->nvox = nvox;
   for (int k = 0; k < 3; k++) {
@@ -344,8 +347,8 @@ int mplx_expand(mplx_ctx *c, const mplx_waypoint *nodes, int n_nodes, const mplx
 
 int mplx_set_kernel(mplx_ctx *c, int which) {
   if (!c) return fail(MPLX_ERR_ARG, "null ctx");
-  if (which < 0 || which > 4)
-    return fail(MPLX_ERR_ARG, "which must be 0 (auto), 1 (sequential), 2 (register), 3 (flat) or 4 (dealing)");
+  if (which < 0 || which > 5)
+    return fail(MPLX_ERR_ARG, "which must be 0 (auto), 1 (sequential), 2 (register), 3 (flat), 4 (dealing) or 5 (fixed-point)");
   c->force_seq = which;
   return MPLX_OK;
 }

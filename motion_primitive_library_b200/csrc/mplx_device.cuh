@@ -35,6 +35,8 @@ struct EnvParams {
   const int *tcount;           // [kNMax+1]
   const double *tdt;           // [kNMax+1]  T/n (env_map.h:98)
   int maxn;                    // largest n the flat sample phase accepts (<= kNMax)
+  // {occupancy word, candidate-summary word} per 32 voxels for the fixed-point kernel (mplx_fx.cu)
+  const uint2 *occ2;
 };
 
 constexpr int kNMax = 128;          // rows of the sample-time table

@@ -183,7 +183,7 @@ __device__ __forceinline__ void phase_ab(const EnvParams &P, const mplx_waypoint
                                          int n_nodes, int item, int items, int nU, int node0,
                                          uint32_t *vbits, int words, const OutPtrs &o,
                                          PrimState<DIM, ORD, YAW> &pr, bool &emit, bool &same,
-                                         double &max_v, size_t &slot) {
+                                         double &max_v, size_t &slot, const uint64_t *s_hcurr = nullptr) {
   const int nl = item / nU;
   const int ci = item - nl * nU;
   const int ni = node0 + nl;
@@ -247,14 +247,17 @@ __device__ __forceinline__ void phase_ab(const EnvParams &P, const mplx_waypoint
     }
     if (ok) {
       // tn == curr  <=>  hash_value(tn) == hash_value(curr)  (waypoint.h:133-135, 93-125)
-      uint64_t hcurr = 0;
+      // hash_value(curr): per thread, or once per node by the caller (s_hcurr[node in CTA])
+      uint64_t hcurr = s_hcurr ? s_hcurr[nl] : 0;
       int nl_ = 0;
 #pragma unroll
       for (int k = 0; k < DIM; k++) {
-        hash_combine(hcurr, lattice_id(cp->pos[k], 0.01, 100.0));
-        if (ORD >= 2) hash_combine(hcurr, lattice_id(cp->vel[k], 0.1, 10.0));
-        if (ORD >= 3) hash_combine(hcurr, lattice_id(cp->acc[k], 0.1, 10.0));
-        if (ORD >= 4) hash_combine(hcurr, lattice_id(cp->jrk[k], 0.1, 10.0));
+        if (!s_hcurr) {
+          hash_combine(hcurr, lattice_id(cp->pos[k], 0.01, 100.0));
+          if (ORD >= 2) hash_combine(hcurr, lattice_id(cp->vel[k], 0.1, 10.0));
+          if (ORD >= 3) hash_combine(hcurr, lattice_id(cp->acc[k], 0.1, 10.0));
+          if (ORD >= 4) hash_combine(hcurr, lattice_id(cp->jrk[k], 0.1, 10.0));
+        }
         int id = lattice_id(tn.pos[k], 0.01, 100.0);
         hash_combine(key, id);
         if (LAT) lat[nl_++] = id;
@@ -263,7 +266,7 @@ __device__ __forceinline__ void phase_ab(const EnvParams &P, const mplx_waypoint
         if (ORD >= 4) { id = lattice_id(tn.jrk[k], 0.1, 10.0); hash_combine(key, id); if (LAT) lat[nl_++] = id; }
       }
       if (YAW) {
-        hash_combine(hcurr, lattice_id(cp->yaw, 0.1, 10.0));
+        if (!s_hcurr) hash_combine(hcurr, lattice_id(cp->yaw, 0.1, 10.0));
         const int id = lattice_id(tn.yaw, 0.1, 10.0);
         hash_combine(key, id);
         if (LAT) lat[nl_++] = id;

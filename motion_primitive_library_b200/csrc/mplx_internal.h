@@ -120,6 +120,7 @@ struct mplx_ctx {
   // static data in HBM
   DevBuf<int8_t> map, pot;
   DevBuf<uint32_t> region, occ;
+  DevBuf<uint2> occ2;  // {occupancy, candidate summary} words of the fixed-point kernel
   DevBuf<double> U, ttab, tdt;
   DevBuf<int> tcount;
   int force_seq = 0;

@@ -350,6 +350,9 @@ cudaError_t launch_expand(const EnvParams &P, const mplx_waypoint *d_nodes, int 
   // dynamic limits reject many primitives (JRK/SNP) and sample loops with per-sample work beyond the
   // voxel bit (potential field, yaw) — once the batch is large enough for multi-round CTAs; the register kernel otherwise
   // (measured: 512^3 JRK-125 +21 %, ACCxYAW-81 with potential +35 %, plain ACC-27 -3 %).
+  // occupancy planning (no potential field, no yaw): the fixed-point kernel (mplx_fx.cu)
+  if ((force_seq == 0 || force_seq == 5) && fx_supported(P)) return launch_expand_fx(P, d_nodes, n_nodes, o, st);
+  if (force_seq == 5) force_seq = 0;  // not applicable to this plan: the auto rule below
   const bool heavy = (P.control & 15) >= MPLX_JRK || (P.control & 16) != 0 || P.pot != nullptr;
   // (at one round per CTA the dealing kernel only adds overhead: 4096-node JRK launches of the lock-step
   // multi-query driver run 0.37 ms faster on the register kernel, so auto needs >= 2 rounds' worth of CTAs)

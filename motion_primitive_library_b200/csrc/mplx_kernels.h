@@ -19,6 +19,12 @@ cudaError_t launch_expand(const EnvParams &P, const mplx_waypoint *d_nodes, int 
 constexpr int kDealMaxRounds = 8;
 cudaError_t launch_expand_deal(const EnvParams &P, const mplx_waypoint *d_nodes, int n_nodes,
                                const mplx_succ_out &o, cudaStream_t st, int rounds);
+// The fixed-point kernel (mplx_fx.cu): occupancy planning only (fx_supported), |U| <= 256.
+bool fx_supported(const EnvParams &P);
+cudaError_t launch_expand_fx(const EnvParams &P, const mplx_waypoint *d_nodes, int n_nodes, const mplx_succ_out &o,
+                             cudaStream_t st);
+// occupancy bits -> {occupancy word, candidate-summary word} per 32 voxels (mplx_fx.cu)
+cudaError_t launch_pack_occ2(const uint32_t *d_occ, size_t nvox, int dim, int nx, int ny, uint2 *d_out, cudaStream_t st);
 // bytes -> 1 bit/voxel: occ ? (byte == 100) : (byte != 0)
 cudaError_t launch_pack_bits(const int8_t *d_bytes, size_t nvox, uint32_t *d_bits, bool occ, cudaStream_t st);
 // sample-time table of `for (t = 0; t < T; t += T/n)` for n = 0..kNMax

@@ -14,4 +14,4 @@ def test_div_round_ceil_identities(tmp_path):
     out = subprocess.run([str(exe), "1000000", "40000"], capture_output=True, text=True, timeout=600)
     print(out.stdout)
     assert out.returncode == 0, out.stdout + out.stderr
-    assert "bad_div 0 bad_round 0 bad_ceil 0 bad_cell 0" in out.stdout
+    assert "bad_div 0 bad_round 0 bad_ceil 0 bad_cell 0 bad_fx 0" in out.stdout

@@ -40,8 +40,9 @@ def gpu_env(sc, region=None):
     return e
 
 
-def run_parity(sc, n, region=None, exact_cost=False, seed=7, kernels=(1, 2, 3, 4)):
-    """All kernels (1 = literal sequential loop, 2 = register kernel, 3 = flat sample-parallel, 4 = dealing) vs the oracle."""
+def run_parity(sc, n, region=None, exact_cost=False, seed=7, kernels=(1, 2, 3, 4, 5, 0)):
+    """All kernels (1 = literal sequential loop, 2 = register kernel, 3 = flat sample-parallel, 4 = dealing,
+    5 = fixed-point sample loop where the plan allows it, 0 = what the auto rule picks) vs the oracle."""
     nodes = sc.frontier(n, seed=seed)
     orc = ob.OracleEnv.from_scenario(sc, region=region).expand(nodes, nthreads=8)
     env = gpu_env(sc, region)
@@ -175,7 +176,7 @@ def test_2d_vel_and_3d_snp_and_jrkyaw():
         nodes["t"] = rng.integers(0, 5, n) * 1.0
         orc = ob.OracleEnv.from_scenario(sc).expand(nodes, nthreads=8)
         env = gpu_env(sc)
-        for which in (1, 2, 3, 4):
+        for which in (1, 2, 3, 4, 5):
             env.set_kernel(which)
             g = env.expand(nodes, want=WANT)
             st = assert_expansion_equal(g, orc, exact_cost=(control & 16) == 0)
@@ -190,9 +191,11 @@ def test_empty_and_ragged_batches_and_pinned_buffers():
     orc_env = ob.OracleEnv.from_scenario(sc)
     r = e.expand(np.zeros(0, dtype=ob.WAYPOINT_DTYPE))
     assert r.count.size == 0
-    for n in (1, 2, 9, 10, 31, 257):  # not multiples of the nodes-per-CTA (9 for |U|=27)
-        nodes = sc.frontier(n, seed=n)
-        assert_expansion_equal(e.expand(nodes, want=WANT), orc_env.expand(nodes), exact_cost=True)
+    for which in (2, 0):
+        e.set_kernel(which)
+        for n in (1, 2, 9, 10, 31, 257):  # not multiples of the nodes-per-CTA (9 for |U|=27)
+            nodes = sc.frontier(n, seed=n)
+            assert_expansion_equal(e.expand(nodes, want=WANT), orc_env.expand(nodes), exact_cost=True)
     nodes = sc.frontier(3000, seed=1)
     assert_expansion_equal(e.expand(nodes, want=WANT, pinned=True), orc_env.expand(nodes, nthreads=8), exact_cost=True)
     # single-node get_succ (the reference signature)

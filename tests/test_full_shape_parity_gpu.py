@@ -1,0 +1,80 @@
+"""GPU parity at the NAMED shapes of BASELINE.json (not down-scaled): 512^3 @0.1 m (headline ACC-27,
+cfg3 JRK-125, cfg4 ACCxYAW-81 with the potential field) and 256^3 @0.25 m (cfg2), a few thousand
+frontier nodes each, checked against the REFERENCE ITSELF (oracle/_ref/libmplref.so = the unmodified
+reference headers, shipped to the GPU box as a built artefact) when present, and against the
+restatement (which also supplies the lattice ints).  Index arithmetic with mdim = 512, indices up to
+2^27, the 16 MiB bitmap and the 128 MiB potential grid are exercised here.
+
+Bar as everywhere: counts, actions, successor waypoints, keys bit-exact; costs exact for occupancy
+planning, rtol 1e-6 with identical +inf pattern when potential / yaw terms are summed.
+"""
+import numpy as np
+import pytest
+
+import oracle_bindings as ob
+from parity import assert_expansion_equal
+from test_expand_parity_gpu import WANT, gpu_env
+
+pytestmark = pytest.mark.gpu
+
+
+def _check(sc, nodes, env, orc_env, exact_cost, kernels):
+    restated = orc_env.expand(nodes, nthreads=16)
+    refs = [("restatement", restated)]
+    if ob.ref_available():
+        r = ob.ref_expand(orc_env, nodes, nthreads=16)
+        # the restatement against the reference on this very input (closes GPU = oracle = reference here)
+        np.testing.assert_array_equal(r["count"], restated["count"])
+        refs.append(("reference", r))
+    st = None
+    for which in kernels:
+        env.set_kernel(which)
+        g = env.expand(nodes, want=WANT)
+        for name, o in refs:
+            st = assert_expansion_equal(g, o, exact_cost=exact_cost)
+    assert st["successors"] > len(nodes)
+    return st
+
+
+def test_headline_512c_acc27_full_shape():
+    from motion_primitive_library_b200 import scenarios as S
+
+    sc = S.cfg_headline()
+    assert sc.dim_cells == (512, 512, 512)
+    nodes = sc.frontier(6000, seed=7)
+    st = _check(sc, nodes, gpu_env(sc), ob.OracleEnv.from_scenario(sc), True, (2, 4, 5, 0))
+    assert st["finite"] < st["successors"]
+
+
+def test_cfg2_256c_acc27_full_shape():
+    from motion_primitive_library_b200 import scenarios as S
+
+    sc = S.cfg2()
+    assert sc.dim_cells == (256, 256, 256)
+    _check(sc, sc.frontier(6000, seed=7), gpu_env(sc), ob.OracleEnv.from_scenario(sc), True, (2, 5, 0))
+
+
+def test_cfg3_512c_jrk125_full_shape():
+    from motion_primitive_library_b200 import scenarios as S
+
+    sc = S.cfg3()
+    _check(sc, sc.frontier(1500, seed=7), gpu_env(sc), ob.OracleEnv.from_scenario(sc), True, (2, 4, 5, 0))
+
+
+def test_cfg4_512c_accyaw81_potential_full_shape():
+    """The potential field is built on the device by mplx_update_potential_map (bit-exact against the
+    reference's updatePotentialMap in tests/test_maps_gpu.py; the scipy generator of the scenario
+    needs minutes at 512^3) and handed to the oracle / the reference as their potential_map_."""
+    from motion_primitive_library_b200 import scenarios as S
+
+    sc = S.cfg4()
+    rad = sc.potential_radius
+    sc.potential_radius = None  # env without a potential: the device builds it below
+    env = gpu_env(sc)
+    env.set_potential_weight(sc.potential_weight)
+    env.set_gradient_weight(sc.gradient_weight)
+    pot = env.update_potential_map(rad).copy()
+    assert pot.size == 512 ** 3 and (pot > 0).mean() > 0.2
+    sc._pot, sc.potential_radius = pot, rad
+    orc_env = ob.OracleEnv.from_scenario(sc)
+    _check(sc, sc.frontier(1200, seed=7), env, orc_env, False, (2, 4, 0))
