@@ -263,7 +263,8 @@ def kernel_name(which, sc, n_nodes):
     if which in names:
         return names[which]
     if (sc.control & 16) == 0 and sc.potential_radius is None and sc.nU <= 256:
-        return "mplx::expand_fx_kernel"  # occupancy planning: fixed-point sample loop (mplx_fx.cu)
+        # occupancy planning: fixed-point sample loop; node-cooperative rows + flat items for large batches
+        return "mplx::expand_fxn_kernel" if n_nodes * sc.nU >= 64 * 256 and sc.v_max > 0 else "mplx::expand_fx_kernel"
     heavy = (sc.control & 15) >= 7 or (sc.control & 16) != 0 or sc.potential_radius is not None
     big = n_nodes * sc.nU >= 2 * 256 * 148 * 4 * 8
     return "mplx::expand_deal_kernel" if heavy and big else "mplx::expand_reg_kernel"

@@ -99,6 +99,10 @@ int mplx_set_map(mplx_ctx *ctx, const int8_t *data, const int32_t *dim, const do
 int mplx_set_potential(mplx_ctx *ctx, const int8_t *data, double potential_weight,
                        double gradient_weight);
 
+/* env_map::set_potential_weight / set_gradient_weight alone (env_map.h:175-178): the potential map
+ * already on the device (mplx_set_potential or mplx_update_potential_map) is kept. */
+int mplx_set_potential_weights(mplx_ctx *ctx, double potential_weight, double gradient_weight);
+
 /* env_base::set_search_region (include/mpl_planner/common/env_base.h:301-303).
  * One byte per voxel, non-zero = inside the tunnel; NULL restores search_region_.empty(). */
 int mplx_set_search_region(mplx_ctx *ctx, const uint8_t *in_region);
@@ -197,12 +201,15 @@ int mplx_edges_cells(mplx_ctx *ctx, const mplx_waypoint *parents, const int32_t 
                      int64_t *out_offset, int32_t *out_cells, int64_t capacity, int64_t *out_total,
                      int32_t *out_table_voxel, int32_t *out_table_edge);
 
-/* Kernel selection (diagnostics): 0 = auto (the dealing kernel for JRK/SNP controls, yaw controls
- * and potential-field planning once a batch fills the GPU, else the register kernel),
+/* Kernel selection (diagnostics): 0 = auto (occupancy planning without a yaw control: the fixed-point
+ * kernels, 5; otherwise the dealing kernel for JRK/SNP controls, yaw controls and potential-field
+ * planning once a batch fills the GPU, else the register kernel),
  * 1 = the sequential kernel that keeps traverse_primitive's literal per-primitive loop
  * (env_map.h:99-130), 2 = the register kernel, 3 = the flat (sample-parallel, shared-memory
- * staged) kernel, 4 = the dealing kernel (sampling pulled from a CTA-wide ticket queue).  All
- * produce identical results.  The environment variable MPLX_KERNEL sets the initial value of a new ctx. */
+ * staged) kernel, 4 = the dealing kernel (sampling pulled from a CTA-wide ticket queue), 5 = the
+ * fixed-point kernel (cells of the sample loop from one fused Horner chain per axis, exact FP64 only
+ * for samples within 2^-25 cell of a boundary next to an obstacle; occupancy planning only, else auto).
+ * All produce identical results.  The environment variable MPLX_KERNEL sets the initial value of a new ctx. */
 int mplx_set_kernel(mplx_ctx *ctx, int which);
 
 /* Synchronise the ctx stream. */

@@ -33,6 +33,7 @@ EXPORTED_SYMBOLS = (
     "mplx_last_error",
     "mplx_set_map",
     "mplx_set_potential",
+    "mplx_set_potential_weights",
     "mplx_set_search_region",
     "mplx_update_potential_map",
     "mplx_set_search_region_path",
@@ -119,6 +120,8 @@ def load() -> C.CDLL:
     lib.mplx_set_map.restype = i32
     lib.mplx_set_potential.argtypes = [vp, vp, f64, f64]
     lib.mplx_set_potential.restype = i32
+    lib.mplx_set_potential_weights.argtypes = [vp, f64, f64]
+    lib.mplx_set_potential_weights.restype = i32
     lib.mplx_set_search_region.argtypes = [vp, vp]
     lib.mplx_set_search_region.restype = i32
     lib.mplx_update_potential_map.argtypes = [vp, vp, f64, vp, vp, f64, f64, vp]

@@ -41,6 +41,10 @@ static void refresh_params(mplx_ctx *c) {
   c->P.stats = c->stats_on ? c->stats.p : nullptr;
   c->P.occ_bits = c->has_map ? c->occ.p : nullptr;
   c->P.occ2 = c->has_map ? c->occ2.p : nullptr;
+  c->P.prow = c->prow.p;
+  c->P.row_u = c->row_u.p;
+  c->P.row_axis = c->row_axis.p;
+  c->P.n_rows = c->n_rows;
   c->P.ttab = c->ttab.p;
   c->P.tcount = c->tcount.p;
   c->P.tdt = c->tdt.p;
@@ -107,8 +111,9 @@ int mplx_destroy(mplx_ctx *c) {
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
   c->map.release(); c->pot.release(); c->region.release(); c->U.release(); c->stats.release();
+  c->prow.release(); c->row_axis.release(); c->row_u.release();
   c->occ.release(); c->occ2.release(); c->ttab.release(); c->tcount.release(); c->tdt.release();
-  c->cb[0].release(); c->cb[1].release(); c->eb.release();
+  c->cb[0].release(); c->cb[1].release(); c->eb.release(); c->fxq.release();
   c->d_nodes.release(); c->d_succ.release(); c->d_count.release(); c->d_action.release();
   c->d_lattice.release(); c->d_cost.release(); c->d_key.release();
   c->h_nodes.release(); c->h_succ.release(); c->h_count.release(); c->h_action.release();
@@ -170,6 +175,13 @@ int mplx_set_potential(mplx_ctx *c, const int8_t *data, double pw, double gw) {
   return MPLX_OK;
 }
 
+int mplx_set_potential_weights(mplx_ctx *c, double pw, double gw) {
+  if (int r = mplx_bind(c)) return r;
+  c->P.pot_w = pw;
+  c->P.grad_w = gw;
+  return MPLX_OK;
+}
+
 int mplx_set_search_region(mplx_ctx *c, const uint8_t *in_region) {
   if (int r = mplx_bind(c)) return r;
   if (!c->has_map) return fail(MPLX_ERR_ARG, "mplx_set_map must be called first");
@@ -206,6 +218,38 @@ int mplx_set_params(mplx_ctx *c, int control, double T, double w, double wyaw, d
   CU(cudaStreamSynchronize(c->stream));
   CU(c->U.reserve((size_t)nU * udim));
   CU(cudaMemcpyAsync(c->U.p, U, sizeof(double) * nU * udim, cudaMemcpyHostToDevice, c->stream));
+  {
+    // per-axis value tables: distinct values (bitwise) of every position axis of U, in order of appearance
+    std::vector<unsigned char> prow((size_t)nU * 3, 0), row_axis;
+    std::vector<double> row_u;
+    bool fits = true;
+    for (int a = 0; a < c->dim && fits; a++) {
+      const size_t first = row_u.size();
+      for (int i = 0; i < nU; i++) {
+        const double v = U[(size_t)i * udim + a];
+        size_t r = first;
+        for (; r < row_u.size(); r++)
+          if (memcmp(&row_u[r], &v, sizeof v) == 0) break;
+        if (r == row_u.size()) {
+          if (row_u.size() >= 255) { fits = false; break; }
+          row_u.push_back(v);
+          row_axis.push_back((unsigned char)a);
+        }
+        prow[(size_t)i * 3 + a] = (unsigned char)r;
+      }
+    }
+    c->n_rows = 0;
+    if (fits) {
+      CU(c->prow.reserve(prow.size()));
+      CU(c->row_u.reserve(row_u.size()));
+      CU(c->row_axis.reserve(row_axis.size()));
+      CU(cudaMemcpyAsync(c->prow.p, prow.data(), prow.size(), cudaMemcpyHostToDevice, c->stream));
+      CU(cudaMemcpyAsync(c->row_u.p, row_u.data(), sizeof(double) * row_u.size(), cudaMemcpyHostToDevice, c->stream));
+      CU(cudaMemcpyAsync(c->row_axis.p, row_axis.data(), row_axis.size(), cudaMemcpyHostToDevice, c->stream));
+      CU(cudaStreamSynchronize(c->stream));  // the vectors die at the end of this block
+      c->n_rows = (int)row_u.size();
+    }
+  }
   CU(c->ttab.reserve((size_t)(mplx::kNMax + 1) * mplx::kTStride + 8));  // + padding: units read 4 times at once
   CU(c->tcount.reserve(mplx::kNMax + 1));
   CU(c->tdt.reserve(mplx::kNMax + 1));
@@ -249,8 +293,9 @@ int mplx_expand_device(mplx_ctx *c, const void *d_nodes, int n_nodes, const mplx
   if (!d_nodes) return fail(MPLX_ERR_ARG, "d_nodes is null");
   cudaStream_t st = stream ? (cudaStream_t)stream : c->stream;
   if (c->stats_on) CU(cudaMemsetAsync(c->stats.p, 0, 2 * sizeof(unsigned long long), st));
-  CU(mplx::launch_expand(c->P, (const mplx_waypoint *)d_nodes, n_nodes, *out, st, c->force_seq));
-  c->launches++;
+  CU(c->fxq.reserve((size_t)n_nodes * c->P.nU));
+  CU(mplx::launch_expand(c->P, (const mplx_waypoint *)d_nodes, n_nodes, *out, st, c->force_seq, &c->fxq.view));
+  c->launches += mplx::fxn_supported(c->P, n_nodes) && c->force_seq == 0 ? 2 : 1;
   if (c->stats_on)
     CU(cudaMemcpyAsync(c->last_stats, c->stats.p, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
   return MPLX_OK;
@@ -306,8 +351,9 @@ int mplx_expand(mplx_ctx *c, const mplx_waypoint *nodes, int n_nodes, const mplx
     d.key = out->key ? c->d_key.p : nullptr;
     d.lattice = out->lattice ? c->d_lattice.p : nullptr;
     if (c->stats_on) CU(cudaMemsetAsync(c->stats.p, 0, 2 * sizeof(unsigned long long), st));
-    CU(mplx::launch_expand(c->P, c->d_nodes.p, m, d, st, c->force_seq));
-    c->launches++;
+    CU(c->fxq.reserve((size_t)m * nU));
+    CU(mplx::launch_expand(c->P, c->d_nodes.p, m, d, st, c->force_seq, &c->fxq.view));
+    c->launches += mplx::fxn_supported(c->P, m) && c->force_seq == 0 ? 2 : 1;
     if (c->stats_on)
       CU(cudaMemcpyAsync(c->last_stats, c->stats.p, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
 #define D2H(field, T, mult, pinflag, hbuf)                                                              \

@@ -37,6 +37,12 @@ struct EnvParams {
   int maxn;                    // largest n the flat sample phase accepts (<= kNMax)
   // {occupancy word, candidate-summary word} per 32 voxels for the fixed-point kernel (mplx_fx.cu)
   const uint2 *occ2;
+  // Per-axis value tables of U for the node-cooperative kernel (mplx_fx.cu): the distinct values of
+  // U[.][a] (bitwise) of all axes listed one after the other as "rows"; U[i][a] == row_u[prow[3*i+a]].
+  const unsigned char *prow;      // [nU*3]
+  const double *row_u;            // [n_rows]
+  const unsigned char *row_axis;  // [n_rows]
+  int n_rows;                     // 0: tables not available (more than 255 rows)
 };
 
 constexpr int kNMax = 128;          // rows of the sample-time table

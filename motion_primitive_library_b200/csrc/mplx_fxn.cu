@@ -1,0 +1,488 @@
+// mplx_fxn.cu — expand_fxn_kernel: the occupancy-planning expansion for large batches, built on the
+// fixed-point cell rule of mplx_fx.cuh with two further ideas.
+//
+// 1. Node-cooperative phase A.  A primitive is Dim independent Primitive1D polynomials
+//    (primitive.h:220-256) and the control sets the reference's users build are products of a few
+//    values per axis (nested loops, test/test_planner_2d.cpp:49-53), so everything phase A computes
+//    per axis — end state, max |vel|/|acc|/|jrk|, lattice ids, the fixed-point coefficients — depends
+//    only on (node, axis, value of u on that axis): 9 distinct evaluations per node for U = {-1,0,1}^3
+//    instead of 81.  mplx_set_params lists the distinct values of every axis (bitwise) as "rows"; the
+//    CTA first fills one shared-memory row per (node, row) — split in three parts over three threads,
+//    each calling exactly the functions the per-thread phase A calls, so the same bits — while 9 more
+//    threads hash the nodes themselves (hash_value(curr), waypoint.h:93-125).  A primitive thread then
+//    only gathers its Dim rows: validity = AND of the row flags, max_v = max of the row maxima,
+//    key = hash over the row ids, tn = the row end states.
+// 2. Flat sample items.  The reference's loop has n or n+1 iterations with n = 10, 20, 31, .. from one
+//    primitive to the next, so a thread-per-primitive loop leaves ~40 % of the lanes idle.  Here every
+//    primitive that needs sampling is cut into items of UNR consecutive samples; the items of the CTA
+//    are numbered by a prefix sum and dealt round-robin to all 256 lanes.  A lane loads the
+//    coefficients of its item's rows from shared memory and the first sample time from the sample-time
+//    table (from there on the reference's own running sum t += dt), runs fx_group, and reports a
+//    certain block / the ambiguous samples into the owner's shared-memory record.  No sample is
+//    skipped and none is decided differently: the verdict of a primitive is the OR over its samples.
+// Ambiguous primitives (an uncertain sample next to an obstacle surface, ~5 %) are appended to a queue
+// in global memory and re-evaluated with the exact FP64 chain by fx_resolve_kernel afterwards.
+#include "mplx_fx.cuh"
+
+namespace mplx {
+
+template <int ORD>
+struct FxnRow {
+  double st[4];       // Primitive1D::p/v/a/j at T (primitive.h:128-145)
+  double C[ORD + 1];  // fixed-point coefficients (fx_axis)
+  double mv;          // max_vel (primitive.h:353-363)
+  double J;           // Primitive1D::J (primitive.h:92-122)
+  int id[4];          // lattice ids of pos, vel, acc, jrk (waypoint.h:96-110)
+  unsigned char f0, f1, f2, pad[5];  // flags written by part 0 / 1 / 2
+};
+// part 0: kSame (c5 == pos, env_map.h:163), kReach (range of the fixed-point bound)
+// part 1: kVel within v_max; part 2: kAcc, kJrk within a_max, j_max (primitive.h:482-496)
+constexpr unsigned char kSame = 1, kReach = 2, kVel = 1, kAcc = 1, kJrk = 2;
+
+struct FxnOwner {
+  unsigned char r[3];  // rows of the primitive (within the CTA's row array)
+  unsigned char n;     // max(5, ceil(max_v*T/res))
+  unsigned short first;  // first item
+  unsigned char count;   // iterations of the sample loop (n or n+1)
+  unsigned char pad;
+};
+
+struct FxnShared {
+  uint64_t hcurr[kThreads];
+  FxnOwner own[kThreads];
+  unsigned amlo[kThreads], amhi[kThreads];  // ambiguous samples k < 64
+  uint32_t vbits[8];
+  unsigned short wtot[8];  // items per warp
+  unsigned char blocked[kThreads], full[kThreads];
+};
+
+template <int DIM, int ORD, int UNR, int MINB, bool LAT, bool REGION>
+__global__ void __launch_bounds__(kThreads, MINB)
+expand_fxn_kernel(const __grid_constant__ EnvParams P, const mplx_waypoint *__restrict__ nodes, int n_nodes, int npb,
+                  int inv_nU, int inv_rows, int rows_bytes, FxAmbRec *__restrict__ amb_q, unsigned *__restrict__ amb_n,
+                  unsigned amb_cap, const __grid_constant__ OutPtrs o) {
+  extern __shared__ __align__(16) unsigned char fx_dyn[];
+  FxnRow<ORD> *rows = reinterpret_cast<FxnRow<ORD> *>(fx_dyn);
+  unsigned char *item_owner = fx_dyn + rows_bytes;
+  __shared__ FxnShared S;
+  const int nU = P.nU;
+  const int items = npb * nU;  // <= 256
+  const int node0 = blockIdx.x * npb;
+  const int n_rows = P.n_rows;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+
+  // ---- phase A0: rows (three parts each) and node hashes ----
+  {
+    const double T = P.T;
+    const int R = npb * n_rows;
+    const int total = 3 * R + npb;
+    for (int it = threadIdx.x; it < total; it += kThreads) {
+      if (it >= 3 * R) {
+        const int j = it - 3 * R;
+        if (node0 + j < n_nodes) S.hcurr[j] = curr_hash<DIM, ORD>(nodes + node0 + j);
+        continue;
+      }
+      const int part = it >= 2 * R ? 2 : (it >= R ? 1 : 0);
+      const int r = it - part * R;
+      const int nl = (r * inv_rows) >> 20;  // r / n_rows
+      const int rr = r - nl * n_rows;
+      if (node0 + nl >= n_nodes) continue;
+      const mplx_waypoint *cp = nodes + node0 + nl;
+      const int a = __ldg(P.row_axis + rr);
+      Axis<ORD> ax;
+      ax.build(__ldg(P.row_u + rr), cp->pos[a], cp->vel[a], cp->acc[a], cp->jrk[a]);
+      FxnRow<ORD> &Rw = rows[r];
+      if (part == 0) {
+        const double origin = a == 0 ? P.origin[0] : (a == 1 ? P.origin[1] : P.origin[2]);
+        const double pw3T = (T * T) * T, pw4T = pw3T * T;
+        const double pos = ax.template p<true>(T, pw3T, pw4T);
+        Rw.st[0] = pos;
+        Rw.id[0] = lattice_id(pos, 0.01, 100.0);
+        unsigned char f = 0;
+        if (ax.c5 == pos) f |= kSame;
+        if ((fabs(ax.c5) + fabs(origin)) * P.rinv < kFxRange) f |= kReach;
+        Rw.f0 = f;
+        Rw.J = ax.J(T);
+      } else if (part == 1) {
+        const double pw3T = (T * T) * T;
+        const double vel = ax.v(T, pw3T);
+        Rw.st[1] = vel;
+        Rw.id[1] = ORD >= 2 ? lattice_id(vel, 0.1, 10.0) : 0;
+        const double mv = ax.max_vel(T);
+        Rw.mv = mv;
+        // validate_xxx (primitive.h:482-496): a limit <= 0 passes
+        Rw.f1 = (ORD >= 2 && P.v_max > 0 && mv > P.v_max) ? 0 : kVel;
+      } else {
+        const double origin = a == 0 ? P.origin[0] : (a == 1 ? P.origin[1] : P.origin[2]);
+        fx_axis<ORD>(ax, origin, P.rinv, Rw.C);
+        const double acc = ax.a(T), jrk = ax.j(T);
+        Rw.st[2] = acc;
+        Rw.st[3] = jrk;
+        Rw.id[2] = ORD >= 3 ? lattice_id(acc, 0.1, 10.0) : 0;
+        Rw.id[3] = ORD >= 4 ? lattice_id(jrk, 0.1, 10.0) : 0;
+        unsigned char f = kAcc | kJrk;
+        if (ORD >= 3 && P.a_max > 0 && ax.max_acc(T) > P.a_max) f &= ~kAcc;
+        if (ORD >= 4 && P.j_max > 0 && ax.max_jrk(T) > P.j_max) f &= ~kJrk;
+        Rw.f2 = f;
+      }
+    }
+  }
+  __syncthreads();  // B1: rows and node hashes are in shared memory
+
+  // ---- phase A1 (thread = primitive): gather the Dim rows ----
+  const int item = threadIdx.x;
+  const int nl = (item * inv_nU) >> 20;  // item / nU
+  const int ci = item - nl * nU;
+  const int ni = node0 + nl;
+  const bool active = item < items && ni < n_nodes;
+  bool ok = false, same = true, reach = true;
+  double max_v = 0;
+  uint64_t key = 0;
+  int ra[DIM];
+#pragma unroll
+  for (int a = 0; a < DIM; a++) ra[a] = 0;
+  if (active) {
+    unsigned f0 = kSame | kReach, f1 = kVel, f2 = kAcc | kJrk;
+#pragma unroll
+    for (int a = 0; a < DIM; a++) {
+      ra[a] = nl * n_rows + __ldg(P.prow + ci * 3 + a);
+      const FxnRow<ORD> &Rw = rows[ra[a]];
+      f0 &= Rw.f0;
+      f1 &= Rw.f1;
+      f2 &= Rw.f2;
+      if (Rw.mv > max_v) max_v = Rw.mv;
+    }
+    ok = f1 == kVel && f2 == (kAcc | kJrk);
+    same = (f0 & kSame) != 0;
+    reach = (f0 & kReach) != 0;
+    if (ok) {
+#pragma unroll
+      for (int a = 0; a < DIM; a++) {
+        const FxnRow<ORD> &Rw = rows[ra[a]];
+        hash_combine(key, Rw.id[0]);
+        if (ORD >= 2) hash_combine(key, Rw.id[1]);
+        if (ORD >= 3) hash_combine(key, Rw.id[2]);
+        if (ORD >= 4) hash_combine(key, Rw.id[3]);
+      }
+    }
+  }
+  // tn == curr  <=>  hash_value(tn) == hash_value(curr)  (waypoint.h:133-135)
+  const bool emit = ok && key != S.hcurr[nl];
+
+  // sample loop of this primitive: n, its iteration count, its number of UNR-sample items
+  int n = 0, count = 0, g = 0;
+  double dt = 0.0;
+  const bool literal = emit && !same && !reach;  // outside the range of the fixed-point bound (rare)
+  bool beyond = false;                           // beyond the sample-time table (rare)
+  if (emit && !same) {
+    n = sample_count_n(P, max_v, dt);
+    beyond = n > kNMax;
+    if (!beyond && !literal) {
+      count = __ldg(P.tcount + n);
+      g = (count + UNR - 1) / UNR;
+    }
+  }
+
+  // ---- phase B: stable per-node compaction (control order); item numbering ----
+  const unsigned bal = __ballot_sync(0xffffffffu, emit);
+  int gincl = g;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const int v = __shfl_up_sync(0xffffffffu, gincl, d);
+    if (lane >= d) gincl += v;
+  }
+  if (lane == 31) S.wtot[warp] = (unsigned short)gincl;
+  if (lane == 0) S.vbits[warp] = bal;
+  S.blocked[threadIdx.x] = 0;
+  S.full[threadIdx.x] = 0;
+  S.amlo[threadIdx.x] = 0;
+  S.amhi[threadIdx.x] = 0;
+  __syncthreads();  // B2
+  size_t slot = 0;
+  int first = gincl - g, gtot = 0;
+#pragma unroll
+  for (int w = 0; w < kWarps; w++) {
+    const int tw = S.wtot[w];
+    if (w < warp) first += tw;
+    gtot += tw;
+  }
+  double intrinsic = 0.0;
+  if (active) {
+    const int s = nl * nU;  // first item of my node
+    int rank = 0;
+    for (int wd = s >> 5; wd <= (item >> 5); wd++) {
+      uint32_t m = S.vbits[wd];
+      const int lo = wd << 5;
+      if (s > lo) m &= ~0u << (s - lo);
+      if (item < lo + 32) m &= (1u << (item - lo)) - 1u;
+      rank += __popc(m);
+    }
+    if (ci == nU - 1) o.count[ni] = rank + (emit ? 1 : 0);
+    if (emit) {
+      slot = (size_t)ni * nU + rank;
+      if (o.succ) {
+        mplx_waypoint tn;
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+          if (k < DIM) {
+            const FxnRow<ORD> &Rw = rows[ra[k < DIM ? k : 0]];
+            tn.pos[k] = Rw.st[0];
+            tn.vel[k] = Rw.st[1];
+            tn.acc[k] = Rw.st[2];
+            tn.jrk[k] = Rw.st[3];
+          } else {
+            tn.pos[k] = tn.vel[k] = tn.acc[k] = tn.jrk[k] = 0.0;
+          }
+        }
+        tn.yaw = 0.0;
+        tn.t = nodes[ni].t + P.T;  // env_map.h:161
+        o.succ[slot] = tn;
+      }
+      if (o.action) o.action[slot] = ci;
+      if (o.key) o.key[slot] = key;
+      if (LAT && o.lattice) {
+        int q = 0;
+#pragma unroll
+        for (int a = 0; a < DIM; a++) {
+          const FxnRow<ORD> &Rw = rows[ra[a]];
+#pragma unroll
+          for (int f = 0; f < ORD; f++) o.lattice[slot * MPLX_LATTICE_MAX + q++] = Rw.id[f];
+        }
+        for (; q < MPLX_LATTICE_MAX; q++) o.lattice[slot * MPLX_LATTICE_MAX + q] = 0;
+      }
+      // calculate_intrinsic_cost (env_base.h:343-345): the axes' J in axis order, + w*T
+      double J = rows[ra[0]].J;
+#pragma unroll
+      for (int a = 1; a < DIM; a++) J += rows[ra[a]].J;
+      intrinsic = J + P.w * P.T;
+      if (g > 0) {
+        FxnOwner ow;
+#pragma unroll
+        for (int a = 0; a < 3; a++) ow.r[a] = (unsigned char)(a < DIM ? ra[a < DIM ? a : 0] : 0);
+        ow.n = (unsigned char)n;
+        ow.first = (unsigned short)first;
+        ow.count = (unsigned char)count;
+        ow.pad = 0;
+        S.own[threadIdx.x] = ow;
+        for (int q = 0; q < g; q++) item_owner[first + q] = (unsigned char)threadIdx.x;
+      }
+    }
+  }
+  __syncthreads();  // B3: owner records and the item table are complete
+
+  // ---- phase C: the CTA's sample items, dealt round-robin to all lanes ----
+  {
+    const unsigned *__restrict__ occ_words = reinterpret_cast<const unsigned *>(P.occ2);
+    for (int it = threadIdx.x; it < gtot; it += kThreads) {
+      const int owner = item_owner[it];
+      if (S.blocked[owner]) continue;  // an earlier item already decided: inf whatever this one says
+      const FxnOwner ow = S.own[owner];
+      const int k0 = (it - ow.first) * UNR;
+      double C[DIM][ORD + 1];
+#pragma unroll
+      for (int a = 0; a < DIM; a++) {
+        const FxnRow<ORD> &Rw = rows[ow.r[a]];
+#pragma unroll
+        for (int i = 0; i <= ORD; i++) C[a][i] = Rw.C[i];
+      }
+      // sample k0 of `for (t = 0; t < T; t += dt)` from the table, then that loop's own running sum
+      double t = __ldg(P.ttab + (int)ow.n * kTStride + k0);
+      const double dtn = __ldg(P.tdt + ow.n);
+      unsigned amb;
+      const int st = fx_group<DIM, ORD, UNR, REGION>(P, occ_words, C, dtn, (int)ow.count - k0, t, amb);
+      if (st == 2) {
+        S.blocked[owner] = 1;
+      } else if (amb) {
+        if (k0 + UNR <= 32)
+          atomicOr(&S.amlo[owner], amb << k0);
+        else if (k0 >= 32 && k0 + UNR <= 64)
+          atomicOr(&S.amhi[owner], amb << (k0 - 32));
+        else
+          S.full[owner] = 1;
+      }
+    }
+  }
+  __syncthreads();  // B4: verdicts are in the owner records
+
+  // ---- owners: cost, or hand the primitive to the exact re-evaluation ----
+  int verdict = -1;  // 0 free, 1 blocked, 2 ambiguous, 3 literal loop
+  unsigned long long amask = 0;
+  bool full = false;
+  if (emit) {
+    verdict = 0;
+    if (g > 0) {
+      if (S.blocked[threadIdx.x]) {
+        verdict = 1;
+      } else {
+        amask = ((unsigned long long)S.amhi[threadIdx.x] << 32) | S.amlo[threadIdx.x];
+        full = S.full[threadIdx.x] != 0;
+        if (amask != 0 || full) verdict = 2;
+      }
+    } else if (literal || beyond) {
+      verdict = 3;
+    }
+  }
+  // warp-aggregated append to this CTA's segment of the global queue
+  const unsigned am = __ballot_sync(0xffffffffu, verdict == 2);
+  if (am) {
+    const unsigned seg = blockIdx.x & (kFxSegments - 1);
+    const unsigned segcap = amb_cap / kFxSegments;
+    unsigned base = 0;
+    const int leader = __ffs(am) - 1;
+    if (lane == leader) base = atomicAdd(amb_n + seg, (unsigned)__popc(am));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    if (verdict == 2) {
+      const unsigned pos = base + __popc(am & ((1u << lane) - 1u));
+      if (pos < segcap) {
+        FxAmbRec rec;
+        rec.slot = (unsigned)slot;
+        rec.node = ni;
+        rec.action = (unsigned short)ci;
+        rec.n = (unsigned char)n;
+        rec.full = full ? 1 : 0;
+        rec.amask = amask;
+        amb_q[(size_t)seg * segcap + pos] = rec;
+      } else {
+        verdict = 3;  // segment full: decide here with the literal loop
+      }
+    }
+  }
+  if (verdict == 3) {
+    PrimState<DIM, ORD, false> pr;
+    const mplx_waypoint *cp = nodes + ni;
+    const double *u = P.U + (size_t)ci * P.udim;
+#pragma unroll
+    for (int k = 0; k < DIM; k++) pr.ax[k].build(__ldg(u + k), cp->pos[k], cp->vel[k], cp->acc[k], cp->jrk[k]);
+    double cf[CoefLayout<DIM, ORD, false>::NCMAX];
+    fill_coef<DIM, ORD, false>(pr, false, cf);
+    unsigned ns = 0;
+    verdict = isinf(traverse_loop<DIM, ORD, false>(P, cf, false, max_v, ns)) ? 1 : 0;
+  }
+  if ((verdict == 0 || verdict == 1) && o.cost) o.cost[slot] = verdict == 1 ? (double)INFINITY : 0.0 + intrinsic;
+}
+
+// Exact re-evaluation of the queued primitives: a thread rebuilds the exact quotients from (node,
+// action) with the code phase A uses, walks the ambiguous samples with eval_pos + sample_cell at the
+// loop's own times (sample-time table), and writes the primitive's cost.
+template <int DIM, int ORD, bool REGION>
+__global__ void __launch_bounds__(128)
+fx_resolve_kernel(const __grid_constant__ EnvParams P, const mplx_waypoint *__restrict__ nodes,
+                  const FxAmbRec *__restrict__ amb_q, const unsigned *__restrict__ amb_n, unsigned amb_cap,
+                  double *__restrict__ cost) {
+  // grid = kFxSegments * k CTAs: CTA b walks segment b % kFxSegments with its k-1 siblings
+  const unsigned seg = blockIdx.x & (kFxSegments - 1);
+  const unsigned segcap = amb_cap / kFxSegments;
+  unsigned total = amb_n[seg];
+  if (total > segcap) total = segcap;
+  const unsigned sib = blockIdx.x / kFxSegments, nsib = gridDim.x / kFxSegments;
+  for (unsigned i = sib * blockDim.x + threadIdx.x; i < total; i += nsib * blockDim.x) {
+    const FxAmbRec rec = amb_q[(size_t)seg * segcap + i];
+    const mplx_waypoint *cp = nodes + rec.node;
+    const double *u = P.U + (size_t)rec.action * P.udim;
+    PrimState<DIM, ORD, false> pr;  // Primitive(curr, U[action], dt): primitive.h:220-256
+#pragma unroll
+    for (int k = 0; k < DIM; k++) pr.ax[k].build(__ldg(u + k), cp->pos[k], cp->vel[k], cp->acc[k], cp->jrk[k]);
+    double cf[CoefLayout<DIM, ORD, false>::NCMAX];
+    fill_coef<DIM, ORD, false>(pr, false, cf);
+    const int n = rec.n;
+    const double *tt = P.ttab + (size_t)n * kTStride;
+    unsigned long long m = rec.amask;
+    const int count = __ldg(P.tcount + n);
+    const bool full = rec.full != 0;
+    bool blocked = false;
+    for (int k = 0; !blocked; k++) {
+      if (full) {
+        if (k >= count) break;
+      } else {
+        if (m == 0) break;
+        k = __ffsll((long long)m) - 1;
+        m &= m - 1;
+      }
+      double pk[DIM];
+      eval_pos<DIM, ORD>(cf, __ldg(tt + k), pk);
+      int idx;
+      blocked = !sample_cell<DIM>(P, pk, idx);
+      if (!blocked) {
+        blocked = (__ldg(P.occ_bits + (idx >> 5)) >> (idx & 31)) & 1u;
+        if (REGION) blocked = blocked || !((__ldg(P.region_bits + (idx >> 5)) >> (idx & 31)) & 1u);
+      }
+    }
+    if (cost) cost[rec.slot] = blocked ? (double)INFINITY : 0.0 + intrinsic_cost<DIM, ORD, false>(P, pr);
+  }
+}
+
+template <int DIM, int ORD>
+static cudaError_t launch_fxn_t(const EnvParams &P, const mplx_waypoint *d_nodes, int n_nodes, const mplx_succ_out &so,
+                                cudaStream_t st, FxAmbRec *amb_q, unsigned *amb_n, unsigned amb_cap) {
+  const OutPtrs o{so.count, so.succ, so.cost, so.action, so.key, so.lattice};
+  const int npb = kThreads / P.nU;
+  const int grid = (n_nodes + npb - 1) / npb;
+  const bool lat = o.lattice != nullptr;
+  const bool region = P.region_bits != nullptr;
+  const int inv_nU = ((1 << 20) + P.nU - 1) / P.nU;
+  const int inv_rows = ((1 << 20) + P.n_rows - 1) / P.n_rows;
+  constexpr int UNR = 4;
+  const int rows_bytes = (int)(((size_t)npb * P.n_rows * sizeof(FxnRow<ORD>) + 15) & ~(size_t)15);
+  const int gmax = (P.maxn + 1 + UNR - 1) / UNR;  // items of one primitive: count <= maxn + 1
+  const size_t smem = (size_t)rows_bytes + (size_t)kThreads * gmax;
+  cudaError_t e = cudaMemsetAsync(amb_n, 0, sizeof(unsigned) * kFxSegments, st);
+  if (e != cudaSuccess) return e;
+#define MPLX_LAUNCH_FXN(LAT, REGION)                                                                            \
+  do {                                                                                                          \
+    if (smem > 48 * 1024) {                                                                                     \
+      e = cudaFuncSetAttribute(expand_fxn_kernel<DIM, ORD, UNR, 4, LAT, REGION>,                                \
+                               cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                         \
+      if (e != cudaSuccess) return e;                                                                           \
+    }                                                                                                           \
+    expand_fxn_kernel<DIM, ORD, UNR, 4, LAT, REGION><<<grid, kThreads, smem, st>>>(                             \
+        P, d_nodes, n_nodes, npb, inv_nU, inv_rows, rows_bytes, amb_q, amb_n, amb_cap, o);                      \
+  } while (0)
+  if (region) { if (lat) MPLX_LAUNCH_FXN(true, true); else MPLX_LAUNCH_FXN(false, true); }
+  else { if (lat) MPLX_LAUNCH_FXN(true, false); else MPLX_LAUNCH_FXN(false, false); }
+#undef MPLX_LAUNCH_FXN
+  e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  const int rgrid = kFxSegments * 8;
+  if (region)
+    fx_resolve_kernel<DIM, ORD, true><<<rgrid, 128, 0, st>>>(P, d_nodes, amb_q, amb_n, amb_cap, o.cost);
+  else
+    fx_resolve_kernel<DIM, ORD, false><<<rgrid, 128, 0, st>>>(P, d_nodes, amb_q, amb_n, amb_cap, o.cost);
+  return cudaGetLastError();
+}
+
+// The rows must pay against Dim evaluations per control, everything must fit shared memory, and the
+// batch must be worth two launches.
+bool fxn_supported(const EnvParams &P, int n_nodes) {
+  if (!fx_supported(P) || P.n_rows <= 0 || P.nU > kThreads) return false;
+  if (P.n_rows * 2 > P.dim * P.nU) return false;
+  const int npb = kThreads / P.nU;
+  if (npb * P.n_rows > 255 || npb > kThreads) return false;  // row indices are bytes
+  if (P.maxn >= kNMax) return false;                           // item table sized from the plan's largest n
+  const size_t smem = (size_t)npb * P.n_rows * 128 + (size_t)kThreads * ((P.maxn + 1 + 3) / 4);
+  if (smem > 64 * 1024) return false;
+  return (long)n_nodes * P.nU >= 64L * kThreads;
+}
+
+cudaError_t launch_expand_fxn(const EnvParams &P, const mplx_waypoint *d_nodes, int n_nodes, const mplx_succ_out &o,
+                              cudaStream_t st, void *amb_q, unsigned *amb_n, unsigned amb_cap) {
+  if (n_nodes <= 0) return cudaSuccess;
+  FxAmbRec *q = static_cast<FxAmbRec *>(amb_q);
+#define MPLX_FXN_ORD(DIM)                                                                         \
+  switch (P.control & 15) {                                                                       \
+    case MPLX_VEL: return launch_fxn_t<DIM, 1>(P, d_nodes, n_nodes, o, st, q, amb_n, amb_cap);     \
+    case MPLX_ACC: return launch_fxn_t<DIM, 2>(P, d_nodes, n_nodes, o, st, q, amb_n, amb_cap);     \
+    case MPLX_JRK: return launch_fxn_t<DIM, 3>(P, d_nodes, n_nodes, o, st, q, amb_n, amb_cap);     \
+    case MPLX_SNP: return launch_fxn_t<DIM, 4>(P, d_nodes, n_nodes, o, st, q, amb_n, amb_cap);     \
+  }
+  if (P.dim == 2) {
+    MPLX_FXN_ORD(2)
+  } else {
+    MPLX_FXN_ORD(3)
+  }
+#undef MPLX_FXN_ORD
+  return cudaErrorInvalidValue;
+}
+
+size_t fx_amb_record_bytes() { return sizeof(FxAmbRec); }
+
+}  // namespace mplx

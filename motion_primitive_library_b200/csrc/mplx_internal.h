@@ -74,6 +74,25 @@ inline bool is_pinned(const void *p) {
   return a.type == cudaMemoryTypeHost;
 }
 
+// Global queue of ambiguous primitives of the fixed-point kernels (mplx_fxn.cu), one per stream in use.
+struct FxQueue {
+  DevBuf<unsigned char> q;
+  DevBuf<unsigned> n;
+  mplx::FxScratch view;
+  // room for a quarter of the batch's primitives (~5 % are ambiguous on the bench maps) + slack per segment
+  cudaError_t reserve(size_t n_prims) {
+    const size_t cap = ((n_prims / 4 + 64 * 4096 + 63) / 64) * 64;
+    cudaError_t e = q.reserve(cap * mplx::fx_amb_record_bytes());
+    if (e == cudaSuccess) e = n.reserve(64);
+    if (e != cudaSuccess) return e;
+    view.q = q.p;
+    view.n = n.p;
+    view.cap = (unsigned)(q.cap / mplx::fx_amb_record_bytes() / 64 * 64);
+    return cudaSuccess;
+  }
+  void release() { q.release(); n.release(); view = mplx::FxScratch(); }
+};
+
 // One set of per-chunk device buffers + its stream: two sets let chunk k+1 compute while
 // chunk k's results cross PCIe (mplx_expand_packed).
 struct ChunkBufs {
@@ -90,7 +109,9 @@ struct ChunkBufs {
   DevBuf<uint16_t> paction;
   DevBuf<uint64_t> pkey;
   PinBuf<long long> h_total;
+  FxQueue fxq;
   void release() {
+    fxq.release();
     nodes.release(); succ.release(); count.release(); action.release(); cost.release(); key.release();
     kcount.release(); offset.release(); total.release(); pstate.release(); pcost.release(); paction.release();
     pkey.release(); h_total.release();
@@ -120,7 +141,10 @@ struct mplx_ctx {
   // static data in HBM
   DevBuf<int8_t> map, pot;
   DevBuf<uint32_t> region, occ;
-  DevBuf<uint2> occ2;  // {occupancy, candidate summary} words of the fixed-point kernel
+  DevBuf<uint2> occ2;
+  DevBuf<unsigned char> prow, row_axis;  // per-axis value tables of U (EnvParams::prow ...)
+  DevBuf<double> row_u;
+  int n_rows = 0;  // {occupancy, candidate summary} words of the fixed-point kernel
   DevBuf<double> U, ttab, tdt;
   DevBuf<int> tcount;
   int force_seq = 0;
@@ -138,6 +162,7 @@ struct mplx_ctx {
   PinBuf<double> h_cost;
   PinBuf<uint64_t> h_key;
   ChunkBufs cb[2];
+  FxQueue fxq;
   EdgeBufs eb;
   int64_t launches = 0;
   unsigned long long last_stats[2] = {0, 0};

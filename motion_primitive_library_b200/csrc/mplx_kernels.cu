@@ -344,8 +344,12 @@ static cudaError_t launch_d(const EnvParams &P, const mplx_waypoint *d_nodes, in
 }
 
 cudaError_t launch_expand(const EnvParams &P, const mplx_waypoint *d_nodes, int n_nodes,
-                          const mplx_succ_out &o, cudaStream_t st, int force_seq) {
+                          const mplx_succ_out &o, cudaStream_t st, int force_seq, const FxScratch *fs) {
   if (n_nodes <= 0) return cudaSuccess;
+  // large occupancy-planning batches: node-cooperative rows + flat sample items (mplx_fxn.cu)
+  static const bool fxn_off = getenv("MPLX_FX_NOROWS") != nullptr;
+  if (force_seq == 0 && !fxn_off && fs && fs->q && fxn_supported(P, n_nodes))
+    return launch_expand_fxn(P, d_nodes, n_nodes, o, st, fs->q, fs->n, fs->cap);
   // auto (0): the dealing kernel where lanes of the register kernel idle most — controls whose
   // dynamic limits reject many primitives (JRK/SNP) and sample loops with per-sample work beyond the
   // voxel bit (potential field, yaw) — once the batch is large enough for multi-round CTAs; the register kernel otherwise

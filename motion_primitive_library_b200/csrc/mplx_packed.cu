@@ -148,7 +148,8 @@ extern "C" int mplx_expand_packed(mplx_ctx *c, const mplx_waypoint *nodes, int n
     // stream order on B.st guarantees chunk k-2's D2H copies have left these buffers
     CU(cudaMemcpyAsync(B.nodes.p, nodes + off, sizeof(mplx_waypoint) * m, cudaMemcpyHostToDevice, B.st));
     mplx_succ_out d{B.count.p, B.succ.p, B.cost.p, B.action.p, B.key.p, nullptr};
-    CU(mplx::launch_expand(c->P, B.nodes.p, m, d, B.st, c->force_seq));
+    CU(B.fxq.reserve((size_t)m * nU));
+    CU(mplx::launch_expand(c->P, B.nodes.p, m, d, B.st, c->force_seq, &B.fxq.view));
     CU(cudaMemsetAsync(B.total.p, 0, sizeof(long long), B.st));
     mplx::pack_kernel<<<(m + 7) / 8, 256, 0, B.st>>>(m, nU, dim, control, drop_inf, B.count.p, B.succ.p, B.cost.p,
                                                      B.action.p, B.key.p, B.total.p, B.kcount.p, B.offset.p,

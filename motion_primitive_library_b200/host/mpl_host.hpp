@@ -128,64 +128,6 @@ inline decimal_t normalize_angle(decimal_t angle) {
   return angle;
 }
 
-/// Closed-form real roots, include/mpl_basis/math.h:22-96 (host side: the minimum-time heuristic).
-/// quad: b t^2 + c t + d;  cubic: a t^3 + b t^2 + c t + d;  quartic: a t^4 + ... + e.
-inline std::vector<decimal_t> quad(decimal_t b, decimal_t c, decimal_t d) {
-  std::vector<decimal_t> dts;
-  const decimal_t p = c * c - 4 * b * d;
-  if (p < 0) return dts;
-  dts.push_back((-c - sqrt(p)) / (2 * b));
-  dts.push_back((-c + sqrt(p)) / (2 * b));
-  return dts;
-}
-inline std::vector<decimal_t> cubic(decimal_t a, decimal_t b, decimal_t c, decimal_t d) {
-  std::vector<decimal_t> dts;
-  const decimal_t a2 = b / a, a1 = c / a, a0 = d / a;
-  const decimal_t Q = (3 * a1 - a2 * a2) / 9;
-  const decimal_t R = (9 * a1 * a2 - 27 * a0 - 2 * a2 * a2 * a2) / 54;
-  const decimal_t D = Q * Q * Q + R * R;
-  if (D > 0) {
-    const decimal_t S = std::cbrt(R + sqrt(D)), T = std::cbrt(R - sqrt(D));
-    dts.push_back(-a2 / 3 + (S + T));
-  } else if (D == 0) {
-    const decimal_t S = std::cbrt(R);
-    dts.push_back(-a2 / 3 + S + S);
-    dts.push_back(-a2 / 3 - S);
-  } else {
-    const decimal_t theta = acos(R / sqrt(-Q * Q * Q));
-    dts.push_back(2 * sqrt(-Q) * cos(theta / 3) - a2 / 3);
-    dts.push_back(2 * sqrt(-Q) * cos((theta + 2 * M_PI) / 3) - a2 / 3);
-    dts.push_back(2 * sqrt(-Q) * cos((theta + 4 * M_PI) / 3) - a2 / 3);
-  }
-  return dts;
-}
-inline std::vector<decimal_t> quartic(decimal_t a, decimal_t b, decimal_t c, decimal_t d, decimal_t e) {
-  std::vector<decimal_t> dts;
-  const decimal_t a3 = b / a, a2 = c / a, a1 = d / a, a0 = e / a;
-  const std::vector<decimal_t> ys = cubic(1, -a2, a1 * a3 - 4 * a0, 4 * a2 * a0 - a1 * a1 - a3 * a3 * a0);
-  const decimal_t y1 = ys.front();
-  const decimal_t r = a3 * a3 / 4 - a2 + y1;
-  if (r < 0) return dts;
-  const decimal_t R = sqrt(r);
-  decimal_t D, E;
-  if (R != 0) {
-    D = sqrt(0.75 * a3 * a3 - R * R - 2 * a2 + 0.25 * (4 * a3 * a2 - 8 * a1 - a3 * a3 * a3) / R);
-    E = sqrt(0.75 * a3 * a3 - R * R - 2 * a2 - 0.25 * (4 * a3 * a2 - 8 * a1 - a3 * a3 * a3) / R);
-  } else {
-    D = sqrt(0.75 * a3 * a3 - 2 * a2 + 2 * sqrt(y1 * y1 - 4 * a0));
-    E = sqrt(0.75 * a3 * a3 - 2 * a2 - 2 * sqrt(y1 * y1 - 4 * a0));
-  }
-  if (!std::isnan(D)) {
-    dts.push_back(-a3 / 4 + R / 2 + D / 2);
-    dts.push_back(-a3 / 4 + R / 2 - D / 2);
-  }
-  if (!std::isnan(E)) {
-    dts.push_back(-a3 / 4 - R / 2 + E / 2);
-    dts.push_back(-a3 / 4 - R / 2 - E / 2);
-  }
-  return dts;
-}
-
 /// Primitive1D: include/mpl_basis/primitive.h:25-197 — the evaluators and the effort integral of one
 /// axis, with the reference's operand order (these run on the host, after planning: sampling a
 /// recovered trajectory is not on the expansion path).
@@ -409,24 +351,34 @@ class MapUtil {
     for (int i = 0; i < Dim; i++) pn(i) = std::round((pt(i) - origin_d_(i)) / res_ - 0.5);
     return pn;
   }
-  /// rayTrace: map_util.h:120-137
-  vec_E<Veci<Dim>> rayTrace(const Vecf<Dim> &pt1, const Vecf<Dim> &pt2) {
-    Vecf<Dim> diff = pt2 - pt1;
-    decimal_t k = 0.8;
-    int max_diff = (diff / res_).lpNormInf() / k;
-    decimal_t s = 1.0 / max_diff;
-    Vecf<Dim> step = diff * s;
-    vec_E<Veci<Dim>> pns;
-    Veci<Dim> prev_pn;
-    for (int i = 0; i < Dim; i++) prev_pn(i) = -1;
-    for (int n = 1; n < max_diff; n++) {
-      Vecf<Dim> pt = pt1 + step * n;
-      Veci<Dim> new_pn = floatToInt(pt);
-      if (isOutside(new_pn)) break;
-      if (new_pn != prev_pn) pns.push_back(new_pn);
-      prev_pn = new_pn;
+  /// Cells crossed by the segment pt1 -> pt2, the way MapUtil::rayTrace samples it (map_util.h:120-137):
+  /// the segment is cut into floor(Linf(diff/res)/0.8) equal steps and the interior points
+  /// pt1 + (diff/steps)*i, i = 1..steps-1, are converted with floatToInt; the walk ends at the first
+  /// point outside the map, and a cell is reported once per run of consecutive equal cells.  `visit`
+  /// returns false to stop early (is_goal stops at the first occupied cell).  The sample points must
+  /// be these exact doubles for the goal test / tunnel to agree with the reference, hence the same
+  /// three operations per point (scale, multiply by i, add).
+  template <typename Visit>
+  void walkRay(const Vecf<Dim> &pt1, const Vecf<Dim> &pt2, Visit visit) {
+    const Vecf<Dim> span = pt2 - pt1;
+    const int steps = (span / res_).lpNormInf() / 0.8;
+    const Vecf<Dim> inc = span * (1.0 / steps);
+    bool have_last = false;
+    Veci<Dim> last;
+    for (int i = 1; i < steps; i++) {
+      const Veci<Dim> cell = floatToInt(pt1 + inc * i);
+      if (isOutside(cell)) return;
+      if (!have_last || cell != last) {
+        if (!visit(cell)) return;
+      }
+      last = cell;
+      have_last = true;
     }
-    return pns;
+  }
+  vec_E<Veci<Dim>> rayTrace(const Vecf<Dim> &pt1, const Vecf<Dim> &pt2) {
+    vec_E<Veci<Dim>> cells;
+    walkRay(pt1, pt2, [&](const Veci<Dim> &c) { cells.push_back(c); return true; });
+    return cells;
   }
   void freeUnknown() { for (auto &v : map_) if (v == val_unknown) v = val_free; version_++; }
   unsigned long version() const { return version_; }
@@ -464,41 +416,26 @@ class env_base {
     if (goal_key_ == state_key) return 0;
     return cal_heur(state, goal_node_);
   }
-  /// cal_heur: env_base.h:55-211.  With heur_ignore_dynamics_ (the default) the Linf distance over
-  /// v_max; otherwise the minimum of the closed-form time-optimal cost (ACC state: a quartic in t).
-  /// The JRK branches need the degree-6 companion-matrix solver of Eigen and are not provided.
+  /// cal_heur: env_base.h:55-64, the heur_ignore_dynamics_ branch (the reference's default, :368): the Linf
+  /// distance over v_max.  The minimum-time heuristics with dynamics (env_base.h:66-211: closed-form
+  /// quartic for ACC states, Eigen's PolynomialSolver for JRK) are outside the expansion path this
+  /// library rebuilds and are not provided: set_heur_ignore_dynamics(false) is ignored.
   virtual decimal_t cal_heur(const Waypoint<Dim> &state, const Waypoint<Dim> &goal) const {
-    if (heur_ignore_dynamics_) {
-      if (v_max_ > 0) return w_ * (state.pos - goal.pos).lpNormInf() / v_max_;
-      return w_ * (state.pos - goal.pos).lpNormInf();
-    }
-    if (state.control == Control::JRK)
-      throw std::runtime_error("cal_heur with dynamics for JRK states needs a degree-6 polynomial solver (not provided)");
-    const bool acc_acc = state.control == Control::ACC && goal.control == Control::ACC;
-    const bool acc_vel = state.control == Control::ACC && goal.control == Control::VEL;
-    if (acc_acc || acc_vel) {
-      const Vecf<Dim> dp = goal.pos - state.pos;
-      const Vecf<Dim> v0 = state.vel, v1 = goal.vel;
-      const decimal_t c1 = acc_acc ? -36 * dp.dot(dp) : -9 * dp.dot(dp);
-      const decimal_t c2 = acc_acc ? 24 * (v0 + v1).dot(dp) : 12 * v0.dot(dp);
-      const decimal_t c3 = acc_acc ? -4 * (v0.dot(v0) + v0.dot(v1) + v1.dot(v1)) : -3 * v0.dot(v0);
-      const decimal_t c4 = 0, c5 = w_;
-      std::vector<decimal_t> ts = quartic(c5, c4, c3, c2, c1);
-      const decimal_t t_bar = (state.pos - goal.pos).lpNormInf() / v_max_;
-      ts.push_back(t_bar);
-      decimal_t cost = std::numeric_limits<decimal_t>::max();
-      for (auto t : ts) {
-        if (t < t_bar) continue;
-        const decimal_t c = -c1 / 3 / t / t / t - c2 / 2 / t / t - c3 / t + w_ * t;
-        if (c < cost) cost = c;
-      }
-      return cost;
-    }
-    if (state.control == Control::VEL && goal.control == Control::VEL) return (w_ + 1) * (state.pos - goal.pos).norm();
-    return w_ * (state.pos - goal.pos).norm() / v_max_;
+    if (v_max_ > 0) return w_ * (state.pos - goal.pos).lpNormInf() / v_max_;
+    return w_ * (state.pos - goal.pos).lpNormInf();
   }
   /// env_base.h:305-306
-  void set_heur_ignore_dynamics(bool ignore) { heur_ignore_dynamics_ = ignore; }
+  /// Only the default (true) is supported; false is reported and ignored (the reference's style: a
+  /// message and no exception, planner_base.h:283-287), the search keeps the admissible Linf heuristic.
+  bool set_heur_ignore_dynamics(bool ignore) {
+    if (!ignore) {
+      std::fprintf(stderr, "[mpl_host] setHeurIgnoreDynamics(false): the minimum-time heuristic with dynamics "
+                           "(env_base.h:66-211) is not provided; keeping the default Linf heuristic\n");
+      return false;
+    }
+    heur_ignore_dynamics_ = true;
+    return true;
+  }
   /// env_base.h:228-231
   void forward_action(const Waypoint<Dim> &curr, int action_id, Primitive<Dim> &pr) const {
     pr = Primitive<Dim>(curr, U_[action_id], dt_);
@@ -590,8 +527,11 @@ class env_map_host : public env_base<Dim> {
     if (goaled && this->tol_acc_ >= 0) goaled = (state.acc - this->goal_node_.acc).lpNormInf() <= this->tol_acc_;
     if (goaled && this->tol_yaw_ >= 0) goaled = std::abs(state.yaw - this->goal_node_.yaw) <= this->tol_yaw_;
     if (goaled) {
-      auto pns = map_util_->rayTrace(state.pos, this->goal_node_.pos);
-      for (const auto &it : pns) if (map_util_->isOccupied(it)) return false;
+      // env_map.h:31-35: the straight line to the goal must not cross an occupied cell
+      map_util_->walkRay(state.pos, this->goal_node_.pos, [&](const Veci<Dim> &c) {
+        if (map_util_->isOccupied(c)) goaled = false;
+        return goaled;
+      });
     }
     return goaled;
   }
@@ -805,6 +745,9 @@ class env_map_gpu : public env_map_host<Dim> {
       check(mplx_set_map(ctx_, map_util_->map().data(), dim.d, ori.d, map_util_->getRes()));
       map_version_ = map_util_->version();
       sent_version_ = 0;
+      // mplx_set_map drops the device's potential map and tunnel (their sizes are tied to the grid); the
+      // reference keeps both across MapUtil::setMap, so they are re-sent from the host copies below
+      potential_on_device_ = region_on_device_ = false;
     }
     if (sent_version_ != this->params_version_) {
       if (this->U_.empty()) throw std::runtime_error("env_map_gpu: set_u() was not called");
@@ -816,6 +759,8 @@ class env_map_gpu : public env_map_host<Dim> {
       if (!potential_on_device_)
         check(mplx_set_potential(ctx_, potential_map_.empty() ? nullptr : potential_map_.data(), potential_weight_,
                                  gradient_weight_));
+      else  // the field was built on the device: only the weights may have changed
+        check(mplx_set_potential_weights(ctx_, potential_weight_, gradient_weight_));
       if (!region_on_device_) {
         if (this->search_region_.empty()) check(mplx_set_search_region(ctx_, nullptr));
         else {
@@ -849,7 +794,7 @@ class env_map_gpu : public env_map_host<Dim> {
 
   mplx_ctx *ctx_ = nullptr;
   int control_ = Control::NONE, speculate_ = 1;
-  bool potential_on_device_ = false, region_on_device_ = false;
+  mutable bool potential_on_device_ = false, region_on_device_ = false;
   std::vector<int8_t> potential_map_;
   decimal_t potential_weight_{0.1}, gradient_weight_{0.0};
   mutable unsigned long map_version_ = ~0ul, sent_version_ = 0;

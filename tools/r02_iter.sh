@@ -1,0 +1,26 @@
+#!/bin/bash
+# one tuning iteration: parity of the expansion kernels, headline bench for a few env settings, one ncu capture.
+TAG=${1:-it}
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests/test_expand_parity_gpu.py tests/test_full_shape_parity_gpu.py -m gpu -x -q 2>&1 | tail -5
+run() { # name, env..., -- bench args
+  local name=$1; shift
+  env "$@" timeout 300 python bench.py --steps 10 --warmup 3 --no-e2e --no-cpu-baseline $BARGS 2>gpurun_out/${TAG}_${name}.err | tail -1 > gpurun_out/${TAG}_${name}.json
+  python - gpurun_out/${TAG}_${name}.json <<'P'
+import json,sys
+try:
+    d=json.loads(open(sys.argv[1]).read().strip().split("\n")[-1])
+    print(sys.argv[1], "ms", round(d.get("ms_per_step"),4), "frac", round(d["roofline"]["frac"],4), d["roofline"]["kernel"], d["config"]["workload"])
+except Exception as e:
+    print(sys.argv[1], "unreadable:", e)
+P
+}
+BARGS="" run fxn MPLX_FX_UNR=0
+BARGS="" run fx8 MPLX_FX_UNR=8 MPLX_FX_NOROWS=1
+BARGS="" run norows4 MPLX_FX_UNR=4 MPLX_FX_NOROWS=1
+BARGS="--workload cfg2" run cfg2 MPLX_FX_UNR=0
+BARGS="--workload cfg3" run cfg3 MPLX_FX_UNR=0
+BARGS="--workload cfg3 --kernel 4" run cfg3deal MPLX_FX_UNR=0
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:expand_fx --launch-skip 2 --launch-count 1 -f \
+  -o gpurun_out/prof_${TAG}_fx python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-e2e > gpurun_out/${TAG}_ncu_fx.log 2>&1
+ls -la gpurun_out/prof_${TAG}_fx.ncu-rep
