@@ -367,6 +367,7 @@ def main():
     #   e2e_full   mplx_expand: the literal get_succ contract (112 B Waypoint + cost + action + key, inf kept).
     e2e = None
     e2e_full = None
+    e2e_state = None
     if not args.no_e2e:
         from motion_primitive_library_b200.abi import PackedOut
 
@@ -391,11 +392,21 @@ def main():
         h_nodes = env._pinned_empty(n, WAYPOINT_DTYPE)
         h_nodes[:] = nodes_np
         nstate = sc.Dim * bin(sc.control & 15).count("1") + (1 if sc.control & 16 else 0)
+        # occupancy planning: the finite edge cost is a function of the action alone and the coordinates of a
+        # successor are needed only when its key is new to the search, where the host planner evaluates them
+        # itself (MPL::MultiQueryPlanner, env_map_gpu::forward_from_pod): the stream is {key, u16 action}.
+        # Potential-field / yaw planning streams the cost too.
+        keys_only = sc.potential_radius is None and not (sc.control & 16)
         pb = dict(count=env._pinned_empty(n, np.int32), offset=env._pinned_empty(n, np.int64),
-                  state=env._pinned_empty(slots * nstate, np.float64), cost=env._pinned_empty(slots, np.float64),
                   action=env._pinned_empty(slots, np.uint16), key=env._pinned_empty(slots, np.uint64))
-        out_p = PackedOut(pb["count"].ctypes.data, pb["offset"].ctypes.data, pb["state"].ctypes.data,
-                          pb["cost"].ctypes.data, pb["action"].ctypes.data, pb["key"].ctypes.data, slots, 0, 0)
+        if not keys_only:
+            pb["cost"] = env._pinned_empty(slots, np.float64)
+
+        def packed_out(b):
+            return PackedOut(b["count"].ctypes.data, b["offset"].ctypes.data, abi.ptr(b.get("state")),
+                             abi.ptr(b.get("cost")), b["action"].ctypes.data, b["key"].ctypes.data, slots, 0, 0)
+
+        out_p = packed_out(pb)
 
         def step_packed():
             abi.check(lib.mplx_expand_packed(env.handle, h_nodes.ctypes.data, n, abi.PACK_DROP_INF, C.byref(out_p)))
@@ -403,12 +414,24 @@ def main():
         secs, launches = timed_host(step_packed, e2e_steps)
         kept = int(out_p.total)
         assert int(pb["count"].sum()) == kept and 0 < kept <= succ_total  # the result is read on the host
+        rec_bytes = 8 + 2 + (0 if keys_only else 8)
         e2e = {"value": world * n * e2e_steps / secs, "unit": UNIT, "h2d_bytes_per_step": int(n * 112),
-               "d2h_bytes_per_step": int(n * 12 + kept * (8 * nstate + 8 + 2 + 8)), "steps": e2e_steps,
-               "ms_per_step": 1e3 * secs / e2e_steps, "launches": int(launches),
-               "records_per_step": kept,
+               "d2h_bytes_per_step": int(n * 12 + kept * rec_bytes), "steps": e2e_steps,
+               "ms_per_step": 1e3 * secs / e2e_steps, "launches": int(launches), "records_per_step": kept,
+               "d2h_gbs": (n * 12 + kept * rec_bytes) * e2e_steps / secs / 1e9,
                "call": "mplx_expand_packed(flags=MPLX_PACK_DROP_INF), pinned host buffers: per finite successor "
-                       f"{nstate} state doubles + cost + key + u16 action; per node count + offset"}
+                       + ("key + u16 action (cost = f(action), coordinates rebuilt by the host for new states only)"
+                          if keys_only else "cost + key + u16 action") + "; per node count + offset"}
+        # the same call with the state fields and the cost in the stream (round-1 protocol)
+        pb["state"] = env._pinned_empty(slots * nstate, np.float64)
+        if "cost" not in pb:
+            pb["cost"] = env._pinned_empty(slots, np.float64)
+        out_p = packed_out(pb)
+        secs, launches = timed_host(step_packed, max(3, e2e_steps // 2))
+        e2e_state = {"value": world * n * max(3, e2e_steps // 2) / secs, "unit": UNIT, "h2d_bytes_per_step": int(n * 112),
+                     "d2h_bytes_per_step": int(n * 12 + kept * (8 * nstate + 8 + 2 + 8)),
+                     "ms_per_step": 1e3 * secs / max(3, e2e_steps // 2), "launches": int(launches),
+                     "call": f"mplx_expand_packed with {nstate} state doubles + cost + key + u16 action per finite successor"}
         del pb
 
         h_count = env._pinned_empty(n, np.int32)
@@ -467,7 +490,7 @@ def main():
         "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
         "config": config_dict(sc, n, world), "primitives_per_sec": value * nU, "parity_checked": parity_checked,
-        "clocks": clocks, "e2e": e2e, "e2e_full_contract": e2e_full, "gpu_launches": int(gpu_launches),
+        "clocks": clocks, "e2e": e2e, "e2e_state_records": e2e_state, "e2e_full_contract": e2e_full, "gpu_launches": int(gpu_launches),
         "roofline": roofline,
         "cpu_baseline": cpu_baseline,
     }

@@ -166,6 +166,24 @@ __device__ __forceinline__ bool validate_yaw(const EnvParams &P, const PrimState
   return true;
 }
 
+// One successor Waypoint (112 bytes = 7 x 16) to global memory as seven 16-byte stores when the
+// destination allows it (cudaMalloc'ed arrays always do): half the store instructions and half the
+// partial-sector writes of fourteen 8-byte stores at a 112-byte stride between lanes.
+__device__ __forceinline__ void store_waypoint(mplx_waypoint *dst, const mplx_waypoint &w) {
+  if ((reinterpret_cast<uintptr_t>(dst) & 15u) == 0) {
+    double2 *d = reinterpret_cast<double2 *>(dst);
+    d[0] = make_double2(w.pos[0], w.pos[1]);
+    d[1] = make_double2(w.pos[2], w.vel[0]);
+    d[2] = make_double2(w.vel[1], w.vel[2]);
+    d[3] = make_double2(w.acc[0], w.acc[1]);
+    d[4] = make_double2(w.acc[2], w.jrk[0]);
+    d[5] = make_double2(w.jrk[1], w.jrk[2]);
+    d[6] = make_double2(w.yaw, w.t);
+  } else {
+    *dst = w;
+  }
+}
+
 struct OutPtrs {
   int32_t *count;
   mplx_waypoint *succ;
@@ -298,7 +316,7 @@ __device__ __forceinline__ void phase_ab(const EnvParams &P, const mplx_waypoint
     if (ci == nU - 1) o.count[ni] = rank + (emit ? 1 : 0);
     if (emit) {
       slot = (size_t)ni * nU + rank;
-      if (o.succ) o.succ[slot] = tn;
+      if (o.succ) store_waypoint(o.succ + slot, tn);
       if (o.action) o.action[slot] = ci;
       if (o.key) o.key[slot] = key;
       if (LAT && o.lattice) {

@@ -205,7 +205,7 @@ expand_fx_kernel(const __grid_constant__ EnvParams P, const mplx_waypoint *__res
     if (ci == nU - 1) o.count[ni] = rank + (emit ? 1 : 0);
     if (emit) {
       slot = (size_t)ni * nU + rank;
-      if (o.succ) o.succ[slot] = tn;
+      if (o.succ) store_waypoint(o.succ + slot, tn);
       if (o.action) o.action[slot] = ci;
       if (o.key) o.key[slot] = key;
       if (LAT && o.lattice) {

@@ -88,6 +88,101 @@ __device__ __forceinline__ int fx_group(const EnvParams &P, const unsigned *__re
   return left <= UNR ? 1 : 0;
 }
 
+// The two halves of fx_group for a software-pipelined loop: fx_issue evaluates the UNR cells starting
+// at time t and issues their word loads; fx_decide consumes the words.  A caller that issues group g+1
+// before deciding group g hides the L2 latency of the voxel words behind the next group's arithmetic.
+template <int UNR>
+struct FxWords {
+  unsigned w[UNR], rot[UNR];
+  unsigned uncm;
+};
+
+template <int DIM, int ORD, int UNR, bool REGION>
+__device__ __forceinline__ void fx_issue(const EnvParams &P, const unsigned *__restrict__ base,
+                                         const double (&C)[DIM][ORD + 1], double dt, double &t, FxWords<UNR> &G) {
+  G.uncm = 0;
+#pragma unroll
+  for (int j = 0; j < UNR; j++) {
+    int cell[DIM];
+    unsigned fr = 0xffffffffu;
+    bool inside = true;
+#pragma unroll
+    for (int a = 0; a < DIM; a++) {
+      double h = C[a][ORD];
+#pragma unroll
+      for (int i = ORD - 1; i >= 1; i--) h = __fma_rn(h, t, C[a][i]);
+      const double m = __fma_rn(h, t, C[a][0]);
+      cell[a] = __double2hiint(m) - kFxHiBase;
+      fr = min(fr, (unsigned)__double2loint(m));
+      inside = inside && ((unsigned)cell[a] < (unsigned)P.mdim[a]);
+    }
+    int idx = cell[0] + P.mdim[0] * cell[1];
+    if (DIM == 3) idx += P.mdim[0] * P.mdim[1] * cell[DIM - 1];
+    const unsigned ub = fr < kFxUnc ? 1u : 0u;
+    G.uncm += ub << j;
+    G.rot[j] = (unsigned)(idx - j);
+    G.w[j] = 0xffffffffu;
+    if (REGION) {
+      if (inside && !ub) {
+        const unsigned wi = (unsigned)idx >> 5;
+        G.w[j] = __ldg(base + 2 * wi) | ~__ldg(P.region_bits + wi);
+      }
+    } else {
+      if (inside) G.w[j] = __ldg(base + ((((unsigned)idx >> 4) & ~1u) | ub));
+    }
+    t += dt;  // the reference's running sum (env_map.h:99)
+  }
+}
+
+template <int UNR>
+__device__ __forceinline__ int fx_decide(const FxWords<UNR> &G, int left, unsigned &amb) {
+  unsigned r = 0;
+#pragma unroll
+  for (int j = 0; j < UNR; j++) r |= rotr_wrap(G.w[j], G.rot[j]) & (1u << j);
+  if (left < UNR) r &= (1u << left) - 1u;
+  amb = r & G.uncm;
+  if (r & ~G.uncm) return 2;
+  return left <= UNR ? 1 : 0;
+}
+
+// The whole sample loop of one primitive, software-pipelined two groups deep.  Returns 1 when a
+// certain sample blocks, else 0 with the ambiguous samples in amask (k < 64) / full (some k >= 64).
+template <int DIM, int ORD, int UNR, bool REGION>
+__device__ __forceinline__ int fx_traverse(const EnvParams &P, const double (&C)[DIM][ORD + 1], double dt, int count,
+                                           unsigned long long &amask, bool &full) {
+  const unsigned *__restrict__ base = reinterpret_cast<const unsigned *>(P.occ2);
+  amask = 0;
+  full = false;
+  double t = 0;
+  int left = count, k0 = 0;
+  FxWords<UNR> A, B;
+  fx_issue<DIM, ORD, UNR, REGION>(P, base, C, dt, t, A);
+  for (;;) {
+    unsigned amb;
+    int st;
+    // ---- group in A; group after it goes to B ----
+    if (left > UNR) fx_issue<DIM, ORD, UNR, REGION>(P, base, C, dt, t, B);
+    st = fx_decide<UNR>(A, left, amb);
+    if (st == 2) return 1;
+    if (amb) {
+      if (k0 + UNR <= 64) amask |= (unsigned long long)amb << k0; else full = true;
+    }
+    if (st == 1) return 0;
+    left -= UNR;
+    k0 += UNR;
+    // ---- group in B; group after it goes to A ----
+    if (left > UNR) fx_issue<DIM, ORD, UNR, REGION>(P, base, C, dt, t, A);
+    st = fx_decide<UNR>(B, left, amb);
+    if (st == 2) return 1;
+    if (amb) {
+      if (k0 + UNR <= 64) amask |= (unsigned long long)amb << k0; else full = true;
+    }
+    if (st == 1) return 0;
+    left -= UNR;
+    k0 += UNR;
+  }
+}
+
 // hash_value(curr) once per node instead of once per (node, control): waypoint.h:93-125.
 template <int DIM, int ORD>
 __device__ __forceinline__ uint64_t curr_hash(const mplx_waypoint *cp) {

@@ -12,14 +12,9 @@
 //    threads hash the nodes themselves (hash_value(curr), waypoint.h:93-125).  A primitive thread then
 //    only gathers its Dim rows: validity = AND of the row flags, max_v = max of the row maxima,
 //    key = hash over the row ids, tn = the row end states.
-// 2. Flat sample items.  The reference's loop has n or n+1 iterations with n = 10, 20, 31, .. from one
-//    primitive to the next, so a thread-per-primitive loop leaves ~40 % of the lanes idle.  Here every
-//    primitive that needs sampling is cut into items of UNR consecutive samples; the items of the CTA
-//    are numbered by a prefix sum and dealt round-robin to all 256 lanes.  A lane loads the
-//    coefficients of its item's rows from shared memory and the first sample time from the sample-time
-//    table (from there on the reference's own running sum t += dt), runs fx_group, and reports a
-//    certain block / the ambiguous samples into the owner's shared-memory record.  No sample is
-//    skipped and none is decided differently: the verdict of a primitive is the OR over its samples.
+// 2. A software-pipelined sample loop (fx_traverse, mplx_fx.cuh): the voxel words of group g+1 are
+//    requested before group g is decided, so their L2 latency — the top stall of the plain loop — is
+//    covered by the next group's arithmetic.
 // Ambiguous primitives (an uncertain sample next to an obstacle surface, ~5 %) are appended to a queue
 // in global memory and re-evaluated with the exact FP64 chain by fx_resolve_kernel afterwards.
 #include "mplx_fx.cuh"
@@ -39,21 +34,9 @@ struct FxnRow {
 // part 1: kVel within v_max; part 2: kAcc, kJrk within a_max, j_max (primitive.h:482-496)
 constexpr unsigned char kSame = 1, kReach = 2, kVel = 1, kAcc = 1, kJrk = 2;
 
-struct FxnOwner {
-  unsigned char r[3];  // rows of the primitive (within the CTA's row array)
-  unsigned char n;     // max(5, ceil(max_v*T/res))
-  unsigned short first;  // first item
-  unsigned char count;   // iterations of the sample loop (n or n+1)
-  unsigned char pad;
-};
-
 struct FxnShared {
   uint64_t hcurr[kThreads];
-  FxnOwner own[kThreads];
-  unsigned amlo[kThreads], amhi[kThreads];  // ambiguous samples k < 64
   uint32_t vbits[8];
-  unsigned short wtot[8];  // items per warp
-  unsigned char blocked[kThreads], full[kThreads];
 };
 
 template <int DIM, int ORD, int UNR, int MINB, bool LAT, bool REGION>
@@ -63,7 +46,6 @@ expand_fxn_kernel(const __grid_constant__ EnvParams P, const mplx_waypoint *__re
                   unsigned amb_cap, const __grid_constant__ OutPtrs o) {
   extern __shared__ __align__(16) unsigned char fx_dyn[];
   FxnRow<ORD> *rows = reinterpret_cast<FxnRow<ORD> *>(fx_dyn);
-  unsigned char *item_owner = fx_dyn + rows_bytes;
   __shared__ FxnShared S;
   const int nU = P.nU;
   const int items = npb * nU;  // <= 256
@@ -169,43 +151,22 @@ expand_fxn_kernel(const __grid_constant__ EnvParams P, const mplx_waypoint *__re
   // tn == curr  <=>  hash_value(tn) == hash_value(curr)  (waypoint.h:133-135)
   const bool emit = ok && key != S.hcurr[nl];
 
-  // sample loop of this primitive: n, its iteration count, its number of UNR-sample items
-  int n = 0, count = 0, g = 0;
+  // sample loop of this primitive: n and its iteration count
+  int n = 0, count = 0;
   double dt = 0.0;
   const bool literal = emit && !same && !reach;  // outside the range of the fixed-point bound (rare)
   bool beyond = false;                           // beyond the sample-time table (rare)
   if (emit && !same) {
     n = sample_count_n(P, max_v, dt);
     beyond = n > kNMax;
-    if (!beyond && !literal) {
-      count = __ldg(P.tcount + n);
-      g = (count + UNR - 1) / UNR;
-    }
+    if (!beyond && !literal) count = __ldg(P.tcount + n);
   }
 
-  // ---- phase B: stable per-node compaction (control order); item numbering ----
+  // ---- phase B: stable per-node compaction (control order) ----
   const unsigned bal = __ballot_sync(0xffffffffu, emit);
-  int gincl = g;
-#pragma unroll
-  for (int d = 1; d < 32; d <<= 1) {
-    const int v = __shfl_up_sync(0xffffffffu, gincl, d);
-    if (lane >= d) gincl += v;
-  }
-  if (lane == 31) S.wtot[warp] = (unsigned short)gincl;
   if (lane == 0) S.vbits[warp] = bal;
-  S.blocked[threadIdx.x] = 0;
-  S.full[threadIdx.x] = 0;
-  S.amlo[threadIdx.x] = 0;
-  S.amhi[threadIdx.x] = 0;
   __syncthreads();  // B2
   size_t slot = 0;
-  int first = gincl - g, gtot = 0;
-#pragma unroll
-  for (int w = 0; w < kWarps; w++) {
-    const int tw = S.wtot[w];
-    if (w < warp) first += tw;
-    gtot += tw;
-  }
   double intrinsic = 0.0;
   if (active) {
     const int s = nl * nU;  // first item of my node
@@ -236,7 +197,7 @@ expand_fxn_kernel(const __grid_constant__ EnvParams P, const mplx_waypoint *__re
         }
         tn.yaw = 0.0;
         tn.t = nodes[ni].t + P.T;  // env_map.h:161
-        o.succ[slot] = tn;
+        store_waypoint(o.succ + slot, tn);
       }
       if (o.action) o.action[slot] = ci;
       if (o.key) o.key[slot] = key;
@@ -255,69 +216,25 @@ expand_fxn_kernel(const __grid_constant__ EnvParams P, const mplx_waypoint *__re
 #pragma unroll
       for (int a = 1; a < DIM; a++) J += rows[ra[a]].J;
       intrinsic = J + P.w * P.T;
-      if (g > 0) {
-        FxnOwner ow;
-#pragma unroll
-        for (int a = 0; a < 3; a++) ow.r[a] = (unsigned char)(a < DIM ? ra[a < DIM ? a : 0] : 0);
-        ow.n = (unsigned char)n;
-        ow.first = (unsigned short)first;
-        ow.count = (unsigned char)count;
-        ow.pad = 0;
-        S.own[threadIdx.x] = ow;
-        for (int q = 0; q < g; q++) item_owner[first + q] = (unsigned char)threadIdx.x;
-      }
     }
   }
-  __syncthreads();  // B3: owner records and the item table are complete
 
-  // ---- phase C: the CTA's sample items, dealt round-robin to all lanes ----
-  {
-    const unsigned *__restrict__ occ_words = reinterpret_cast<const unsigned *>(P.occ2);
-    for (int it = threadIdx.x; it < gtot; it += kThreads) {
-      const int owner = item_owner[it];
-      if (S.blocked[owner]) continue;  // an earlier item already decided: inf whatever this one says
-      const FxnOwner ow = S.own[owner];
-      const int k0 = (it - ow.first) * UNR;
-      double C[DIM][ORD + 1];
-#pragma unroll
-      for (int a = 0; a < DIM; a++) {
-        const FxnRow<ORD> &Rw = rows[ow.r[a]];
-#pragma unroll
-        for (int i = 0; i <= ORD; i++) C[a][i] = Rw.C[i];
-      }
-      // sample k0 of `for (t = 0; t < T; t += dt)` from the table, then that loop's own running sum
-      double t = __ldg(P.ttab + (int)ow.n * kTStride + k0);
-      const double dtn = __ldg(P.tdt + ow.n);
-      unsigned amb;
-      const int st = fx_group<DIM, ORD, UNR, REGION>(P, occ_words, C, dtn, (int)ow.count - k0, t, amb);
-      if (st == 2) {
-        S.blocked[owner] = 1;
-      } else if (amb) {
-        if (k0 + UNR <= 32)
-          atomicOr(&S.amlo[owner], amb << k0);
-        else if (k0 >= 32 && k0 + UNR <= 64)
-          atomicOr(&S.amhi[owner], amb << (k0 - 32));
-        else
-          S.full[owner] = 1;
-      }
-    }
-  }
-  __syncthreads();  // B4: verdicts are in the owner records
-
-  // ---- owners: cost, or hand the primitive to the exact re-evaluation ----
+  // ---- phase C (thread = primitive): the fixed-point sample loop, two groups in flight ----
   int verdict = -1;  // 0 free, 1 blocked, 2 ambiguous, 3 literal loop
   unsigned long long amask = 0;
   bool full = false;
   if (emit) {
     verdict = 0;
-    if (g > 0) {
-      if (S.blocked[threadIdx.x]) {
-        verdict = 1;
-      } else {
-        amask = ((unsigned long long)S.amhi[threadIdx.x] << 32) | S.amlo[threadIdx.x];
-        full = S.full[threadIdx.x] != 0;
-        if (amask != 0 || full) verdict = 2;
+    if (count > 0) {
+      double C[DIM][ORD + 1];
+#pragma unroll
+      for (int a = 0; a < DIM; a++) {
+        const FxnRow<ORD> &Rw = rows[ra[a]];
+#pragma unroll
+        for (int i = 0; i <= ORD; i++) C[a][i] = Rw.C[i];
       }
+      verdict = fx_traverse<DIM, ORD, UNR, REGION>(P, C, dt, count, amask, full);
+      if (verdict == 0 && (amask != 0 || full)) verdict = 2;
     } else if (literal || beyond) {
       verdict = 3;
     }
@@ -421,24 +338,29 @@ static cudaError_t launch_fxn_t(const EnvParams &P, const mplx_waypoint *d_nodes
   const bool region = P.region_bits != nullptr;
   const int inv_nU = ((1 << 20) + P.nU - 1) / P.nU;
   const int inv_rows = ((1 << 20) + P.n_rows - 1) / P.n_rows;
-  constexpr int UNR = 4;
   const int rows_bytes = (int)(((size_t)npb * P.n_rows * sizeof(FxnRow<ORD>) + 15) & ~(size_t)15);
-  const int gmax = (P.maxn + 1 + UNR - 1) / UNR;  // items of one primitive: count <= maxn + 1
-  const size_t smem = (size_t)rows_bytes + (size_t)kThreads * gmax;
+  const size_t smem = (size_t)rows_bytes;
   cudaError_t e = cudaMemsetAsync(amb_n, 0, sizeof(unsigned) * kFxSegments, st);
   if (e != cudaSuccess) return e;
-#define MPLX_LAUNCH_FXN(LAT, REGION)                                                                            \
+  static const int unr_env = [] { const char *v = getenv("MPLX_FXN_UNR"); return v ? atoi(v) : 0; }();    // tuning
+  static const int minb_env = [] { const char *v = getenv("MPLX_FXN_MINB"); return v ? atoi(v) : 0; }();  // tuning
+#define MPLX_LAUNCH_FXN(UNR, MINB, LAT, REGION)                                                                 \
   do {                                                                                                          \
     if (smem > 48 * 1024) {                                                                                     \
-      e = cudaFuncSetAttribute(expand_fxn_kernel<DIM, ORD, UNR, 4, LAT, REGION>,                                \
+      e = cudaFuncSetAttribute(expand_fxn_kernel<DIM, ORD, UNR, MINB, LAT, REGION>,                             \
                                cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                         \
       if (e != cudaSuccess) return e;                                                                           \
     }                                                                                                           \
-    expand_fxn_kernel<DIM, ORD, UNR, 4, LAT, REGION><<<grid, kThreads, smem, st>>>(                             \
+    expand_fxn_kernel<DIM, ORD, UNR, MINB, LAT, REGION><<<grid, kThreads, smem, st>>>(                          \
         P, d_nodes, n_nodes, npb, inv_nU, inv_rows, rows_bytes, amb_q, amb_n, amb_cap, o);                      \
   } while (0)
-  if (region) { if (lat) MPLX_LAUNCH_FXN(true, true); else MPLX_LAUNCH_FXN(false, true); }
-  else { if (lat) MPLX_LAUNCH_FXN(true, false); else MPLX_LAUNCH_FXN(false, false); }
+  if (region) { if (lat) MPLX_LAUNCH_FXN(4, 4, true, true); else MPLX_LAUNCH_FXN(4, 4, false, true); }
+  else if (lat) MPLX_LAUNCH_FXN(4, 4, true, false);
+  else if (unr_env == 8 && minb_env == 5) MPLX_LAUNCH_FXN(8, 5, false, false);
+  else if (unr_env == 8) MPLX_LAUNCH_FXN(8, 4, false, false);
+  else if (minb_env == 5) MPLX_LAUNCH_FXN(4, 5, false, false);
+  else if (minb_env == 6) MPLX_LAUNCH_FXN(4, 6, false, false);
+  else MPLX_LAUNCH_FXN(4, 4, false, false);
 #undef MPLX_LAUNCH_FXN
   e = cudaGetLastError();
   if (e != cudaSuccess) return e;
@@ -457,8 +379,7 @@ bool fxn_supported(const EnvParams &P, int n_nodes) {
   if (P.n_rows * 2 > P.dim * P.nU) return false;
   const int npb = kThreads / P.nU;
   if (npb * P.n_rows > 255 || npb > kThreads) return false;  // row indices are bytes
-  if (P.maxn >= kNMax) return false;                           // item table sized from the plan's largest n
-  const size_t smem = (size_t)npb * P.n_rows * 128 + (size_t)kThreads * ((P.maxn + 1 + 3) / 4);
+  const size_t smem = (size_t)npb * P.n_rows * 128;
   if (smem > 64 * 1024) return false;
   return (long)n_nodes * P.nU >= 64L * kThreads;
 }

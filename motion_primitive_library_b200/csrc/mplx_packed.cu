@@ -105,7 +105,10 @@ extern "C" int mplx_expand_packed(mplx_ctx *c, const mplx_waypoint *nodes, int n
     ChunkBufs &B = c->cb[b];
     if (!B.st) CU(cudaStreamCreateWithFlags(&B.st, cudaStreamNonBlocking));
     if (!B.ready) CU(cudaEventCreateWithFlags(&B.ready, cudaEventDisableTiming));
-    CU(B.nodes.reserve(chunk)); CU(B.count.reserve(chunk)); CU(B.succ.reserve(slots)); CU(B.cost.reserve(slots));
+    // successor waypoints are produced only when the caller wants state fields: a keys-only stream
+    // (state == NULL: the host rebuilds coordinates of NEW states itself, graph_search.h:84-88) never
+    // writes the 112-byte records to HBM
+    CU(B.nodes.reserve(chunk)); CU(B.count.reserve(chunk)); if (out->state) CU(B.succ.reserve(slots)); CU(B.cost.reserve(slots));
     CU(B.action.reserve(slots)); CU(B.key.reserve(slots)); CU(B.kcount.reserve(chunk)); CU(B.offset.reserve(chunk));
     CU(B.total.reserve(1)); CU(B.h_total.reserve(1));
     if (out->state) CU(B.pstate.reserve(slots * nstate));
@@ -147,12 +150,12 @@ extern "C" int mplx_expand_packed(mplx_ctx *c, const mplx_waypoint *nodes, int n
     const int m = n_nodes - off < chunk ? n_nodes - off : chunk;
     // stream order on B.st guarantees chunk k-2's D2H copies have left these buffers
     CU(cudaMemcpyAsync(B.nodes.p, nodes + off, sizeof(mplx_waypoint) * m, cudaMemcpyHostToDevice, B.st));
-    mplx_succ_out d{B.count.p, B.succ.p, B.cost.p, B.action.p, B.key.p, nullptr};
+    mplx_succ_out d{B.count.p, out->state ? B.succ.p : nullptr, B.cost.p, B.action.p, B.key.p, nullptr};
     CU(B.fxq.reserve((size_t)m * nU));
     CU(mplx::launch_expand(c->P, B.nodes.p, m, d, B.st, c->force_seq, &B.fxq.view));
     CU(cudaMemsetAsync(B.total.p, 0, sizeof(long long), B.st));
-    mplx::pack_kernel<<<(m + 7) / 8, 256, 0, B.st>>>(m, nU, dim, control, drop_inf, B.count.p, B.succ.p, B.cost.p,
-                                                     B.action.p, B.key.p, B.total.p, B.kcount.p, B.offset.p,
+    mplx::pack_kernel<<<(m + 7) / 8, 256, 0, B.st>>>(m, nU, dim, control, drop_inf, B.count.p,
+                                                     out->state ? B.succ.p : nullptr, B.cost.p, B.action.p, B.key.p, B.total.p, B.kcount.p, B.offset.p,
                                                      out->state ? B.pstate.p : nullptr, out->cost ? B.pcost.p : nullptr,
                                                      out->action ? B.paction.p : nullptr, out->key ? B.pkey.p : nullptr);
     CU(cudaGetLastError());

@@ -658,18 +658,51 @@ class env_map_gpu : public env_map_host<Dim> {
   /// Packed batched expansion for lock-step drivers (mplx_expand_packed, +inf successors dropped
   /// on the device: A* skips them, graph_search.h:81).  Results stay in the env's buffers until the
   /// next call: record r of node i is r in [p_offset[i], p_offset[i] + p_count[i]).
-  void expand_packed(const std::vector<mplx_waypoint> &nodes) const {
+  ///
+  /// keys_only: per record only {key, action} cross PCIe (10 B instead of 66 B for 3-D ACC).  Possible
+  /// for occupancy planning (keys_only_possible()): the finite edge cost is calculate_intrinsic_cost,
+  /// a function of the action alone (action_cost()), and the coordinates of a successor are needed only
+  /// when its key is new to the search (graph_search.h:84-88), where forward_from_pod() evaluates them
+  /// on the host with the reference's own operand order (the same bits the device produces).
+  void expand_packed(const std::vector<mplx_waypoint> &nodes, bool keys_only = false) const {
     sync();
     const int n = (int)nodes.size(), nU = (int)this->U_.size();
     const std::size_t cap = (std::size_t)n * nU;
     const int nstate = Dim * __builtin_popcount(control_ & 15) + ((control_ & 16) ? 1 : 0);
-    p_count.reserve(n); p_offset.reserve(n); p_state.reserve(cap * nstate); p_cost.reserve(cap); p_action.reserve(cap); p_key.reserve(cap);
-    mplx_packed_out out{p_count.data(), (int64_t *)p_offset.data(), p_state.data(), p_cost.data(), p_action.data(),
-                        p_key.data(), (int64_t)cap, 0, 0};
+    p_count.reserve(n); p_offset.reserve(n); p_action.reserve(cap); p_key.reserve(cap);
+    if (!keys_only) { p_state.reserve(cap * nstate); p_cost.reserve(cap); }
+    mplx_packed_out out{p_count.data(), (int64_t *)p_offset.data(), keys_only ? nullptr : p_state.data(),
+                        keys_only ? nullptr : p_cost.data(), p_action.data(), p_key.data(), (int64_t)cap, 0, 0};
     check(mplx_expand_packed(ctx_, nodes.data(), n, MPLX_PACK_DROP_INF, &out));
     p_nstate = out.nstate;
     stats_nodes_ += n;
     stats_calls_++;
+  }
+  /// No potential field and no yaw control: traverse_primitive contributes 0 to every finite cost.
+  bool keys_only_possible() const { return potential_map_.empty() && !(control_ & 16); }
+  /// calculate_intrinsic_cost (env_base.h:343-345) of Primitive(., U[action], dt): for a primitive built
+  /// from a state and a control only the control's own term of Primitive1D::J is non-zero
+  /// (primitive.h:92-122), so the cost does not depend on the state.
+  decimal_t action_cost(int action) const {
+    if (action_cost_version_ != this->params_version_ || action_cost_.size() != this->U_.size()) {
+      action_cost_.resize(this->U_.size());
+      const Waypoint<Dim> zero(control_);
+      for (std::size_t a = 0; a < this->U_.size(); a++) {
+        const Primitive<Dim> pr(zero, this->U_[a], this->dt_);
+        action_cost_[a] = pr.J(control_ & 15) + this->w_ * this->dt_;
+      }
+      action_cost_version_ = this->params_version_;
+    }
+    return action_cost_[action];
+  }
+  /// env_map.h:156-161 on the host for one successor: tn = Primitive(curr, U[action], dt).evaluate(dt),
+  /// tn.t = curr.t + dt.
+  Waypoint<Dim> forward_from_pod(const mplx_waypoint &curr, int action) const {
+    const Waypoint<Dim> c = from_pod(curr, control_);
+    const Primitive<Dim> pr(c, this->U_[action], this->dt_);
+    Waypoint<Dim> tn = pr.evaluate(this->dt_);
+    tn.t = c.t + this->dt_;
+    return tn;
   }
   /// Rebuild the successor Waypoint of packed record r (parent `curr`): the state fields come from
   /// the record; the rest are copies, not results (include/mplx.h, mplx_packed_out): the first
@@ -715,6 +748,8 @@ class env_map_gpu : public env_map_host<Dim> {
   mutable Pinned<uint16_t> p_action;
   mutable Pinned<uint64_t> p_key;
   mutable int p_nstate = 0;
+  mutable std::vector<decimal_t> action_cost_;
+  mutable unsigned long action_cost_version_ = ~0ul;
   static mplx_waypoint pod(const Waypoint<Dim> &w) { return to_pod(w); }
   int control() const { return control_; }
 
@@ -1850,6 +1885,8 @@ class MultiQueryPlanner {
 
   /// host threads used for the per-query bookkeeping (default: all cores)
   void setHostThreads(int n) { host_threads_ = n; }
+  /// keys-only result stream for occupancy planning (default on; see env_map_gpu::expand_packed)
+  void setKeysOnly(bool on) { keys_only_ = on; }
 
   std::vector<Result> plan(const vec_E<Waypoint<Dim>> &starts, const vec_E<Waypoint<Dim>> &goals, decimal_t eps,
                            int max_expand) {
@@ -1885,7 +1922,9 @@ class MultiQueryPlanner {
       auto t0 = std::chrono::steady_clock::now();
       pool.run(who.size(), [&](std::size_t b) { batch[b] = env_map_gpu<Dim>::pod(st[who[b]]->pop()); });
       auto t1 = std::chrono::steady_clock::now();
-      gpu_->expand_packed(batch);
+      const bool keys_only = keys_only_ && gpu_->keys_only_possible();
+      if (keys_only) gpu_->action_cost(0);  // build the table before the parallel phase
+      gpu_->expand_packed(batch, keys_only);
       auto t2 = std::chrono::steady_clock::now();
       iterations_++;
       nodes_ += (long)batch.size();
@@ -1895,8 +1934,15 @@ class MultiQueryPlanner {
         const int cnt = gpu_->p_count[b];
         int act[kMaxSucc];
         for (int j = 0; j < cnt; j++) act[j] = gpu_->p_action[r0 + j];
-        st[who[b]]->consume(cnt, [&](int s) { return gpu_->packed_waypoint(r0 + s, batch[b]); },
-                            gpu_->p_cost.data() + r0, act, [&](int s) { return (std::size_t)gpu_->p_key[r0 + s]; });
+        if (keys_only) {
+          decimal_t cst[kMaxSucc];
+          for (int j = 0; j < cnt; j++) cst[j] = gpu_->action_cost(act[j]);
+          st[who[b]]->consume(cnt, [&](int s) { return gpu_->forward_from_pod(batch[b], act[s]); }, cst, act,
+                              [&](int s) { return (std::size_t)gpu_->p_key[r0 + s]; });
+        } else {
+          st[who[b]]->consume(cnt, [&](int s) { return gpu_->packed_waypoint(r0 + s, batch[b]); },
+                              gpu_->p_cost.data() + r0, act, [&](int s) { return (std::size_t)gpu_->p_key[r0 + s]; });
+        }
       });
       auto t3 = std::chrono::steady_clock::now();
       t_pop_ += std::chrono::duration<double>(t1 - t0).count();
@@ -1942,6 +1988,7 @@ class MultiQueryPlanner {
   long iterations_ = 0, nodes_ = 0;
   double t_pop_ = 0, t_dev_ = 0, t_relax_ = 0;
   int host_threads_ = 0;
+  bool keys_only_ = true;
   static constexpr int kMaxSucc = 1024;  // |U| upper bound of libmplx
 };
 }  // namespace MPL
