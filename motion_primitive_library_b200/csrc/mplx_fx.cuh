@@ -48,7 +48,7 @@ __device__ __forceinline__ int fx_group(const EnvParams &P, const unsigned *__re
 #pragma unroll
   for (int j = 0; j < UNR; j++) {
     int cell[DIM];
-    unsigned fr = 0xffffffffu;
+    unsigned lo[DIM];
     bool inside = true;
 #pragma unroll
     for (int a = 0; a < DIM; a++) {
@@ -57,9 +57,10 @@ __device__ __forceinline__ int fx_group(const EnvParams &P, const unsigned *__re
       for (int i = ORD - 1; i >= 1; i--) h = __fma_rn(h, t, C[a][i]);
       const double m = __fma_rn(h, t, C[a][0]);
       cell[a] = __double2hiint(m) - kFxHiBase;
-      fr = min(fr, (unsigned)__double2loint(m));
+      lo[a] = (unsigned)__double2loint(m);
       inside = inside && ((unsigned)cell[a] < (unsigned)P.mdim[a]);
     }
+    const unsigned fr = DIM == 3 ? min(min(lo[0], lo[1]), lo[DIM - 1]) : min(lo[0], lo[1]);
     int idx = cell[0] + P.mdim[0] * cell[1];
     if (DIM == 3) idx += P.mdim[0] * P.mdim[1] * cell[DIM - 1];
     const unsigned ub = fr < kFxUnc ? 1u : 0u;
@@ -104,7 +105,7 @@ __device__ __forceinline__ void fx_issue(const EnvParams &P, const unsigned *__r
 #pragma unroll
   for (int j = 0; j < UNR; j++) {
     int cell[DIM];
-    unsigned fr = 0xffffffffu;
+    unsigned lo[DIM];
     bool inside = true;
 #pragma unroll
     for (int a = 0; a < DIM; a++) {
@@ -113,9 +114,10 @@ __device__ __forceinline__ void fx_issue(const EnvParams &P, const unsigned *__r
       for (int i = ORD - 1; i >= 1; i--) h = __fma_rn(h, t, C[a][i]);
       const double m = __fma_rn(h, t, C[a][0]);
       cell[a] = __double2hiint(m) - kFxHiBase;
-      fr = min(fr, (unsigned)__double2loint(m));
+      lo[a] = (unsigned)__double2loint(m);
       inside = inside && ((unsigned)cell[a] < (unsigned)P.mdim[a]);
     }
+    const unsigned fr = DIM == 3 ? min(min(lo[0], lo[1]), lo[DIM - 1]) : min(lo[0], lo[1]);
     int idx = cell[0] + P.mdim[0] * cell[1];
     if (DIM == 3) idx += P.mdim[0] * P.mdim[1] * cell[DIM - 1];
     const unsigned ub = fr < kFxUnc ? 1u : 0u;

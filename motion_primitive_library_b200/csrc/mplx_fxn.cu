@@ -34,15 +34,27 @@ struct FxnRow {
 // part 1: kVel within v_max; part 2: kAcc, kJrk within a_max, j_max (primitive.h:482-496)
 constexpr unsigned char kSame = 1, kReach = 2, kVel = 1, kAcc = 1, kJrk = 2;
 
-struct FxnShared {
-  uint64_t hcurr[kThreads];
-  uint32_t vbits[8];
+
+struct FxnWork {
+  unsigned rows_n;  // the primitive's three rows (bytes 0..2) and n (byte 3)
+  unsigned slot;    // output slot of the successor
 };
 
-template <int DIM, int ORD, int UNR, int MINB, bool LAT, bool REGION>
+struct FxnShared {
+  uint64_t hcurr[kThreads];
+  FxnWork work[kThreads];      // primitives that need sampling, longest loops first
+  unsigned char owner[kThreads];  // their phase-A threads (node, control)
+  uint32_t vbits[8];
+  // stable counting sort by number of sample groups (clamped to 32): members per (warp, bin) and the
+  // first sorted position of each (warp, bin)
+  unsigned short cnt[kWarps][33], start[kWarps][33];
+};
+constexpr unsigned kNoWork = 0xffffffffu;
+
+template <int DIM, int ORD, int UNR, int MINB, bool LAT, bool REGION, bool SORT>
 __global__ void __launch_bounds__(kThreads, MINB)
 expand_fxn_kernel(const __grid_constant__ EnvParams P, const mplx_waypoint *__restrict__ nodes, int n_nodes, int npb,
-                  int inv_nU, int inv_rows, int rows_bytes, FxAmbRec *__restrict__ amb_q, unsigned *__restrict__ amb_n,
+                  int inv_nU, int inv_rows, FxAmbRec *__restrict__ amb_q, unsigned *__restrict__ amb_n,
                   unsigned amb_cap, const __grid_constant__ OutPtrs o) {
   extern __shared__ __align__(16) unsigned char fx_dyn[];
   FxnRow<ORD> *rows = reinterpret_cast<FxnRow<ORD> *>(fx_dyn);
@@ -52,6 +64,11 @@ expand_fxn_kernel(const __grid_constant__ EnvParams P, const mplx_waypoint *__re
   const int node0 = blockIdx.x * npb;
   const int n_rows = P.n_rows;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+
+  if (SORT) {
+    for (int b = threadIdx.x; b < kWarps * 33; b += kThreads) (&S.cnt[0][0])[b] = 0;
+    S.work[threadIdx.x].slot = kNoWork;
+  }
 
   // ---- phase A0: rows (three parts each) and node hashes ----
   {
@@ -161,44 +178,96 @@ expand_fxn_kernel(const __grid_constant__ EnvParams P, const mplx_waypoint *__re
     beyond = n > kNMax;
     if (!beyond && !literal) count = __ldg(P.tcount + n);
   }
+  // CTA-wide counting sort of the primitives that need sampling by their number of sample groups,
+  // longest first: the lanes of a warp then run loops of (nearly) the same length instead of idling
+  // until the warp's longest one ends.  Which lane samples a primitive does not enter any result.
+  // The sort is stable (thread order kept inside a bin), so the lanes of a warp still hold primitives
+  // of the same few nodes and their voxel words share sectors.
+  // SORT pays where many lanes would idle (JRK/SNP: half the primitives fail the dynamic limits, cfg3
+  // 2.16 -> 1.85 ms); for ACC-27 the exchange and its barrier cost more than the idle lanes.
+  const int g = (count + UNR - 1) / UNR;
+  const int gk = g > 32 ? 32 : g;
+  int bin_rank = 0;
+  if (SORT) {
+    const unsigned peers = __match_any_sync(0xffffffffu, gk);
+    bin_rank = __popc(peers & ((1u << lane) - 1u));
+    if (gk > 0 && bin_rank == 0) S.cnt[warp][gk] = (unsigned short)__popc(peers);
+  }
 
   // ---- phase B: stable per-node compaction (control order) ----
   const unsigned bal = __ballot_sync(0xffffffffu, emit);
   if (lane == 0) S.vbits[warp] = bal;
   __syncthreads();  // B2
+  if (SORT) {
+    if (warp == 0) {
+      // lane l owns bin l+1: members per warp, bins sorted descending
+      unsigned c[kWarps], tot = 0;
+#pragma unroll
+      for (int w = 0; w < kWarps; w++) {
+        c[w] = S.cnt[w][lane + 1];
+        tot += c[w];
+      }
+      unsigned above = tot;  // inclusive suffix sum over the bins >= mine
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const unsigned v = __shfl_down_sync(0xffffffffu, above, d);
+        if (lane + d < 32) above += v;
+      }
+      unsigned at = above - tot;
+#pragma unroll
+      for (int w = 0; w < kWarps; w++) {
+        S.start[w][lane + 1] = (unsigned short)at;
+        at += c[w];
+      }
+    }
+    __syncthreads();  // B2b: sorted positions are known
+  }
   size_t slot = 0;
   double intrinsic = 0.0;
   if (active) {
     const int s = nl * nU;  // first item of my node
     int rank = 0;
-    for (int wd = s >> 5; wd <= (item >> 5); wd++) {
-      uint32_t m = S.vbits[wd];
-      const int lo = wd << 5;
-      if (s > lo) m &= ~0u << (s - lo);
-      if (item < lo + 32) m &= (1u << (item - lo)) - 1u;
-      rank += __popc(m);
+    if (nU <= 32) {
+      // the node's items sit in this warp and at most the one before it
+      const unsigned below = (1u << lane) - 1u;
+      if ((s >> 5) == warp) {
+        rank = __popc(bal & below & (~0u << (s & 31)));
+      } else {
+        rank = __popc(bal & below) + __popc(S.vbits[warp - 1] >> (s & 31));
+      }
+    } else {
+      for (int wd = s >> 5; wd <= (item >> 5); wd++) {
+        uint32_t m = S.vbits[wd];
+        const int lo = wd << 5;
+        if (s > lo) m &= ~0u << (s - lo);
+        if (item < lo + 32) m &= (1u << (item - lo)) - 1u;
+        rank += __popc(m);
+      }
     }
     if (ci == nU - 1) o.count[ni] = rank + (emit ? 1 : 0);
+    if (o.succ && emit) {
+      mplx_waypoint tn;
+#pragma unroll
+      for (int k = 0; k < 3; k++) {
+        if (k < DIM) {
+          const FxnRow<ORD> &Rw = rows[ra[k < DIM ? k : 0]];
+          tn.pos[k] = Rw.st[0];
+          tn.vel[k] = Rw.st[1];
+          tn.acc[k] = Rw.st[2];
+          tn.jrk[k] = Rw.st[3];
+        } else {
+          tn.pos[k] = tn.vel[k] = tn.acc[k] = tn.jrk[k] = 0.0;
+        }
+      }
+      tn.yaw = 0.0;
+      tn.t = nodes[ni].t + P.T;  // env_map.h:161
+      // seven 16-byte stores per record.  (Staging the CTA's records in shared memory for a fully
+      // coalesced copy-out was measured: slower on every workload — the extra pass and barrier cost
+      // more than the halved sector count saves.)
+      store_waypoint(o.succ + (size_t)ni * nU + rank, tn);
+    }
     if (emit) {
       slot = (size_t)ni * nU + rank;
-      if (o.succ) {
-        mplx_waypoint tn;
-#pragma unroll
-        for (int k = 0; k < 3; k++) {
-          if (k < DIM) {
-            const FxnRow<ORD> &Rw = rows[ra[k < DIM ? k : 0]];
-            tn.pos[k] = Rw.st[0];
-            tn.vel[k] = Rw.st[1];
-            tn.acc[k] = Rw.st[2];
-            tn.jrk[k] = Rw.st[3];
-          } else {
-            tn.pos[k] = tn.vel[k] = tn.acc[k] = tn.jrk[k] = 0.0;
-          }
-        }
-        tn.yaw = 0.0;
-        tn.t = nodes[ni].t + P.T;  // env_map.h:161
-        store_waypoint(o.succ + slot, tn);
-      }
       if (o.action) o.action[slot] = ci;
       if (o.key) o.key[slot] = key;
       if (LAT && o.lattice) {
@@ -219,25 +288,67 @@ expand_fxn_kernel(const __grid_constant__ EnvParams P, const mplx_waypoint *__re
     }
   }
 
-  // ---- phase C (thread = primitive): the fixed-point sample loop, two groups in flight ----
-  int verdict = -1;  // 0 free, 1 blocked, 2 ambiguous, 3 literal loop
+  // my work record: published at its sorted position, or kept
+  FxnWork wk;
+  wk.rows_n = (unsigned)ra[0] | ((unsigned)ra[1] << 8) | ((unsigned)(DIM == 3 ? ra[DIM - 1] : 0) << 16) | ((unsigned)n << 24);
+  wk.slot = g > 0 ? (unsigned)slot : kNoWork;
+  int wowner = threadIdx.x;
+  if (SORT && g > 0) {
+    const int pos = (int)S.start[warp][gk] + bin_rank;
+    S.work[pos] = wk;
+    S.owner[pos] = (unsigned char)threadIdx.x;
+  }
+  // primitives that are not sampled: curr.pos == tn.pos (cost 0 + intrinsic, env_map.h:163-165) or the
+  // rare literal-loop cases
+  if (emit && g == 0) {
+    int v = 0;
+    if (literal || beyond) {
+      PrimState<DIM, ORD, false> pr;
+      const mplx_waypoint *cp = nodes + ni;
+      const double *u = P.U + (size_t)ci * P.udim;
+#pragma unroll
+      for (int k = 0; k < DIM; k++) pr.ax[k].build(__ldg(u + k), cp->pos[k], cp->vel[k], cp->acc[k], cp->jrk[k]);
+      double cf[CoefLayout<DIM, ORD, false>::NCMAX];
+      fill_coef<DIM, ORD, false>(pr, false, cf);
+      unsigned ns = 0;
+      v = isinf(traverse_loop<DIM, ORD, false>(P, cf, false, max_v, ns)) ? 1 : 0;
+    }
+    if (o.cost) o.cost[slot] = v == 1 ? (double)INFINITY : 0.0 + intrinsic;
+  }
+  if (SORT) {
+    __syncthreads();  // B3: the sorted work list is complete
+    wk = S.work[threadIdx.x];
+    wowner = S.owner[threadIdx.x];
+  }
+
+  // ---- phase C (thread = work item): the fixed-point sample loop, two groups in flight ----
+  int verdict = -1;  // 0 free, 1 blocked, 2 ambiguous, 3 literal loop (queue full)
   unsigned long long amask = 0;
   bool full = false;
-  if (emit) {
-    verdict = 0;
-    if (count > 0) {
-      double C[DIM][ORD + 1];
+  unsigned wslot = 0;
+  int wn = 0;
+  double wintr = 0.0;
+  if (wk.slot != kNoWork) {
+    wslot = wk.slot;
+    wn = (int)(wk.rows_n >> 24);
+    int wr[DIM];
+    wr[0] = wk.rows_n & 255u;
+    wr[1] = (wk.rows_n >> 8) & 255u;
+    if (DIM == 3) wr[DIM - 1] = (wk.rows_n >> 16) & 255u;
+    double C[DIM][ORD + 1];
 #pragma unroll
-      for (int a = 0; a < DIM; a++) {
-        const FxnRow<ORD> &Rw = rows[ra[a]];
+    for (int a = 0; a < DIM; a++) {
+      const FxnRow<ORD> &Rw = rows[wr[a]];
 #pragma unroll
-        for (int i = 0; i <= ORD; i++) C[a][i] = Rw.C[i];
-      }
-      verdict = fx_traverse<DIM, ORD, UNR, REGION>(P, C, dt, count, amask, full);
-      if (verdict == 0 && (amask != 0 || full)) verdict = 2;
-    } else if (literal || beyond) {
-      verdict = 3;
+      for (int i = 0; i <= ORD; i++) C[a][i] = Rw.C[i];
     }
+    // calculate_intrinsic_cost (env_base.h:343-345) again from the rows: the same sum as the owner's
+    double J = rows[wr[0]].J;
+#pragma unroll
+    for (int a = 1; a < DIM; a++) J += rows[wr[a]].J;
+    wintr = J + P.w * P.T;
+    verdict = fx_traverse<DIM, ORD, UNR, REGION>(P, C, __ldg(P.tdt + wn), __ldg(P.tcount + wn), amask, full);
+    if (verdict == 0 && (amask != 0 || full)) verdict = 2;
   }
   // warp-aggregated append to this CTA's segment of the global queue
   const unsigned am = __ballot_sync(0xffffffffu, verdict == 2);
@@ -252,10 +363,11 @@ expand_fxn_kernel(const __grid_constant__ EnvParams P, const mplx_waypoint *__re
       const unsigned pos = base + __popc(am & ((1u << lane) - 1u));
       if (pos < segcap) {
         FxAmbRec rec;
-        rec.slot = (unsigned)slot;
-        rec.node = ni;
-        rec.action = (unsigned short)ci;
-        rec.n = (unsigned char)n;
+        const int onl = (wowner * inv_nU) >> 20;
+        rec.slot = wslot;
+        rec.node = node0 + onl;
+        rec.action = (unsigned short)(wowner - onl * nU);
+        rec.n = (unsigned char)wn;
         rec.full = full ? 1 : 0;
         rec.amask = amask;
         amb_q[(size_t)seg * segcap + pos] = rec;
@@ -265,17 +377,23 @@ expand_fxn_kernel(const __grid_constant__ EnvParams P, const mplx_waypoint *__re
     }
   }
   if (verdict == 3) {
+    const int onl = (wowner * inv_nU) >> 20;
     PrimState<DIM, ORD, false> pr;
-    const mplx_waypoint *cp = nodes + ni;
-    const double *u = P.U + (size_t)ci * P.udim;
+    const mplx_waypoint *cp = nodes + node0 + onl;
+    const double *u = P.U + (size_t)(wowner - onl * nU) * P.udim;
+    double mv = 0;
 #pragma unroll
-    for (int k = 0; k < DIM; k++) pr.ax[k].build(__ldg(u + k), cp->pos[k], cp->vel[k], cp->acc[k], cp->jrk[k]);
+    for (int k = 0; k < DIM; k++) {
+      pr.ax[k].build(__ldg(u + k), cp->pos[k], cp->vel[k], cp->acc[k], cp->jrk[k]);
+      const double m1 = pr.ax[k].max_vel(P.T);
+      if (m1 > mv) mv = m1;
+    }
     double cf[CoefLayout<DIM, ORD, false>::NCMAX];
     fill_coef<DIM, ORD, false>(pr, false, cf);
     unsigned ns = 0;
-    verdict = isinf(traverse_loop<DIM, ORD, false>(P, cf, false, max_v, ns)) ? 1 : 0;
+    verdict = isinf(traverse_loop<DIM, ORD, false>(P, cf, false, mv, ns)) ? 1 : 0;
   }
-  if ((verdict == 0 || verdict == 1) && o.cost) o.cost[slot] = verdict == 1 ? (double)INFINITY : 0.0 + intrinsic;
+  if ((verdict == 0 || verdict == 1) && o.cost) o.cost[wslot] = verdict == 1 ? (double)INFINITY : 0.0 + wintr;
 }
 
 // Exact re-evaluation of the queued primitives: a thread rebuilds the exact quotients from (node,
@@ -340,28 +458,34 @@ static cudaError_t launch_fxn_t(const EnvParams &P, const mplx_waypoint *d_nodes
   const int inv_rows = ((1 << 20) + P.n_rows - 1) / P.n_rows;
   const int rows_bytes = (int)(((size_t)npb * P.n_rows * sizeof(FxnRow<ORD>) + 15) & ~(size_t)15);
   const size_t smem = (size_t)rows_bytes;
+  static const int sort_env = [] { const char *v = getenv("MPLX_FXN_SORT"); return v ? atoi(v) : -1; }();  // tuning
+  const bool sort = sort_env >= 0 ? sort_env != 0 : ORD >= 3;
   cudaError_t e = cudaMemsetAsync(amb_n, 0, sizeof(unsigned) * kFxSegments, st);
   if (e != cudaSuccess) return e;
   static const int unr_env = [] { const char *v = getenv("MPLX_FXN_UNR"); return v ? atoi(v) : 0; }();    // tuning
   static const int minb_env = [] { const char *v = getenv("MPLX_FXN_MINB"); return v ? atoi(v) : 0; }();  // tuning
-#define MPLX_LAUNCH_FXN(UNR, MINB, LAT, REGION)                                                                 \
+#define MPLX_LAUNCH_FXN_S(UNR, MINB, LAT, REGION, SORT)                                                         \
   do {                                                                                                          \
-    if (smem > 48 * 1024) {                                                                                     \
-      e = cudaFuncSetAttribute(expand_fxn_kernel<DIM, ORD, UNR, MINB, LAT, REGION>,                             \
+    if (smem > 32 * 1024) { /* static + dynamic may pass the 48 KB default */                                   \
+      e = cudaFuncSetAttribute(expand_fxn_kernel<DIM, ORD, UNR, MINB, LAT, REGION, SORT>,                       \
                                cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                         \
       if (e != cudaSuccess) return e;                                                                           \
     }                                                                                                           \
-    expand_fxn_kernel<DIM, ORD, UNR, MINB, LAT, REGION><<<grid, kThreads, smem, st>>>(                          \
-        P, d_nodes, n_nodes, npb, inv_nU, inv_rows, rows_bytes, amb_q, amb_n, amb_cap, o);                      \
+    expand_fxn_kernel<DIM, ORD, UNR, MINB, LAT, REGION, SORT><<<grid, kThreads, smem, st>>>(                    \
+        P, d_nodes, n_nodes, npb, inv_nU, inv_rows, amb_q, amb_n, amb_cap, o);                                  \
+  } while (0)
+#define MPLX_LAUNCH_FXN(UNR, MINB, LAT, REGION)                     \
+  do {                                                              \
+    if (sort) MPLX_LAUNCH_FXN_S(UNR, MINB, LAT, REGION, true);      \
+    else MPLX_LAUNCH_FXN_S(UNR, MINB, LAT, REGION, false);          \
   } while (0)
   if (region) { if (lat) MPLX_LAUNCH_FXN(4, 4, true, true); else MPLX_LAUNCH_FXN(4, 4, false, true); }
   else if (lat) MPLX_LAUNCH_FXN(4, 4, true, false);
-  else if (unr_env == 8 && minb_env == 5) MPLX_LAUNCH_FXN(8, 5, false, false);
   else if (unr_env == 8) MPLX_LAUNCH_FXN(8, 4, false, false);
   else if (minb_env == 5) MPLX_LAUNCH_FXN(4, 5, false, false);
-  else if (minb_env == 6) MPLX_LAUNCH_FXN(4, 6, false, false);
   else MPLX_LAUNCH_FXN(4, 4, false, false);
 #undef MPLX_LAUNCH_FXN
+#undef MPLX_LAUNCH_FXN_S
   e = cudaGetLastError();
   if (e != cudaSuccess) return e;
   const int rgrid = kFxSegments * 8;
