@@ -44,6 +44,9 @@ def parse():
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-multi-query", action="store_true", help="skip the cfg5 leg (sharded many-query planning)")
+    ap.add_argument("--mq-queries", type=int, default=4096)
+    ap.add_argument("--mq-max-expand", type=int, default=300)
     ap.add_argument("--kernel", type=int, default=0,
                     help="0 = auto, 1 = literal loop, 2 = register, 3 = flat, 4 = dealing, 5 = fixed-point")
     return ap.parse_args()
@@ -196,7 +199,7 @@ def cpu_reference(sc, nodes, threads, budget_s):
 def host_threads():
     """Threads for the CPU arm: every CPU the process may use (cgroup quota respected — running 128
     threads inside a 16-CPU quota only adds throttling and would flatter the GPU)."""
-    from motion_primitive_library_b200.scenarios import effective_cpus
+    from scenarios import effective_cpus
 
     return effective_cpus()
 
@@ -257,6 +260,95 @@ def parity_spot_check(env, sc, nodes):
     return {"nodes": int(len(nodes)), "successors": st["successors"], "against": against}
 
 
+def run_cfg5_workload(args, rank, local, world):
+    """`--workload cfg5`: the whole line is the sharded many-query planning run (BASELINE.json configs[4]).
+    A step = planning the full query set once; value = expansions/s of the whole job, end to end (device
+    expansion + PCIe + host A* bookkeeping + release of the search states)."""
+    import scenarios as S
+
+    sc5 = S.cfg3()
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        sys.path.insert(0, str(ROOT / "tests"))
+        import cfg5_bench
+        import planner_bindings as pb
+        from concurrent.futures import ThreadPoolExecutor
+
+        from motion_primitive_library_b200 import planner
+
+        q = cfg5_bench.make_queries(sc5, args.mq_queries, 20.0)
+        nt = host_threads()
+        n = min(len(q), 8 * nt)  # bounded sample of the same query set
+        grid = sc5.grid()
+
+        def one(k):
+            a = planner.make_args(3, sc5.control, grid, sc5.dim_cells, sc5.origin, sc5.res, sc5.U,
+                                  start=dict(pos=q["start"]["pos"][k]), goal=dict(pos=q["goal"]["pos"][k]), v_max=sc5.v_max,
+                                  a_max=sc5.a_max, T=sc5.T, w=sc5.w, max_num=args.mq_max_expand)
+            return pb.plan_reference(a)
+
+        vals = []
+        for it in range(args.warmup + args.steps):
+            with ThreadPoolExecutor(nt) as ex:
+                outs = list(ex.map(one, range(n)))
+            if it >= args.warmup:
+                vals.append(sum(o["n_closed"] for o in outs) / (sum(o["seconds"] for o in outs) / min(nt, n)))
+        v = float(np.mean(vals))
+        print(json.dumps({"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus,
+                          "steps": args.steps, "warmup": args.warmup, "ms_per_step": None, "higher_is_better": True,
+                          "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                          "config": {"workload": "cfg5", "queries": args.mq_queries, "max_expand": args.mq_max_expand,
+                                     "map": "512x512x512 @0.1 m int8", "control": "0x07", "primitives_per_node": 125},
+                          "cpu_baseline": {"value": v, "unit": UNIT, "cores": nt, "kind": "reference",
+                                           "sample": f"{n} of the {args.mq_queries} queries per step, one reference MapPlanner::plan per "
+                                                     f"host thread, time inside plan() only"},
+                          "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}), flush=True)
+        return
+    import torch
+    import torch.distributed as dist
+
+    import cfg5_bench
+    from motion_primitive_library_b200 import sharding
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the expansion engine has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        sharding.bind_to_gpu_numa(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    grid = sharding.broadcast_array(sc5.grid() if rank == 0 else None, src=0)
+    sampler = ClockSampler(local)
+    runs = []
+    for it in range(args.warmup + args.steps):
+        if it == args.warmup and rank == 0:
+            sampler.start()
+        r = cfg5_bench.run(sc5, grid, local, n_queries=args.mq_queries, max_expand=args.mq_max_expand,
+                           ref_queries=32 if (world == 1 and it == 0) else 0)
+        if it >= args.warmup:
+            runs.append(r)
+        elif it == 0:
+            first = r
+    if rank == 0:
+        clocks = sampler.stop()
+        secs = float(np.mean([r["seconds"] for r in runs]))
+        v = runs[0]["expansions"] / secs
+        line = {"metric": METRIC, "value": v, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": 1e3 * secs, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+                "data": "synthetic",
+                "config": {"workload": "cfg5", "queries": args.mq_queries, "max_expand": args.mq_max_expand,
+                           "map": "512x512x512 @0.1 m int8", "control": "0x07", "primitives_per_node": 125,
+                           "parallelism": f"queries sharded over {world} rank(s), map broadcast once, results all-gathered"},
+                "clocks": clocks, "multi_query": runs[-1], "reference_check": (first if args.warmup else runs[0]).get("reference"),
+                "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": None, "d2h_bytes_per_step": None,
+                        "note": "the value IS end to end: every iteration copies the popped nodes to the device and the "
+                                "{key, action} records of their successors back"},
+                "roofline": None, "cpu_baseline": None}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def kernel_name(which, sc, n_nodes):
     """The kernel mplx_set_kernel(which) launches for this workload (auto rule: mplx_kernels.cu launch_expand)."""
     names = {1: "mplx::expand_seq_kernel", 2: "mplx::expand_reg_kernel", 3: "mplx::expand_flat_kernel", 4: "mplx::expand_deal_kernel"}
@@ -275,8 +367,11 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
-    from motion_primitive_library_b200 import scenarios as S
+    import scenarios as S
 
+    if args.workload == "cfg5":
+        run_cfg5_workload(args, rank, local, world)
+        return
     sc = S.WORKLOADS[args.workload]()
     if args.impl == "reference":
         run_reference(args, sc, rank, world)
@@ -292,7 +387,11 @@ def main():
         raise SystemExit("bench.py: no CUDA device; the expansion engine has no CPU fallback "
                          "(use --impl reference for the CPU path)")
     torch.cuda.set_device(local)
+    numa = None
     if world > 1:
+        from motion_primitive_library_b200 import sharding
+
+        numa = sharding.bind_to_gpu_numa(local)  # before any pinned allocation
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     lib = abi.load()
 
@@ -452,6 +551,19 @@ def main():
                     "ms_per_step": 1e3 * secs / max(3, e2e_steps // 2), "launches": int(launches),
                     "call": "mplx_expand: full get_succ contract, 132 B per successor slot, +inf kept"}
 
+    # ---- cfg5 leg: the path's actual multi-GPU split — 4096 start/goal queries sharded over the ranks ----
+    multi_query = None
+    if not args.no_multi_query and args.workload == "512c_acc27":
+        import cfg5_bench
+        from motion_primitive_library_b200 import sharding
+
+        sc5 = S.cfg3()  # same map generator and seed as the headline workload, JRK-125 controls
+        grid5 = sharding.broadcast_array(sc.grid() if rank == 0 else None, src=0)  # the one set-up collective
+        env.close()
+        torch.cuda.empty_cache()
+        multi_query = cfg5_bench.run(sc5, grid5, local, n_queries=args.mq_queries, max_expand=args.mq_max_expand,
+                                     ref_queries=32 if world == 1 else 0)
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -490,8 +602,8 @@ def main():
         "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
         "config": config_dict(sc, n, world), "primitives_per_sec": value * nU, "parity_checked": parity_checked,
-        "clocks": clocks, "e2e": e2e, "e2e_state_records": e2e_state, "e2e_full_contract": e2e_full, "gpu_launches": int(gpu_launches),
-        "roofline": roofline,
+        "clocks": clocks, "numa": numa, "e2e": e2e, "e2e_state_records": e2e_state, "e2e_full_contract": e2e_full, "gpu_launches": int(gpu_launches),
+        "roofline": roofline, "multi_query": multi_query,
         "cpu_baseline": cpu_baseline,
     }
     print(json.dumps(line), flush=True)

@@ -2,9 +2,9 @@
 
 The product is libmplx.so (hand-written sm_100a CUDA behind the C ABI of include/mplx.h).
 This package holds the host-side mirror of the reference's operator interface for that one
-path and the synthetic-workload generators used by the tests and bench.py.
+path (benchmark input generators live in scenarios.py at the repository root).
 """
-from . import abi, scenarios  # noqa: F401
+from . import abi  # noqa: F401
 from .env import Expansion, MapUtil, env_map  # noqa: F401
 
-__all__ = ["abi", "scenarios", "env_map", "MapUtil", "Expansion"]
+__all__ = ["abi", "env_map", "MapUtil", "Expansion"]

@@ -1,4 +1,5 @@
-"""Deterministic synthetic inputs for the configurations of BASELINE.json / SURVEY.md §8d.
+"""Benchmark / test INPUT generators (not part of the product package): deterministic synthetic inputs for
+the configurations of BASELINE.json / SURVEY.md §8d.
 
 Maps are random axis-aligned boxes + a 1-voxel boundary shell (occupied = 100, free = 0,
 no unknowns), seed 42.  Control sets follow the nested-loop order of the reference tests
@@ -12,7 +13,7 @@ from dataclasses import dataclass, field
 
 import numpy as np
 
-from .abi import ACC, ACCxYAW, JRK, WAYPOINT_DTYPE
+from motion_primitive_library_b200.abi import ACC, ACCxYAW, JRK, WAYPOINT_DTYPE
 
 
 def effective_cpus() -> int:

@@ -44,7 +44,7 @@ def check(sc, nodes, region=None, extra=500, seed=0):
 @pytest.mark.parametrize("control,dim", [(VEL, 2), (ACC, 2), (JRK, 2), (SNP, 2), (ACCxYAW, 2), (VEL, 3), (ACC, 3),
                                          (JRK, 3), (SNP, 3)])
 def test_all_controls_random_states(control, dim):
-    from motion_primitive_library_b200.scenarios import Scenario, control_set
+    from scenarios import Scenario, control_set
     from test_oracle_vs_ref import random_nodes
 
     rng = np.random.default_rng(200 + control * 10 + dim)
@@ -58,7 +58,7 @@ def test_all_controls_random_states(control, dim):
 
 
 def test_headline_and_jrk_workload_edges():
-    from motion_primitive_library_b200 import scenarios as S
+    import scenarios as S
 
     for sc, n in ((S.scaled(S.cfg_headline(), 128), 3000), (S.scaled(S.cfg3(), 96), 500)):
         check(sc, sc.frontier(n, seed=9), extra=2000)
@@ -66,7 +66,7 @@ def test_headline_and_jrk_workload_edges():
 
 def test_capacity_retry_empty_and_errors():
     from motion_primitive_library_b200 import abi
-    from motion_primitive_library_b200 import scenarios as S
+    import scenarios as S
     import ctypes as C
 
     sc = S.scaled(S.cfg_headline(), 64)

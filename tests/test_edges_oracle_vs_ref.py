@@ -25,7 +25,7 @@ def edges_of(env, nodes, rng, extra=400):
 @pytest.mark.parametrize("control,dim", [(VEL, 2), (ACC, 2), (JRK, 2), (SNP, 2), (ACCxYAW, 2), (VEL, 3), (ACC, 3),
                                          (JRK, 3), (SNP, 3)])
 def test_is_free_and_cost_match_reference(control, dim):
-    from motion_primitive_library_b200.scenarios import Scenario, control_set
+    from scenarios import Scenario, control_set
     from test_oracle_vs_ref import random_nodes
 
     rng = np.random.default_rng(100 + control * 10 + dim)
@@ -48,7 +48,7 @@ def test_is_free_and_cost_match_reference(control, dim):
 def test_empty_map_edges_free_unless_they_leave_the_map():
     """On an empty map an edge is free iff all n+1 samples stay inside; is_free also samples t = T
     exactly (Primitive::sample), which traverse_primitive's running sum may not."""
-    from motion_primitive_library_b200.scenarios import control_set
+    from scenarios import control_set
 
     grid = np.zeros(32 ** 3, dtype=np.int8)
     env = ob.OracleEnv(3, ACC, control_set(1.0, 3, 3), grid, (32, 32, 32), (-4.0, -4.0, -4.0), 0.25, T=1.0, w=10.0,

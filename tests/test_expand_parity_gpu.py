@@ -55,7 +55,7 @@ def run_parity(sc, n, region=None, exact_cost=False, seed=7, kernels=(1, 2, 3, 4
 
 
 def test_headline_acc27_small_map():
-    from motion_primitive_library_b200 import scenarios as S
+    import scenarios as S
 
     st, g, orc = run_parity(S.scaled(S.cfg_headline(), 128), 6000, exact_cost=True)
     inf_frac = np.isinf(orc["cost"][: 27]).mean()
@@ -63,25 +63,25 @@ def test_headline_acc27_small_map():
 
 
 def test_cfg2_acc27_coarse_map():
-    from motion_primitive_library_b200 import scenarios as S
+    import scenarios as S
 
     run_parity(S.scaled(S.cfg2(), 96), 4000, exact_cost=True)
 
 
 def test_cfg3_jrk125():
-    from motion_primitive_library_b200 import scenarios as S
+    import scenarios as S
 
     run_parity(S.scaled(S.cfg3(), 128), 1500, exact_cost=True)
 
 
 def test_cfg4_accyaw81_potential():
-    from motion_primitive_library_b200 import scenarios as S
+    import scenarios as S
 
     run_parity(S.scaled(S.cfg4(), 96), 1500)
 
 
 def test_cfg4_with_gradient_weight():
-    from motion_primitive_library_b200 import scenarios as S
+    import scenarios as S
 
     sc = S.scaled(S.cfg4(), 64)
     sc.gradient_weight = 0.3
@@ -89,7 +89,7 @@ def test_cfg4_with_gradient_weight():
 
 
 def test_search_region_tunnel():
-    from motion_primitive_library_b200 import scenarios as S
+    import scenarios as S
 
     sc = S.scaled(S.cfg_headline(), 64)
     rng = np.random.default_rng(3)
@@ -98,7 +98,7 @@ def test_search_region_tunnel():
 
 
 def _custom(dim, control, U, cells, res, seed=5, **kw):
-    from motion_primitive_library_b200.scenarios import Scenario
+    from scenarios import Scenario
 
     return Scenario(f"custom{dim}d_{control:x}", (cells,) * dim, res, tuple(-cells * res / 2 for _ in range(dim)),
                     control, U, n_boxes=max(2, cells // 6), edge_m=(4 * res, 12 * res), seed=seed, **kw)
@@ -145,7 +145,7 @@ def test_corridor_2d_acc9_reference_test_config():
 
 def test_corridor_2d_accyaw27_reference_test_config():
     """test/test_planner_2d_with_yaw.cpp parameters (yaw_max 0.7, 27 controls)."""
-    from motion_primitive_library_b200.scenarios import Scenario
+    from scenarios import Scenario
 
     c = fixtures.corridor()
     sc = Scenario("corridor_yaw", tuple(int(x) for x in c["dim"]), c["res"], tuple(c["origin"]), ACCxYAW,
@@ -155,7 +155,7 @@ def test_corridor_2d_accyaw27_reference_test_config():
 
 
 def test_2d_vel_and_3d_snp_and_jrkyaw():
-    from motion_primitive_library_b200.scenarios import control_set
+    from scenarios import control_set
 
     # frontier generator handles ACC/JRK; for VEL/SNP build nodes by hand on a free map
     rng = np.random.default_rng(11)
@@ -184,7 +184,7 @@ def test_2d_vel_and_3d_snp_and_jrkyaw():
 
 
 def test_empty_and_ragged_batches_and_pinned_buffers():
-    from motion_primitive_library_b200 import scenarios as S
+    import scenarios as S
 
     sc = S.scaled(S.cfg_headline(), 64)
     e = gpu_env(sc)
@@ -206,7 +206,7 @@ def test_empty_and_ragged_batches_and_pinned_buffers():
 
 
 def test_setter_invalidation_and_stats():
-    from motion_primitive_library_b200 import scenarios as S
+    import scenarios as S
 
     sc = S.scaled(S.cfg_headline(), 64)
     e = gpu_env(sc)
@@ -229,7 +229,7 @@ def test_setter_invalidation_and_stats():
 def test_unbounded_velocity_falls_back_past_the_sample_table():
     """v_max <= 0 (unlimited, env_base.h:380) with fast nodes: n = ceil(max_v*T/res) exceeds the
     128-row sample-time table for some primitives -> in-kernel sequential fallback."""
-    from motion_primitive_library_b200.scenarios import control_set
+    from scenarios import control_set
 
     sc = _custom(3, ACC, control_set(1.0, 3, 3), 64, 0.05)
     sc.v_max = -1.0
@@ -250,7 +250,7 @@ def test_unbounded_velocity_falls_back_past_the_sample_table():
 
 def test_many_controls_uses_sequential_kernel():
     """|U| = 343 > 256 primitives per node: served by the sequential kernel."""
-    from motion_primitive_library_b200.scenarios import control_set
+    from scenarios import control_set
 
     sc = _custom(3, ACC, control_set(1.5, 7, 3), 48, 0.2, v_max=3.0)
     nodes = sc.frontier(300, seed=9)
@@ -306,7 +306,7 @@ def _check_packed(env, sc, orc, nodes, drop_inf):
 def test_packed_stream_matches_oracle():
     """mplx_expand_packed: dense state/cost/action/key records, with and without +inf successors,
     across several pipeline chunks (60k nodes > 19k-node chunks)."""
-    from motion_primitive_library_b200 import scenarios as S
+    import scenarios as S
 
     for sc, n in ((S.scaled(S.cfg_headline(), 96), 60000), (S.scaled(S.cfg3(), 64), 9000), (S.scaled(S.cfg4(), 64), 3000)):
         nodes = sc.frontier(n, seed=21)
@@ -316,7 +316,7 @@ def test_packed_stream_matches_oracle():
             _check_packed(env, sc, orc, nodes, drop)
     # 2-D, pageable buffers, tiny and empty batches
     c = fixtures.corridor()
-    from motion_primitive_library_b200.scenarios import Scenario
+    from scenarios import Scenario
 
     sc = Scenario("corridor", tuple(int(x) for x in c["dim"]), c["res"], tuple(c["origin"]), ACC, fixtures.U_2d(),
                   v_max=1.0, a_max=1.0)

@@ -37,7 +37,7 @@ def _check(sc, nodes, env, orc_env, exact_cost, kernels):
 
 
 def test_headline_512c_acc27_full_shape():
-    from motion_primitive_library_b200 import scenarios as S
+    import scenarios as S
 
     sc = S.cfg_headline()
     assert sc.dim_cells == (512, 512, 512)
@@ -47,7 +47,7 @@ def test_headline_512c_acc27_full_shape():
 
 
 def test_cfg2_256c_acc27_full_shape():
-    from motion_primitive_library_b200 import scenarios as S
+    import scenarios as S
 
     sc = S.cfg2()
     assert sc.dim_cells == (256, 256, 256)
@@ -55,7 +55,7 @@ def test_cfg2_256c_acc27_full_shape():
 
 
 def test_cfg3_512c_jrk125_full_shape():
-    from motion_primitive_library_b200 import scenarios as S
+    import scenarios as S
 
     sc = S.cfg3()
     _check(sc, sc.frontier(1500, seed=7), gpu_env(sc), ob.OracleEnv.from_scenario(sc), True, (2, 4, 5, 0))
@@ -65,7 +65,7 @@ def test_cfg4_512c_accyaw81_potential_full_shape():
     """The potential field is built on the device by mplx_update_potential_map (bit-exact against the
     reference's updatePotentialMap in tests/test_maps_gpu.py; the scipy generator of the scenario
     needs minutes at 512^3) and handed to the oracle / the reference as their potential_map_."""
-    from motion_primitive_library_b200 import scenarios as S
+    import scenarios as S
 
     sc = S.cfg4()
     rad = sc.potential_radius

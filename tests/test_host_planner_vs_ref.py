@@ -47,7 +47,7 @@ def test_corridor_yaw_and_eps_and_max_expand():
 
 
 def test_3d_voxel_maps_acc_and_jrk():
-    from motion_primitive_library_b200 import scenarios as S
+    import scenarios as S
 
     for sc, maxn in ((S.scaled(S.cfg_headline(), 64), 1500), (S.scaled(S.cfg3(), 48), 300)):
         nodes = sc.frontier(16, seed=4, max_steps=0)
@@ -59,7 +59,7 @@ def test_3d_voxel_maps_acc_and_jrk():
 
 
 def test_potential_field_generator_vs_updatePotentialMap():
-    from motion_primitive_library_b200 import scenarios as S
+    import scenarios as S
 
     rng = np.random.default_rng(2)
     for dims, res, rad in (((30, 28, 26), 0.1, (0.5, 0.5, 0.3)), ((24, 24, 24), 0.25, (1.0, 1.0, 0.5))):

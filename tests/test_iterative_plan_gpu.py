@@ -31,7 +31,7 @@ def test_corridor_tunnel_replanning(radius, speculate):
 
 
 def test_voxel_map_tunnel():
-    from motion_primitive_library_b200 import scenarios as S
+    import scenarios as S
 
     sc = S.scaled(S.cfg_headline(), 64)
     nodes = sc.frontier(16, seed=4, max_steps=0)

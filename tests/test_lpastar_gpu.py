@@ -28,7 +28,7 @@ def test_corridor_block_clear_sessions(idx, half, speculate):
 
 @pytest.mark.parametrize("which,q,speculate", [("acc", 0, 1), ("acc", 4, 16), ("jrk", 2, 4)])
 def test_voxel_map_sessions(which, q, speculate):
-    from motion_primitive_library_b200 import scenarios as S
+    import scenarios as S
 
     sc, maxn = (S.scaled(S.cfg_headline(), 64), 4000) if which == "acc" else (S.scaled(S.cfg3(), 48), 600)
     a = voxel_session_args(sc, q, maxn)

@@ -122,7 +122,7 @@ def voxel_script(sc, a, first):
 
 @pytest.mark.parametrize("which,q", [("acc", 0), ("acc", 4), ("jrk", 2)])
 def test_voxel_map_sessions(which, q):
-    from motion_primitive_library_b200 import scenarios as S
+    import scenarios as S
 
     sc, maxn = (S.scaled(S.cfg_headline(), 64), 4000) if which == "acc" else (S.scaled(S.cfg3(), 48), 600)
     a = voxel_session_args(sc, q, maxn)

@@ -27,7 +27,7 @@ def ref_args(grid, dims, origin, res):
 
 
 def test_potential_map_3d_matches_reference():
-    from motion_primitive_library_b200 import scenarios as S
+    import scenarios as S
 
     rng = np.random.default_rng(3)
     for dims, res, rad, powv in (((40, 36, 30), 0.1, (0.5, 0.5, 0.3), 1.0), ((33, 31, 29), 0.25, (1.0, 1.0, 0.5), 1.0),
@@ -70,7 +70,7 @@ def test_search_region_matches_reference():
         ref = pb.reference_search_region(ref_args(c["grid"], dims, origin, res), path, (0.5, 0.35), c["grid"].size, dense)
         np.testing.assert_array_equal(got, ref)
         assert 0 < got.sum() < got.size
-    from motion_primitive_library_b200 import scenarios as S
+    import scenarios as S
 
     sc = S.scaled(S.cfg_headline(), 48)
     path3 = np.array([[-2.0, -2.0, -2.0], [0.0, 1.0, 0.5], [2.0, 2.0, 2.0]])
@@ -82,7 +82,7 @@ def test_search_region_matches_reference():
 def test_expansion_after_device_side_potential_and_tunnel():
     """The distance-map planner flow (test/test_distance_map_planner_2d.cpp:77-94): tunnel around a path,
     potential field from the grid, then get_succ — all device-side, against the oracle fed the same arrays."""
-    from motion_primitive_library_b200 import scenarios as S
+    import scenarios as S
 
     sc = S.scaled(S.cfg_headline(), 64)
     env = gpu_env(sc.grid(), sc.dim_cells, sc.origin, sc.res)

@@ -39,7 +39,7 @@ def test_batch_equals_individual_plans_corridor():
 
 
 def test_batch_3d_jrk_voxel_map():
-    from motion_primitive_library_b200 import scenarios as S
+    import scenarios as S
 
     sc = S.scaled(S.cfg3(), 64)
     nodes = sc.frontier(32, seed=5, max_steps=0)

@@ -71,7 +71,7 @@ def test_corridor_reference_test_config_first_expansions():
                                          (JRKxYAW, 2), (SNPxYAW, 2), (VEL, 3), (ACC, 3), (JRK, 3), (SNP, 3),
                                          (ACCxYAW, 3), (JRKxYAW, 3), (SNPxYAW, 3)])
 def test_all_controls_random_states(control, dim):
-    from motion_primitive_library_b200.scenarios import Scenario, control_set
+    from scenarios import Scenario, control_set
 
     rng = np.random.default_rng(control * 10 + dim)
     yaw = bool(control & 16)
@@ -86,7 +86,7 @@ def test_all_controls_random_states(control, dim):
 
 
 def test_potential_gradient_and_region():
-    from motion_primitive_library_b200 import scenarios as S
+    import scenarios as S
 
     sc = S.scaled(S.cfg4(), 48)
     sc.gradient_weight = 0.3
@@ -99,7 +99,7 @@ def test_potential_gradient_and_region():
 
 def test_unlimited_dynamics_and_large_sample_counts():
     """limits <= 0 are 'unlimited' (env_base.h:380-386); fast nodes give n up to ~200 samples."""
-    from motion_primitive_library_b200.scenarios import Scenario, control_set
+    from scenarios import Scenario, control_set
 
     sc = Scenario("x", (64, 64, 64), 0.05, (-1.6, -1.6, -1.6), ACC, control_set(1.0, 3, 3), n_boxes=6,
                   edge_m=(0.2, 0.6), seed=5)
@@ -112,7 +112,7 @@ def test_unlimited_dynamics_and_large_sample_counts():
 
 
 def test_headline_workload_sample():
-    from motion_primitive_library_b200 import scenarios as S
+    import scenarios as S
 
     for sc, n in ((S.scaled(S.cfg_headline(), 96), 1500), (S.scaled(S.cfg3(), 96), 400), (S.scaled(S.cfg2(), 64), 800)):
         env = ob.OracleEnv.from_scenario(sc)

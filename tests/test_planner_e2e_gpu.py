@@ -60,7 +60,7 @@ def test_corridor_with_yaw():
 
 
 def test_3d_acc_and_jrk_voxel_maps():
-    from motion_primitive_library_b200 import scenarios as S
+    import scenarios as S
 
     for sc, maxn in ((S.scaled(S.cfg_headline(), 96), 3000), (S.scaled(S.cfg3(), 64), 600)):
         grid = sc.grid()

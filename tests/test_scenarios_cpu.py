@@ -1,7 +1,7 @@
 """Synthetic-input generators (host logic, CPU)."""
 import numpy as np
 
-from motion_primitive_library_b200 import scenarios as S
+import scenarios as S
 
 
 def test_potential_field_fast_path_equals_literal_stencil():

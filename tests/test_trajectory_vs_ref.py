@@ -35,7 +35,7 @@ def test_corridor_trajectory(control, U, kw, n_samples):
 
 
 def test_voxel_jrk_trajectory():
-    from motion_primitive_library_b200 import scenarios as S
+    import scenarios as S
 
     sc = S.scaled(S.cfg3(), 48)
     nodes = sc.frontier(16, seed=4, max_steps=0)

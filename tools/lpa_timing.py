@@ -12,7 +12,7 @@ ROOT = Path(__file__).resolve().parent.parent
 sys.path.insert(0, str(ROOT))
 sys.path.insert(0, str(ROOT / "tests"))
 import planner_bindings as pb  # noqa: E402
-from motion_primitive_library_b200 import scenarios as S  # noqa: E402
+import scenarios as S  # noqa: E402
 from test_lpastar_vs_ref import FIELDS, integrate_cells  # noqa: E402
 
 cells = int(sys.argv[1]) if len(sys.argv) > 1 else 256
