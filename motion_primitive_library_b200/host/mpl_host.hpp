@@ -843,15 +843,74 @@ class env_map_gpu : public env_map_host<Dim> {
   mutable long stats_nodes_ = 0, stats_calls_ = 0, stats_hits_ = 0;
 };
 
+/// Bump allocator for the overflow buffers of a search's predecessor lists: one rewind() returns
+/// everything at once, so recycling the states of a finished search costs nothing per state.
+class BumpPool {
+ public:
+  BumpPool() {}
+  BumpPool(const BumpPool &) = delete;
+  BumpPool &operator=(const BumpPool &) = delete;
+  ~BumpPool() {
+    for (char *b : blocks_) std::free(b);
+    for (char *b : big_) std::free(b);
+  }
+  void *alloc(std::size_t n) {
+    n = (n + 15) & ~(std::size_t)15;
+    if (n > kBytes) {  // never for predecessor lists; kept correct
+      char *p = (char *)std::malloc(n);
+      if (!p) throw std::bad_alloc();
+      big_.push_back(p);
+      return p;
+    }
+    if (blocks_.empty() || used_ + n > kBytes) {
+      if (!blocks_.empty() && cur_ + 1 < blocks_.size()) {
+        cur_++;
+      } else {
+        char *b = (char *)std::malloc(kBytes);
+        if (!b) throw std::bad_alloc();
+        blocks_.push_back(b);
+        cur_ = blocks_.size() - 1;
+      }
+      used_ = 0;
+    }
+    void *p = blocks_[cur_] + used_;
+    used_ += n;
+    return p;
+  }
+  void rewind() {
+    cur_ = 0;
+    used_ = 0;
+    for (char *b : big_) std::free(b);
+    big_.clear();
+  }
+
+ private:
+  static constexpr std::size_t kBytes = 1 << 16;
+  std::vector<char *> blocks_, big_;
+  std::size_t cur_ = 0, used_ = 0;
+};
+/// The pool the SmallVecs of the calling thread grow into (set for the duration of one relax step by
+/// PoolScope); null = malloc.
+inline BumpPool *&tl_pred_pool() {
+  static thread_local BumpPool *p = nullptr;
+  return p;
+}
+struct PoolScope {
+  BumpPool *prev;
+  explicit PoolScope(BumpPool *p) : prev(tl_pred_pool()) { tl_pred_pool() = p; }
+  ~PoolScope() { tl_pred_pool() = prev; }
+};
+
 /// A vector with room for N elements inside the object: most states have one or two predecessors,
-/// so the common case needs no heap allocation.  Only what the planner uses.
+/// so the common case needs no heap allocation.  Only what the planner uses.  A buffer grown while a
+/// PoolScope is active lives in that pool (never freed individually); otherwise it is malloc'ed.
 template <typename T, int N>
 class SmallVec {
  public:
   SmallVec() {}
   SmallVec(const SmallVec &) = delete;
   SmallVec &operator=(const SmallVec &) = delete;
-  ~SmallVec() { if (heap_) std::free(heap_); }
+  ~SmallVec() { if (heap_ && owned_) std::free(heap_); }
   std::size_t size() const { return n_; }
   bool empty() const { return n_ == 0; }
   void clear() { n_ = 0; }
@@ -872,16 +931,19 @@ class SmallVec {
   const T *data() const { return heap_ ? heap_ : inl_; }
   void grow() {
     const unsigned nc = cap_ * 2;
-    T *p = (T *)std::malloc(sizeof(T) * nc);
+    BumpPool *pool = tl_pred_pool();
+    T *p = (T *)(pool ? pool->alloc(sizeof(T) * nc) : std::malloc(sizeof(T) * nc));
     if (!p) throw std::bad_alloc();
     std::memcpy(p, data(), sizeof(T) * n_);
-    if (heap_) std::free(heap_);
+    if (heap_ && owned_) std::free(heap_);
     heap_ = p;
+    owned_ = pool == nullptr;
     cap_ = nc;
   }
   T inl_[N];
   T *heap_ = nullptr;
   unsigned n_ = 0, cap_ = N;
+  bool owned_ = false;
 };
 
 /// State: include/mpl_planner/common/state_space.h:36-74 (A* members)
@@ -1005,6 +1067,11 @@ class KeyMap {
     }
   }
   std::size_t size() const { return size_; }
+  /// forget every key, keep the table
+  void clear() {
+    std::fill(tab_.begin(), tab_.end(), std::pair<std::size_t, V *>(0, nullptr));
+    size_ = 0;
+  }
   void swap(KeyMap &o) { tab_.swap(o.tab_); std::swap(mask_, o.mask_); std::swap(size_, o.size_); }
 
  private:
@@ -1035,26 +1102,55 @@ struct StateSpace {
   /// of getSubStateSpace :184-192 and getLinkedNodes depend on it).
   KeyMap<S> hm_;
   std::vector<S *> order_;
-  /// states are carved out of 256-state blocks: one allocation per block, addresses never move
+  /// states are carved out of 256-state blocks: one allocation per block, addresses never move; blocks
+  /// survive reset() and are handed out again
   struct Arena {
     static constexpr std::size_t kBlock = 256;
     std::vector<S *> blocks;
+    std::size_t in_use = 0;  // blocks holding states
     std::size_t used = kBlock;
     S *emplace(const Waypoint<Dim> &c, std::size_t k) {
       if (used == kBlock) {
-        blocks.push_back((S *)::operator new(sizeof(S) * kBlock));
+        if (in_use == blocks.size()) blocks.push_back((S *)::operator new(sizeof(S) * kBlock));
+        in_use++;
         used = 0;
       }
-      return new (blocks.back() + used++) S(c, k);
+      return new (blocks[in_use - 1] + used++) S(c, k);
+    }
+    /// end the life of every state; `trivial`: no state owns memory (A*-only search whose predecessor
+    /// lists grew into the space's pool), so nothing has to be visited
+    void rewind(bool trivial) {
+      if (!trivial)
+        for (std::size_t b = 0; b < in_use; b++) {
+          const std::size_t n = b + 1 == in_use ? used : kBlock;
+          for (std::size_t i = 0; i < n; i++) blocks[b][i].~S();
+        }
+      in_use = 0;
+      used = kBlock;
     }
     ~Arena() {
-      for (std::size_t b = 0; b < blocks.size(); b++) {
-        const std::size_t n = b + 1 == blocks.size() ? used : kBlock;
-        for (std::size_t i = 0; i < n; i++) blocks[b][i].~S();
-        ::operator delete(blocks[b]);
-      }
+      for (S *b : blocks) ::operator delete(b);
     }
   } arena_;
+  /// overflow buffers of the predecessor lists of an A* search (AstarStepper::consume)
+  BumpPool pred_pool_;
+  /// true while only AstarStepper touched the states: none of them owns memory
+  bool trivial_states_ = true;
+  ~StateSpace() { arena_.rewind(trivial_states_); }
+  /// Forget the search but keep every allocation (state blocks, predecessor pool, hash table, heap and
+  /// order arrays) for the next one on this space.
+  void reset(decimal_t eps) {
+    arena_.rewind(trivial_states_);
+    pred_pool_.rewind();
+    trivial_states_ = true;
+    hm_.clear();
+    order_.clear();
+    pq_.clear();
+    best_child_.clear();
+    expand_iteration_ = 0;
+    eps_ = eps;
+    start_t_ = start_g_ = start_rhs_ = 0;
+  }
   /// hm_[coord] of a key that is not in the map yet: create the state and enter it
   S *make_state(const Waypoint<Dim> &c, std::size_t k) {
     S *n = arena_.emplace(c, k);
@@ -1315,6 +1411,7 @@ class AstarStepper {
   /// graph_search.h:79-161 with the successors of the node returned by pop()
   template <typename SuccAt, typename KeyAt>
   void consume(int n_succ, SuccAt succ_at, const decimal_t *succ_cost, const int *succ_act_id, KeyAt key_at) {
+    const PoolScope pool(&ss_ptr->pred_pool_);  // predecessor lists grow into the space's pool
     for (int s = 0; s < n_succ; ++s) {
       if (std::isinf(succ_cost[s])) continue;  // graph_search.h:81
       const std::size_t skey = key_at(s);
@@ -1409,6 +1506,7 @@ class GraphSearch {
   /// reference dereferences pq_.top() there).
   decimal_t LPAstar(const Waypoint<Dim> &start_coord, const std::shared_ptr<env_base<Dim>> &ENV,
                     std::shared_ptr<StateSpace<Dim>> &ss_ptr, std::vector<Edge<Dim>> &traj, int max_expand = -1) {
+    ss_ptr->trivial_states_ = false;  // LPA* keeps successor lists and malloc'ed predecessor lists in the states
     using S = State<Dim>;
     const decimal_t inf = std::numeric_limits<decimal_t>::infinity();
     traj.clear();
@@ -1890,7 +1988,9 @@ class MultiQueryPlanner {
 
   std::vector<Result> plan(const vec_E<Waypoint<Dim>> &starts, const vec_E<Waypoint<Dim>> &goals, decimal_t eps,
                            int max_expand) {
-    release();
+    // the search states of the previous plan() are recycled, not freed: a planner that answers batch
+    // after batch allocates (and page-faults) its state memory once
+    if (ss_.size() != starts.size()) release();
     WorkerPool pool(host_threads_ > 0 ? host_threads_ : effective_cpus());
     const std::size_t Q = starts.size();
     auto &envs = envs_;
@@ -1899,12 +1999,13 @@ class MultiQueryPlanner {
     envs.resize(Q); ss.resize(Q); st.resize(Q);
     std::vector<Result> res(Q);
     pool.run(Q, [&](std::size_t q) {
-      envs[q].reset(new QueryEnv(map_util_));
+      if (!envs[q]) envs[q].reset(new QueryEnv(map_util_));
       QueryEnv &e = *envs[q];
       e.w_ = gpu_->w_; e.v_max_ = gpu_->v_max_; e.dt_ = gpu_->dt_; e.t_max_ = gpu_->t_max_;
       e.tol_pos_ = gpu_->tol_pos_; e.tol_vel_ = gpu_->tol_vel_; e.tol_acc_ = gpu_->tol_acc_; e.tol_yaw_ = gpu_->tol_yaw_;
       e.set_goal(goals[q]);
-      ss[q].reset(new StateSpace<Dim>(eps));
+      if (ss[q]) ss[q]->reset(eps);
+      else ss[q].reset(new StateSpace<Dim>(eps));
       st[q].reset(new AstarStepper<Dim>(&e, ss[q], max_expand));
       if (e.is_free(starts[q].pos)) st[q]->start(starts[q]);  // planner_base.h:283-287
     });

@@ -127,62 +127,114 @@ int mplh_lpa_run(const mplh_plan_args *a, const mplh_lpa_step *steps, int n_step
   }
 }
 
-/* Lock-step batched A* over n_q (start, goal) pairs on the map/params of `a` (a->start/goal are
- * ignored).  totals[0] = lock-step iterations (= device launches of the expansion kernel),
- * totals[1] = nodes expanded over all queries, totals[2] = wall seconds of the search,
- * totals[3..5] = seconds in the pop / device expansion (incl. PCIe) / relax phases,
- * totals[6] = seconds spent freeing the search states afterwards (7 doubles). */
-int mplh_plan_batch(const mplh_plan_args *a, const mplx_waypoint *starts, const mplx_waypoint *goals, int n_q,
+/* Lock-step batched A* over many (start, goal) pairs on one map (MPL::MultiQueryPlanner) as a
+ * session: open once (map upload, parameters), plan any number of query sets — the search states of a
+ * set are recycled for the next one, so a steady stream of batches allocates its state memory once —
+ * and close.  totals (7 doubles): [0] lock-step iterations (= device launches of the expansion
+ * kernel), [1] nodes expanded over all queries, [2] wall seconds of the search, [3..5] seconds in the
+ * pop / device expansion (incl. PCIe) / relax phases, [6] 0 (states are kept for the next set). */
+}  // extern "C"
+namespace {
+struct BatchSession {
+  int dim = 0;
+  int control = 0;
+  void *mq = nullptr;  // MPL::MultiQueryPlanner<dim>*
+};
+template <int Dim>
+MPL::MultiQueryPlanner<Dim> *open_mq(const mplh_plan_args *a) {
+  auto *mq = new MPL::MultiQueryPlanner<Dim>(mplh::make_map<Dim>(a), a->device);
+  auto &e = mq->env();
+  if (const char *t = std::getenv("MPLH_THREADS")) mq->setHostThreads(std::atoi(t));
+  vec_E<VecDf> U;
+  for (int i = 0; i < a->nU; i++) U.push_back(VecDf(a->U + (size_t)i * a->udim, a->U + (size_t)(i + 1) * a->udim));
+  e.set_u(U); e.set_control(a->control);
+  e.set_v_max(a->v_max); e.set_a_max(a->a_max); e.set_j_max(a->j_max); e.set_yaw_max(a->yaw_max);
+  e.set_dt(a->T); e.set_w(a->w); e.set_wyaw(a->wyaw);
+  e.set_tol_pos(a->tol_pos); e.set_tol_vel(a->tol_vel); e.set_tol_acc(a->tol_acc);
+  if (a->potential) {
+    size_t n = 1;
+    for (int k = 0; k < Dim; k++) n *= (size_t)a->mdim[k];
+    e.set_potential_map(std::vector<int8_t>(a->potential, a->potential + n));
+    e.set_potential_weight(a->potential_weight);
+    e.set_gradient_weight(a->gradient_weight);
+  }
+  return mq;
+}
+template <int Dim>
+void plan_mq(MPL::MultiQueryPlanner<Dim> *mq, int control, const mplx_waypoint *starts, const mplx_waypoint *goals, int n_q,
+             double eps, int max_num, mplh_query_result *out, double *totals) {
+  vec_E<Waypoint<Dim>> S, G;
+  for (int q = 0; q < n_q; q++) {
+    S.push_back(mplh::wp_from<Dim>(starts[q], control));
+    G.push_back(mplh::wp_from<Dim>(goals[q], control));
+  }
+  auto t0 = std::chrono::steady_clock::now();
+  auto res = mq->plan(S, G, eps, max_num);
+  const double secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+  for (int q = 0; q < n_q; q++) {
+    out[q].valid = res[q].valid ? 1 : 0;
+    out[q].cost = res[q].cost;
+    out[q].expanded = res[q].expanded;
+    out[q].n_closed = (int)res[q].n_closed;
+    out[q].n_actions = (int)res[q].actions.size();
+  }
+  if (totals) {
+    totals[0] = (double)mq->iterations(); totals[1] = (double)mq->nodes_expanded(); totals[2] = secs;
+    totals[3] = mq->t_pop(); totals[4] = mq->t_device(); totals[5] = mq->t_relax(); totals[6] = 0.0;
+  }
+}
+}  // namespace
+extern "C" {
+
+void *mplh_batch_open(const mplh_plan_args *a) {
+  try {
+    if (a->dim != 2 && a->dim != 3) throw std::runtime_error("dim must be 2 or 3");
+    BatchSession *s = new BatchSession();
+    s->dim = a->dim;
+    s->control = a->control;
+    s->mq = a->dim == 2 ? (void *)open_mq<2>(a) : (void *)open_mq<3>(a);
+    return s;
+  } catch (const std::exception &e) {
+    g_err = e.what();
+    return nullptr;
+  }
+}
+
+int mplh_batch_plan(void *session, const mplx_waypoint *starts, const mplx_waypoint *goals, int n_q, double eps, int max_num,
                     mplh_query_result *out, double *totals) {
   try {
-    auto go = [&](auto dimtag) {
-      constexpr int Dim = decltype(dimtag)::value;
-      MPL::MultiQueryPlanner<Dim> mq(mplh::make_map<Dim>(a), a->device);
-      auto &e = mq.env();
-      if (const char *t = std::getenv("MPLH_THREADS")) mq.setHostThreads(std::atoi(t));
-      vec_E<VecDf> U;
-      for (int i = 0; i < a->nU; i++) U.push_back(VecDf(a->U + (size_t)i * a->udim, a->U + (size_t)(i + 1) * a->udim));
-      e.set_u(U); e.set_control(a->control);
-      e.set_v_max(a->v_max); e.set_a_max(a->a_max); e.set_j_max(a->j_max); e.set_yaw_max(a->yaw_max);
-      e.set_dt(a->T); e.set_w(a->w); e.set_wyaw(a->wyaw);
-      e.set_tol_pos(a->tol_pos); e.set_tol_vel(a->tol_vel); e.set_tol_acc(a->tol_acc);
-      if (a->potential) {
-        size_t n = 1;
-        for (int k = 0; k < Dim; k++) n *= (size_t)a->mdim[k];
-        e.set_potential_map(std::vector<int8_t>(a->potential, a->potential + n));
-        e.set_potential_weight(a->potential_weight);
-        e.set_gradient_weight(a->gradient_weight);
-      }
-      vec_E<Waypoint<Dim>> S, G;
-      for (int q = 0; q < n_q; q++) {
-        S.push_back(mplh::wp_from<Dim>(starts[q], a->control));
-        G.push_back(mplh::wp_from<Dim>(goals[q], a->control));
-      }
-      auto t0 = std::chrono::steady_clock::now();
-      auto res = mq.plan(S, G, a->eps, a->max_num);
-      const double secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
-      for (int q = 0; q < n_q; q++) {
-        out[q].valid = res[q].valid ? 1 : 0;
-        out[q].cost = res[q].cost;
-        out[q].expanded = res[q].expanded;
-        out[q].n_closed = (int)res[q].n_closed;
-        out[q].n_actions = (int)res[q].actions.size();
-      }
-      auto t1 = std::chrono::steady_clock::now();
-      mq.release();
-      const double secs_release = std::chrono::duration<double>(std::chrono::steady_clock::now() - t1).count();
-      if (totals) {
-        totals[0] = (double)mq.iterations(); totals[1] = (double)mq.nodes_expanded(); totals[2] = secs;
-        totals[3] = mq.t_pop(); totals[4] = mq.t_device(); totals[5] = mq.t_relax(); totals[6] = secs_release;
-      }
-    };
-    if (a->dim == 2) go(std::integral_constant<int, 2>());
-    else if (a->dim == 3) go(std::integral_constant<int, 3>());
-    else { g_err = "dim must be 2 or 3"; return 1; }
+    BatchSession *s = (BatchSession *)session;
+    if (!s || !s->mq) throw std::runtime_error("null session");
+    if (s->dim == 2) plan_mq<2>((MPL::MultiQueryPlanner<2> *)s->mq, s->control, starts, goals, n_q, eps, max_num, out, totals);
+    else plan_mq<3>((MPL::MultiQueryPlanner<3> *)s->mq, s->control, starts, goals, n_q, eps, max_num, out, totals);
     return 0;
   } catch (const std::exception &e) {
     g_err = e.what();
-    return 2;
+    return 1;
   }
+}
+
+/* Frees the session incl. the search states it kept; seconds spent are returned in *release_seconds. */
+int mplh_batch_close(void *session, double *release_seconds) {
+  BatchSession *s = (BatchSession *)session;
+  if (!s) return 0;
+  auto t0 = std::chrono::steady_clock::now();
+  if (s->dim == 2) delete (MPL::MultiQueryPlanner<2> *)s->mq;
+  else delete (MPL::MultiQueryPlanner<3> *)s->mq;
+  delete s;
+  if (release_seconds) *release_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+  return 0;
+}
+
+/* One-shot form: open, plan one set, close.  totals[6] = seconds spent freeing the search states. */
+int mplh_plan_batch(const mplh_plan_args *a, const mplx_waypoint *starts, const mplx_waypoint *goals, int n_q,
+                    mplh_query_result *out, double *totals) {
+  void *s = mplh_batch_open(a);
+  if (!s) return 1;
+  const int rc = mplh_batch_plan(s, starts, goals, n_q, a->eps, a->max_num, out, totals);
+  double rel = 0;
+  mplh_batch_close(s, &rel);
+  if (totals) totals[6] = rel;
+  return rc;
 }
 }

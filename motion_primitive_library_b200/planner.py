@@ -247,6 +247,12 @@ def _host():
     lib.mplh_last_error.restype = C.c_char_p
     lib.mplh_plan_batch.argtypes = [C.POINTER(PlanArgs), C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
     lib.mplh_plan_batch.restype = C.c_int
+    lib.mplh_batch_open.argtypes = [C.POINTER(PlanArgs)]
+    lib.mplh_batch_open.restype = C.c_void_p
+    lib.mplh_batch_plan.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_double, C.c_int, C.c_void_p, C.c_void_p]
+    lib.mplh_batch_plan.restype = C.c_int
+    lib.mplh_batch_close.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
+    lib.mplh_batch_close.restype = C.c_int
     return lib, fn
 
 
@@ -273,3 +279,51 @@ def plan_batch(args, starts, goals):
         res[q] = (out[q].valid, out[q].cost, out[q].expanded, out[q].n_closed, out[q].n_actions)
     return res, dict(iterations=int(totals[0]), nodes=int(totals[1]), seconds=float(totals[2]), t_pop=float(totals[3]),
                      t_device=float(totals[4]), t_relax=float(totals[5]), t_release=float(totals[6]))
+
+
+_QRES = [("valid", "i4"), ("cost", "f8"), ("expanded", "i4"), ("n_closed", "i4"), ("n_actions", "i4")]
+
+
+class BatchPlanner:
+    """A MPL::MultiQueryPlanner session: the map is uploaded once, and the search states of one query set
+    are recycled for the next (a planner that answers batch after batch allocates its state memory once).
+    `args` supplies the map, the controls and the limits (its start/goal are ignored)."""
+
+    def __init__(self, args):
+        self._lib, _ = _host()
+        self._args = args  # keeps the arrays the struct points at alive
+        self._h = self._lib.mplh_batch_open(C.byref(args))
+        if not self._h:
+            raise RuntimeError(self._lib.mplh_last_error().decode())
+
+    def plan(self, starts, goals, eps=None, max_num=None):
+        starts = np.ascontiguousarray(starts, dtype=WAYPOINT_DTYPE)
+        goals = np.ascontiguousarray(goals, dtype=WAYPOINT_DTYPE)
+        nq = len(starts)
+        out = (QueryResult * max(nq, 1))()
+        totals = np.zeros(7)
+        rc = self._lib.mplh_batch_plan(self._h, starts.ctypes.data, goals.ctypes.data, nq,
+                                       self._args.eps if eps is None else eps,
+                                       self._args.max_num if max_num is None else max_num, out, totals.ctypes.data)
+        if rc != 0:
+            raise RuntimeError(self._lib.mplh_last_error().decode())
+        res = np.zeros(nq, dtype=_QRES)
+        for q in range(nq):
+            res[q] = (out[q].valid, out[q].cost, out[q].expanded, out[q].n_closed, out[q].n_actions)
+        return res, dict(iterations=int(totals[0]), nodes=int(totals[1]), seconds=float(totals[2]), t_pop=float(totals[3]),
+                         t_device=float(totals[4]), t_relax=float(totals[5]), t_release=0.0)
+
+    def close(self) -> float:
+        """Free the session (incl. the kept search states); returns the seconds that took."""
+        if not self._h:
+            return 0.0
+        rel = C.c_double(0.0)
+        self._lib.mplh_batch_close(self._h, C.byref(rel))
+        self._h = None
+        return rel.value
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -23,7 +23,7 @@ def main():
     ap.add_argument("--cells", type=int, default=512)
     ap.add_argument("--min-dist", type=float, default=20.0)
     ap.add_argument("--ref-queries", type=int, default=256)
-    ap.add_argument("--repeat", type=int, default=1)
+    ap.add_argument("--repeat", type=int, default=2)
     args = ap.parse_args()
     rank, local, world = (int(os.environ.get(k, d)) for k, d in (("RANK", "0"), ("LOCAL_RANK", "0"), ("WORLD_SIZE", "1")))
     import torch
