@@ -45,6 +45,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-multi-query", action="store_true", help="skip the cfg5 leg (sharded many-query planning)")
+    ap.add_argument("--no-replay", action="store_true", help="skip the replay-frontier batch sweep")
     ap.add_argument("--mq-queries", type=int, default=4096)
     ap.add_argument("--mq-max-expand", type=int, default=300)
     ap.add_argument("--kernel", type=int, default=0,
@@ -349,6 +350,64 @@ def run_cfg5_workload(args, rank, local, world):
         dist.destroy_process_group()
 
 
+def replay_sweep(env, sc, lib, stream, local, max_nodes=65536):
+    """Record the pop order of one long A* query on the workload's map (MPL::MapPlanner::plan with the GPU env,
+    speculative batches of 64), then re-expand that sequence through mplx_expand_device in batches of
+    B = 1, 256, 4096, 65536 nodes (inputs resident in HBM, CUDA events on the launching stream): the pure
+    expansion rate on the frontier a search really produces, and how it depends on the batch size."""
+    import torch
+
+    from motion_primitive_library_b200 import abi, planner
+    from motion_primitive_library_b200.abi import SuccOut
+
+    pts = sc.frontier(64, seed=3, max_steps=0)["pos"]
+    d = np.abs(pts[:, None, :] - pts[None, :, :]).max(-1)
+    i, j = np.unravel_index(np.argmax(d), d.shape)  # the farthest pair of the sample: a long search
+    a = planner.make_args(sc.Dim, sc.control, sc.grid(), sc.dim_cells, sc.origin, sc.res, sc.U, start=dict(pos=pts[i]),
+                          goal=dict(pos=pts[j]), v_max=sc.v_max, a_max=sc.a_max, T=sc.T, w=sc.w, max_num=max_nodes, speculate=64)
+    a.device = local
+    t0 = time.perf_counter()
+    tr = planner.plan_trace(a, cap=max_nodes)
+    plan_s = time.perf_counter() - t0
+    trace = tr["trace"]
+    n, nU = len(trace), sc.nU
+    if n < 256:
+        return {"nodes": int(n), "note": "query solved too quickly for a sweep"}
+    d_nodes = torch.from_numpy(np.ascontiguousarray(trace).view(np.uint8).reshape(n, 112)).cuda()
+    bmax = min(n, 65536)
+    slots = bmax * nU
+    d_count = torch.empty(bmax, dtype=torch.int32, device="cuda")
+    d_succ = torch.empty((slots, 112), dtype=torch.uint8, device="cuda")
+    d_cost = torch.empty(slots, dtype=torch.float64, device="cuda")
+    d_action = torch.empty(slots, dtype=torch.int32, device="cuda")
+    d_key = torch.empty(slots, dtype=torch.int64, device="cuda")
+    out_d = SuccOut(d_count.data_ptr(), d_succ.data_ptr(), d_cost.data_ptr(), d_action.data_ptr(), d_key.data_ptr(), None)
+    stream.wait_stream(torch.cuda.current_stream())
+    res = {}
+    for B in (1, 256, 4096, 65536):
+        if B > n:
+            continue
+        total = min(n, 2048 if B == 1 else n) // B * B  # bound the single-node case
+        def run_once():
+            for off in range(0, total, B):
+                abi.check(lib.mplx_expand_device(env.handle, d_nodes.data_ptr() + off * 112, B, C.byref(out_d), stream.cuda_stream))
+        run_once()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = 3
+        e0.record(stream)
+        for _ in range(reps):
+            run_once()
+        e1.record(stream)
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / reps
+        res[str(B)] = {"expansions_per_s": total / (ms * 1e-3), "us_per_batch": 1e3 * ms / (total // B), "nodes": int(total)}
+    return {"nodes": int(n), "query": {"expanded": int(tr["expanded"]), "valid": int(tr["valid"]), "plan_seconds": plan_s,
+                                        "speculate": 64},
+            "batch_sweep": res,
+            "what": "A* pop order of one long query (MPL::MapPlanner::plan, GPU env) replayed through mplx_expand_device"}
+
+
 def kernel_name(which, sc, n_nodes):
     """The kernel mplx_set_kernel(which) launches for this workload (auto rule: mplx_kernels.cu launch_expand)."""
     names = {1: "mplx::expand_seq_kernel", 2: "mplx::expand_reg_kernel", 3: "mplx::expand_flat_kernel", 4: "mplx::expand_deal_kernel"}
@@ -551,6 +610,11 @@ def main():
                     "ms_per_step": 1e3 * secs / max(3, e2e_steps // 2), "launches": int(launches),
                     "call": "mplx_expand: full get_succ contract, 132 B per successor slot, +inf kept"}
 
+    # ---- replay frontier (SURVEY.md §8d i): the nodes a real A* pops, re-expanded in batches of B ----
+    replay = None
+    if not args.no_replay and rank == 0 and args.workload in ("512c_acc27", "cfg2"):
+        replay = replay_sweep(env, sc, lib, stream, local)
+
     # ---- cfg5 leg: the path's actual multi-GPU split — 4096 start/goal queries sharded over the ranks ----
     multi_query = None
     if not args.no_multi_query and args.workload == "512c_acc27":
@@ -603,7 +667,7 @@ def main():
         "dtype": "f64", "data": "synthetic",
         "config": config_dict(sc, n, world), "primitives_per_sec": value * nU, "parity_checked": parity_checked,
         "clocks": clocks, "numa": numa, "e2e": e2e, "e2e_state_records": e2e_state, "e2e_full_contract": e2e_full, "gpu_launches": int(gpu_launches),
-        "roofline": roofline, "multi_query": multi_query,
+        "roofline": roofline, "replay": replay, "multi_query": multi_query,
         "cpu_baseline": cpu_baseline,
     }
     print(json.dumps(line), flush=True)

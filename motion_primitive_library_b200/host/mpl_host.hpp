@@ -562,6 +562,9 @@ class env_map_gpu : public env_map_host<Dim> {
   void set_control(int control) { control_ = control; this->touch(); }
   /// nodes speculatively expanded per launch (1 = plain one-node get_succ)
   void set_speculation(int k) { speculate_ = std::max(1, k); }
+  /// record the node of every get_succ call, in call order = the A* pop order (graph_search.h:66-75);
+  /// the replay frontier of the benchmark (SURVEY.md §8d i)
+  void set_trace(std::vector<mplx_waypoint> *trace) { trace_ = trace; }
 
   void begin_plan() const override { cache_.clear(); stats_nodes_ = stats_calls_ = stats_hits_ = 0; }
 
@@ -570,6 +573,7 @@ class env_map_gpu : public env_map_host<Dim> {
                 std::vector<int> &action_idx) const override {
     succ.clear(); succ_cost.clear(); action_idx.clear();
     this->expanded_nodes_.push_back(curr.pos);  // env_map.h:154, at real pop time
+    if (trace_) trace_->push_back(to_pod(curr));
     const std::size_t key = hash_value(curr);
     auto it = cache_.find(key);
     if (it == cache_.end()) {
@@ -828,6 +832,7 @@ class env_map_gpu : public env_map_host<Dim> {
   }
 
   mplx_ctx *ctx_ = nullptr;
+  std::vector<mplx_waypoint> *trace_ = nullptr;
   int control_ = Control::NONE, speculate_ = 1;
   mutable bool potential_on_device_ = false, region_on_device_ = false;
   std::vector<int8_t> potential_map_;

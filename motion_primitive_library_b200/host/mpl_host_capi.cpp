@@ -41,6 +41,37 @@ int mplh_plan(const mplh_plan_args *a, mplh_plan_result *r, uint64_t *closed_key
   }
 }
 
+/* mplh_plan that also returns the nodes A* expanded, in pop order (graph_search.h:66-75): the replay
+ * frontier of the benchmark.  *n_trace = nodes recorded (<= cap_trace). */
+int mplh_plan_trace(const mplh_plan_args *a, mplh_plan_result *r, mplx_waypoint *trace, int cap_trace, int32_t *n_trace) {
+  try {
+    *r = mplh_plan_result{};
+    std::vector<mplx_waypoint> tr;
+    auto go = [&](auto dimtag) {
+      constexpr int Dim = decltype(dimtag)::value;
+      MPL::MapPlanner<Dim> planner(false);
+      planner.setMapUtil(mplh::make_map<Dim>(a), a->device);
+      planner.setControl(a->control);
+      planner.setSpeculation(a->speculate);
+      planner.gpu_env()->set_trace(&tr);
+      std::vector<uint64_t> closed(1);
+      std::vector<int32_t> actions(1);
+      mplh::run<Dim>(planner, a, r, closed.data(), 0, actions.data(), 0);
+      planner.gpu_env()->set_trace(nullptr);
+    };
+    if (a->dim == 2) go(std::integral_constant<int, 2>());
+    else if (a->dim == 3) go(std::integral_constant<int, 3>());
+    else { g_err = "dim must be 2 or 3"; return 1; }
+    const int n = (int)std::min<std::size_t>(tr.size(), (std::size_t)cap_trace);
+    for (int i = 0; i < n; i++) trace[i] = tr[i];
+    if (n_trace) *n_trace = n;
+    return 0;
+  } catch (const std::exception &e) {
+    g_err = e.what();
+    return 2;
+  }
+}
+
 /* MapPlanner::plan() with the GPU env, then the recovered Trajectory (include/mpl_basis/trajectory.h):
  * sample(N), getTotalTime / J / Jyaw, getWaypoints and evaluate(t); layouts in plan_capi.hpp. */
 int mplh_plan_trajectory(const mplh_plan_args *a, int N, mplh_plan_result *r, double *samples, double *totals,

@@ -262,6 +262,22 @@ def plan(args):
     return run_plan(fn, lib, args)
 
 
+def plan_trace(args, cap=1 << 20):
+    """plan() with the GPU env, returning also the expanded nodes in A* pop order (WAYPOINT_DTYPE array)."""
+    lib, _ = _host()
+    lib.mplh_plan_trace.argtypes = [C.POINTER(PlanArgs), C.POINTER(PlanResult), C.c_void_p, C.c_int, C.POINTER(C.c_int32)]
+    lib.mplh_plan_trace.restype = C.c_int
+    r = PlanResult()
+    trace = np.zeros(cap, dtype=WAYPOINT_DTYPE)
+    n = C.c_int32(0)
+    rc = lib.mplh_plan_trace(C.byref(args), C.byref(r), trace.ctypes.data, cap, C.byref(n))
+    if rc != 0:
+        raise RuntimeError(lib.mplh_last_error().decode())
+    out = {k: getattr(r, k) for k, _ in PlanResult._fields_}
+    out["trace"] = trace[: n.value].copy()
+    return out
+
+
 def plan_batch(args, starts, goals):
     """MPL::MultiQueryPlanner: lock-step A* over many (start, goal) pairs; one device launch per
     iteration expands the current node of every live query.  starts/goals: WAYPOINT_DTYPE arrays."""

@@ -104,3 +104,21 @@ def reference_search_region(args, path, radius, n_cells, dense=False):
     lib.refp_set_search_region(C.byref(args), path.ctypes.data, len(path), rad.ctypes.data, 1 if dense else 0,
                                out.ctypes.data)
     return out
+
+
+REF_B200 = ROOT / "oracle" / "_ref" / "libmplref_b200.so"
+
+
+def ref_b200_available():
+    return REF_B200.exists()
+
+
+def plan_reference_b200(args):
+    """The REFERENCE's MapPlanner<Dim>::plan() with integration/env_map_b200.h (libmplx behind the
+    reference's virtual get_succ) installed through the virtual setMapUtil — the drop-in of INTEGRATION.md."""
+    import ctypes as C
+
+    lib, fn = load_fn(REF_B200, "refb_plan")
+    lib.refb_last_error.restype = C.c_char_p
+    lib.mplh_last_error = lib.refb_last_error
+    return run_plan(fn, lib, args)
