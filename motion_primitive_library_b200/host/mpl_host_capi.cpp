@@ -18,7 +18,7 @@ int mplh_plan(const mplh_plan_args *a, mplh_plan_result *r, uint64_t *closed_key
       MPL::MapPlanner<Dim> planner(false);
       planner.setMapUtil(mplh::make_map<Dim>(a), a->device);  // installs env_map_gpu (map_planner.cpp:14-18)
       planner.setControl(a->control);
-      planner.setSpeculation(a->speculate);
+      if (a->speculate > 0) planner.setSpeculation(a->speculate);  // 0 = the library default
       if (a->potential) {
         size_t n = 1;
         for (int k = 0; k < Dim; k++) n *= (size_t)a->mdim[k];
@@ -52,7 +52,7 @@ int mplh_plan_trace(const mplh_plan_args *a, mplh_plan_result *r, mplx_waypoint 
       MPL::MapPlanner<Dim> planner(false);
       planner.setMapUtil(mplh::make_map<Dim>(a), a->device);
       planner.setControl(a->control);
-      planner.setSpeculation(a->speculate);
+      if (a->speculate > 0) planner.setSpeculation(a->speculate);  // 0 = the library default
       planner.gpu_env()->set_trace(&tr);
       std::vector<uint64_t> closed(1);
       std::vector<int32_t> actions(1);
@@ -83,7 +83,7 @@ int mplh_plan_trajectory(const mplh_plan_args *a, int N, mplh_plan_result *r, do
       MPL::MapPlanner<Dim> planner(false);
       planner.setMapUtil(mplh::make_map<Dim>(a), a->device);
       planner.setControl(a->control);
-      planner.setSpeculation(a->speculate);
+      if (a->speculate > 0) planner.setSpeculation(a->speculate);  // 0 = the library default
       mplh::run_trajectory<Dim>(planner, a, N, r, samples, totals, waypoints, cap_wp, n_wp, mids);
     };
     if (a->dim == 2) go(std::integral_constant<int, 2>());
@@ -111,7 +111,7 @@ int mplh_iterative_plan(const mplh_plan_args *a, const double *search_radius, in
       MPL::MapPlanner<Dim> planner(false);
       planner.setMapUtil(mplh::make_map<Dim>(a), a->device);
       planner.setControl(a->control);
-      planner.setSpeculation(a->speculate);
+      if (a->speculate > 0) planner.setSpeculation(a->speculate);  // 0 = the library default
       if (a->potential) {
         size_t n = 1;
         for (int k = 0; k < Dim; k++) n *= (size_t)a->mdim[k];
@@ -145,7 +145,7 @@ int mplh_lpa_run(const mplh_plan_args *a, const mplh_lpa_step *steps, int n_step
       auto mu = mplh::make_map<Dim>(a);
       planner.setMapUtil(mu, a->device);
       planner.setControl(a->control);
-      planner.setSpeculation(a->speculate);
+      if (a->speculate > 0) planner.setSpeculation(a->speculate);  // 0 = the library default
       mplh::run_lpa<Dim>(planner, mu, a, steps, n_steps, outs, actions, cap_actions);
     };
     if (a->dim == 2) go(std::integral_constant<int, 2>());
