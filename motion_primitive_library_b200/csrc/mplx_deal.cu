@@ -97,6 +97,7 @@ expand_deal_kernel(const __grid_constant__ EnvParams P, const mplx_waypoint *__r
   const int total = n_front + q_short;
   double cf[CoefLayout<DIM, ORD, YAW>::NCMAX];
   double dt = 0.0, t = 0.0, c = 0.0, intrinsic = 0.0;
+  YawRot yr;
   unsigned slot = 0, n_samples = 0;
   int left = 0;  // iterations of the reference's sample loop still to visit
   bool have = false, dry = false;
@@ -129,13 +130,14 @@ expand_deal_kernel(const __grid_constant__ EnvParams P, const mplx_waypoint *__r
           slot = tk.slot;
           t = 0.0;
           c = 0.0;
+          if (YAW) yr.init(pr.yaw_u, pr.yaw0, dt);
           have = true;
         }
       }
     }
     if (!__any_sync(0xffffffffu, have)) break;
     if (have) {
-      const int st = sample_group<DIM, ORD, YAW, UNR>(P, cf, VEL, dt, left, t, c, n_samples);
+      const int st = sample_group<DIM, ORD, YAW, UNR>(P, cf, VEL, dt, left, t, c, n_samples, yr);
       left -= UNR;
       if (st != 0) {
         if (o.cost) o.cost[slot] = st == 2 ? (double)INFINITY : c + intrinsic;

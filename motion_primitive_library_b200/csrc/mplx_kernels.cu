@@ -83,8 +83,10 @@ __device__ __forceinline__ double traverse_groups(const EnvParams &P, const doub
                                                  bool need_vel, double dt, int count, unsigned &n_samples) {
   double c = 0;
   double t = 0;
+  YawRot yr;
+  if (YAW) yr.init(cf[CoefLayout<DIM, ORD, YAW>::ncoef(need_vel) - 2], cf[CoefLayout<DIM, ORD, YAW>::ncoef(need_vel) - 1], dt);
   for (int left = count;; left -= UNR) {
-    const int st = sample_group<DIM, ORD, YAW, UNR>(P, cf, need_vel, dt, left, t, c, n_samples);
+    const int st = sample_group<DIM, ORD, YAW, UNR>(P, cf, need_vel, dt, left, t, c, n_samples, yr);
     if (st == 2) return INFINITY;
     if (st == 1) return c;
   }

@@ -34,7 +34,7 @@ def test_reference_planner_on_b200_env_config1_corridor():
         a = pb.make_args(2, ACC, c["grid"], c["dim"], c["origin"], c["res"], fixtures.U_2d(), start=dict(pos=c["start"]),
                          goal=dict(pos=c["goal"]), v_max=1.0, a_max=1.0, eps=eps)
         ref = pb.plan_reference(a)
-        assert ref["valid"] == 1 and ref["n_closed"] > 100
+        assert ref["valid"] == 1 and ref["n_closed"] > 50
         same(pb.plan_reference_b200(a), ref)
 
 
