@@ -68,10 +68,16 @@ def make_env(sc, device):
     e.set_a_max(sc.a_max)
     e.set_j_max(sc.j_max)
     e.set_yaw_max(sc.yaw_max)
-    if sc.potential() is not None:
+    if sc.potential_radius is not None:
         e.set_potential_weight(sc.potential_weight)
         e.set_gradient_weight(sc.gradient_weight)
-        e.set_potential_map(sc.potential())
+        if sc._pot is None:
+            # MapPlanner::updatePotentialMap on the device (mplx_update_potential_map; bit-exact against the
+            # reference's own function, tests/test_maps_gpu.py) — the scipy generator of scenarios.py needs
+            # minutes at 512^3.  The CPU arms receive this very field as their potential_map_.
+            sc._pot = e.update_potential_map(sc.potential_radius).copy()
+        else:
+            e.set_potential_map(sc.potential())
     e._sync_params()
     return e
 

@@ -11,6 +11,8 @@
 // walks the reference's loop four samples at a time (sample_group), writes the cost, and pulls the next ticket
 // while its neighbours are still busy.  Results are identical to the other kernels (the order in
 // which primitives are sampled does not enter any result).
+#include <stdlib.h>
+
 #include "mplx_expand.cuh"
 
 namespace mplx {
@@ -162,7 +164,8 @@ static cudaError_t launch_deal_t(const EnvParams &P, const mplx_waypoint *d_node
   const int grid = (n_nodes + per_cta - 1) / per_cta;
   const size_t smem = (size_t)rounds * kThreads * sizeof(Ticket);
   const bool nv = YAW || (P.pot != nullptr && P.grad_w != 0.0);
-  const bool short_loops = P.maxn <= 15;
+  static const int unr_env = [] { const char *v = getenv("MPLX_DEAL_UNR"); return v ? atoi(v) : 0; }();  // tuning
+  const bool short_loops = unr_env ? unr_env == 2 : P.maxn <= 15;
   const bool lat = o.lattice != nullptr;
 #define MPLX_LAUNCH_DEAL(VEL, UNR, LAT) \
   expand_deal_kernel<DIM, ORD, YAW, VEL, UNR, 4, LAT><<<grid, kThreads, smem, st>>>(P, d_nodes, n_nodes, npb, o, rounds)

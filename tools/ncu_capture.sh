@@ -1,12 +1,15 @@
 #!/bin/bash
-# ncu --set full captures of the dominant kernels, skipping bench.py's first launch (the one with the
-# stats counters enabled, which adds shared-memory atomics).  Run through gpurun; reports land in gpurun_out/.
-R=${1:-r01}
+# ncu --set full captures of the dominant kernels, skipping bench.py's first launches (the stats pass and the
+# parity spot check).  Run through gpurun; reports land in gpurun_out/.
+R=${1:-r02}
 mkdir -p gpurun_out
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:expand_reg_kernel --launch-skip 2 --launch-count 1 -f \
-  -o gpurun_out/prof_${R}_reg python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/${R}_ncu_reg.log 2>&1
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:expand_deal_kernel --launch-skip 2 --launch-count 1 -f \
-  -o gpurun_out/prof_${R}_deal_cfg3 python bench.py --workload cfg3 --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/${R}_ncu_deal.log 2>&1
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:expand_reg_kernel --launch-skip 2 --launch-count 1 -f \
-  -o gpurun_out/prof_${R}_reg_cfg3 python bench.py --workload cfg3 --kernel 2 --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/${R}_ncu_reg_cfg3.log 2>&1
+cap() { # name, kernel regex, bench args...
+  local name=$1 rx=$2; shift 2
+  timeout 900 ncu --set full --clock-control none --import-source on -k regex:$rx --launch-skip 2 --launch-count 1 -f \
+    -o gpurun_out/prof_${R}_${name} python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-e2e --no-multi-query --no-replay "$@" > gpurun_out/${R}_ncu_${name}.log 2>&1
+}
+cap fxn_headline expand_fxn_kernel
+cap fxn_cfg2 expand_fxn_kernel --workload cfg2
+cap fxn_cfg3 expand_fxn_kernel --workload cfg3
+cap deal_cfg4 expand_deal_kernel --workload cfg4
 ls -la gpurun_out/*.ncu-rep
