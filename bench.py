@@ -33,6 +33,17 @@ S_IN = 112  # bytes of one frontier node (3-D Waypoint payload)
 S_OUT = 132  # bytes of one successor record: 112 Waypoint + 8 cost + 4 action + 8 key
 
 
+def emit(line: dict) -> None:
+    """Print the JSON line as the LAST line of stdout: the reference planner (oracle/_ref) printf()s its own
+    messages through C stdio, whose buffer would otherwise be flushed after Python's at exit."""
+    try:
+        C.CDLL(None).fflush(None)
+    except Exception:
+        pass
+    sys.stdout.flush()
+    print(json.dumps(line), flush=True)
+
+
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -246,7 +257,7 @@ def run_reference(args, sc, rank, world):
                          "sample": f"{per_step} frontier nodes/step x {args.steps} steps; {arm.describe(threads)}"},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def parity_spot_check(env, sc, nodes):
@@ -302,7 +313,7 @@ def run_cfg5_workload(args, rank, local, world):
             if it >= args.warmup:
                 vals.append(sum(o["n_closed"] for o in outs) / (sum(o["seconds"] for o in outs) / min(nt, n)))
         v = float(np.mean(vals))
-        print(json.dumps({"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus,
+        emit({"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus,
                           "steps": args.steps, "warmup": args.warmup, "ms_per_step": None, "higher_is_better": True,
                           "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                           "config": {"workload": "cfg5", "queries": args.mq_queries, "max_expand": args.mq_max_expand,
@@ -310,7 +321,7 @@ def run_cfg5_workload(args, rank, local, world):
                           "cpu_baseline": {"value": v, "unit": UNIT, "cores": nt, "kind": "reference",
                                            "sample": f"{n} of the {args.mq_queries} queries per step, one reference MapPlanner::plan per "
                                                      f"host thread, time inside plan() only"},
-                          "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}), flush=True)
+                          "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
         return
     import torch
     import torch.distributed as dist
@@ -351,7 +362,7 @@ def run_cfg5_workload(args, rank, local, world):
                         "note": "the value IS end to end: every iteration copies the popped nodes to the device and the "
                                 "{key, action} records of their successors back"},
                 "roofline": None, "cpu_baseline": None}
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
@@ -676,7 +687,7 @@ def main():
         "roofline": roofline, "replay": replay, "multi_query": multi_query,
         "cpu_baseline": cpu_baseline,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 
