@@ -41,7 +41,8 @@ def emit(line: dict) -> None:
     except Exception:
         pass
     sys.stdout.flush()
-    print(json.dumps(line), flush=True)
+    # the reference's messages end with an ANSI reset and no newline: start a fresh line for the JSON
+    print("\n" + json.dumps(line), flush=True)
 
 
 def parse():
@@ -507,10 +508,10 @@ def main():
     # ---- untimed spot check: a slice of the very frontier that is timed, against the CPU checker ----
     parity_checked = parity_spot_check(env, sc, nodes_np[: min(n, 4096)])
 
-    launches0 = env.launch_count()
     for _ in range(args.warmup):
         step_device()
     torch.cuda.synchronize()
+    launches0 = env.launch_count()
     if world > 1:
         dist.barrier()
     sampler = ClockSampler(local)
@@ -528,7 +529,7 @@ def main():
     clocks = sampler.stop() if rank == 0 else None
     elapsed_ms = ev[0].elapsed_time(ev[-1])
     kernel_ms = [ev[k].elapsed_time(ev[k + 1]) for k in range(args.steps)]
-    gpu_launches = env.launch_count() - launches0 - args.warmup
+    gpu_launches = env.launch_count() - launches0  # kernels of this library launched inside the timed region
     t_el = torch.tensor([elapsed_ms], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t_el, op=dist.ReduceOp.MAX)

@@ -41,6 +41,7 @@ static void refresh_params(mplx_ctx *c) {
   c->P.stats = c->stats_on ? c->stats.p : nullptr;
   c->P.occ_bits = c->has_map ? c->occ.p : nullptr;
   c->P.occ2 = c->has_map ? c->occ2.p : nullptr;
+  c->P.occ2_bytes = c->has_map ? c->occ2_window : 0;
   c->P.prow = c->prow.p;
   c->P.row_u = c->row_u.p;
   c->P.row_axis = c->row_axis.p;
@@ -141,6 +142,21 @@ int mplx_set_map(mplx_ctx *c, const int8_t *data, const int32_t *dim, const doub
   CU(c->occ2.reserve((nvox + 31) / 32));
   CU(mplx::launch_pack_occ2(c->occ.p, nvox, c->dim, dim[0], dim[1], c->occ2.p, c->stream));
   c->launches += 2;
+  {
+    // L2 persisting carve-out for the bitmap pairs (up to what the device grants): see launch_fxn_t
+    const size_t bytes = ((nvox + 31) / 32) * sizeof(uint2);
+    int maxp = 0, maxw = 0;
+    cudaDeviceGetAttribute(&maxp, cudaDevAttrMaxPersistingL2CacheSize, c->device);
+    cudaDeviceGetAttribute(&maxw, cudaDevAttrMaxAccessPolicyWindowSize, c->device);
+    c->occ2_window = 0;
+    if (maxp > 0 && maxw > 0) {
+      const size_t want = bytes < (size_t)maxp ? bytes : (size_t)maxp;
+      if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want) == cudaSuccess)
+        c->occ2_window = bytes < (size_t)maxw ? bytes : (size_t)maxw;
+      else
+        cudaGetLastError();
+    }
+  }
   CU(cudaStreamSynchronize(c->stream));
   c->nvox = nvox;
   for (int k = 0; k < 3; k++) {

@@ -37,6 +37,7 @@ struct EnvParams {
   int maxn;                    // largest n the flat sample phase accepts (<= kNMax)
   // {occupancy word, candidate-summary word} per 32 voxels for the fixed-point kernel (mplx_fx.cu)
   const uint2 *occ2;
+  size_t occ2_bytes;  // size of occ2 when an L2 persisting carve-out was granted for it, else 0
   // Per-axis value tables of U for the node-cooperative kernel (mplx_fx.cu): the distinct values of
   // U[.][a] (bitwise) of all axes listed one after the other as "rows"; U[i][a] == row_u[prow[3*i+a]].
   const unsigned char *prow;      // [nU*3]

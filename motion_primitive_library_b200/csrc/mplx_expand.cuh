@@ -193,19 +193,32 @@ __device__ __forceinline__ bool validate_yaw(const EnvParams &P, const PrimState
 // One successor Waypoint (112 bytes = 7 x 16) to global memory as seven 16-byte stores when the
 // destination allows it (cudaMalloc'ed arrays always do): half the store instructions and half the
 // partial-sector writes of fourteen 8-byte stores at a 112-byte stride between lanes.
+// The stores are streaming (st.global.cs): the 132-byte records are written once and never read by the
+// kernel, and at ~0.9 GB per launch they would otherwise sweep the voxel bitmaps out of the L2.
 __device__ __forceinline__ void store_waypoint(mplx_waypoint *dst, const mplx_waypoint &w) {
   if ((reinterpret_cast<uintptr_t>(dst) & 15u) == 0) {
     double2 *d = reinterpret_cast<double2 *>(dst);
-    d[0] = make_double2(w.pos[0], w.pos[1]);
-    d[1] = make_double2(w.pos[2], w.vel[0]);
-    d[2] = make_double2(w.vel[1], w.vel[2]);
-    d[3] = make_double2(w.acc[0], w.acc[1]);
-    d[4] = make_double2(w.acc[2], w.jrk[0]);
-    d[5] = make_double2(w.jrk[1], w.jrk[2]);
-    d[6] = make_double2(w.yaw, w.t);
+    __stcs(d + 0, make_double2(w.pos[0], w.pos[1]));
+    __stcs(d + 1, make_double2(w.pos[2], w.vel[0]));
+    __stcs(d + 2, make_double2(w.vel[1], w.vel[2]));
+    __stcs(d + 3, make_double2(w.acc[0], w.acc[1]));
+    __stcs(d + 4, make_double2(w.acc[2], w.jrk[0]));
+    __stcs(d + 5, make_double2(w.jrk[1], w.jrk[2]));
+    __stcs(d + 6, make_double2(w.yaw, w.t));
   } else {
     *dst = w;
   }
+}
+// L2 policy for the words that should stay: the voxel bitmaps (re-read by every CTA of every launch)
+__device__ __forceinline__ unsigned long long l2_keep_policy() {
+  unsigned long long p;
+  asm("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ unsigned ldg_keep(const unsigned *a, unsigned long long pol) {
+  unsigned v;
+  asm volatile("ld.global.nc.L2::cache_hint.u32 %0, [%1], %2;" : "=r"(v) : "l"(a), "l"(pol));
+  return v;
 }
 
 struct OutPtrs {
@@ -341,8 +354,8 @@ __device__ __forceinline__ void phase_ab(const EnvParams &P, const mplx_waypoint
     if (emit) {
       slot = (size_t)ni * nU + rank;
       if (o.succ) store_waypoint(o.succ + slot, tn);
-      if (o.action) o.action[slot] = ci;
-      if (o.key) o.key[slot] = key;
+      if (o.action) __stcs(o.action + slot, ci);
+      if (o.key) __stcs(reinterpret_cast<unsigned long long *>(o.key + slot), (unsigned long long)key);
       if (LAT && o.lattice) {
 #pragma unroll
         for (int q = 0; q < MPLX_LATTICE_MAX; q++) o.lattice[slot * MPLX_LATTICE_MAX + q] = lat[q];

@@ -206,8 +206,8 @@ expand_fx_kernel(const __grid_constant__ EnvParams P, const mplx_waypoint *__res
     if (emit) {
       slot = (size_t)ni * nU + rank;
       if (o.succ) store_waypoint(o.succ + slot, tn);
-      if (o.action) o.action[slot] = ci;
-      if (o.key) o.key[slot] = key;
+      if (o.action) __stcs(o.action + slot, ci);
+      if (o.key) __stcs(reinterpret_cast<unsigned long long *>(o.key + slot), (unsigned long long)key);
       if (LAT && o.lattice) {
 #pragma unroll
         for (int q = 0; q < MPLX_LATTICE_MAX; q++) o.lattice[slot * MPLX_LATTICE_MAX + q] = lat[q];

@@ -17,6 +17,8 @@
 //    covered by the next group's arithmetic.
 // Ambiguous primitives (an uncertain sample next to an obstacle surface, ~5 %) are appended to a queue
 // in global memory and re-evaluated with the exact FP64 chain by fx_resolve_kernel afterwards.
+#include <string.h>
+
 #include "mplx_fx.cuh"
 
 namespace mplx {
@@ -268,8 +270,8 @@ expand_fxn_kernel(const __grid_constant__ EnvParams P, const mplx_waypoint *__re
     }
     if (emit) {
       slot = (size_t)ni * nU + rank;
-      if (o.action) o.action[slot] = ci;
-      if (o.key) o.key[slot] = key;
+      if (o.action) __stcs(o.action + slot, ci);
+      if (o.key) __stcs(reinterpret_cast<unsigned long long *>(o.key + slot), (unsigned long long)key);
       if (LAT && o.lattice) {
         int q = 0;
 #pragma unroll
@@ -393,7 +395,7 @@ expand_fxn_kernel(const __grid_constant__ EnvParams P, const mplx_waypoint *__re
     unsigned ns = 0;
     verdict = isinf(traverse_loop<DIM, ORD, false>(P, cf, false, mv, ns)) ? 1 : 0;
   }
-  if ((verdict == 0 || verdict == 1) && o.cost) o.cost[wslot] = verdict == 1 ? (double)INFINITY : 0.0 + wintr;
+  if ((verdict == 0 || verdict == 1) && o.cost) __stcs(o.cost + wslot, verdict == 1 ? (double)INFINITY : 0.0 + wintr);
 }
 
 // Exact re-evaluation of the queued primitives: a thread rebuilds the exact quotients from (node,
@@ -462,6 +464,19 @@ static cudaError_t launch_fxn_t(const EnvParams &P, const mplx_waypoint *d_nodes
   const bool sort = sort_env >= 0 ? sort_env != 0 : ORD >= 3;
   cudaError_t e = cudaMemsetAsync(amb_n, 0, sizeof(unsigned) * kFxSegments, st);
   if (e != cudaSuccess) return e;
+  // Keep the voxel bitmaps in the L2's persisting carve-out: every CTA of every launch re-reads them while
+  // ~0.9 GB of successor records stream through the same cache (mplx_set_map sized the carve-out).
+  static const bool no_window = getenv("MPLX_NO_L2_WINDOW") != nullptr;  // tuning / A-B
+  if (!no_window && P.occ2_bytes > 0) {
+    cudaStreamAttrValue av;
+    memset(&av, 0, sizeof av);
+    av.accessPolicyWindow.base_ptr = const_cast<uint2 *>(P.occ2);
+    av.accessPolicyWindow.num_bytes = P.occ2_bytes;
+    av.accessPolicyWindow.hitRatio = 1.0f;
+    av.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+    av.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+    if (cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &av) != cudaSuccess) cudaGetLastError();
+  }
   static const int unr_env = [] { const char *v = getenv("MPLX_FXN_UNR"); return v ? atoi(v) : 0; }();    // tuning
   static const int minb_env = [] { const char *v = getenv("MPLX_FXN_MINB"); return v ? atoi(v) : 0; }();  // tuning
 #define MPLX_LAUNCH_FXN_S(UNR, MINB, LAT, REGION, SORT)                                                         \

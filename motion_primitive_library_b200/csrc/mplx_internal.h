@@ -144,7 +144,8 @@ struct mplx_ctx {
   DevBuf<uint2> occ2;
   DevBuf<unsigned char> prow, row_axis;  // per-axis value tables of U (EnvParams::prow ...)
   DevBuf<double> row_u;
-  int n_rows = 0;  // {occupancy, candidate summary} words of the fixed-point kernel
+  int n_rows = 0;
+  size_t occ2_window = 0;  // bytes of occ2 covered by the L2 access-policy window (0 = none)  // {occupancy, candidate summary} words of the fixed-point kernel
   DevBuf<double> U, ttab, tdt;
   DevBuf<int> tcount;
   int force_seq = 0;

@@ -301,9 +301,9 @@ static cudaError_t launch_t(const EnvParams &P, const mplx_waypoint *d_nodes, in
     // (n <= 15: a group of 4 would mostly run past the end of the loop)
     const bool short_loops = P.maxn <= 15;
     const bool lat = o.lattice != nullptr;
-    // MPLX_UNR8=1: groups of 8 samples for plain long-loop planning (measured 0.810 vs 0.828 ms on
-    // 512^3 ACC-27, no change on 256^3; opt-in until the round's artefacts are re-taken with it)
-    static const bool unr8 = getenv("MPLX_UNR8") != nullptr;
+    // groups of 8 samples for plain long-loop planning (measured 0.810 vs 0.828 ms on 512^3 ACC-27, no
+    // change on 256^3); MPLX_UNR4=1 restores groups of 4
+    static const bool unr8 = getenv("MPLX_UNR4") == nullptr;
 #define MPLX_LAUNCH_REG(VEL, UNR, LAT) \
   expand_reg_kernel<DIM, ORD, YAW, VEL, UNR, 4, LAT><<<grid, kThreads, 0, st>>>(P, d_nodes, n_nodes, npb, o)
     if (nv) {

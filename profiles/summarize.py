@@ -37,7 +37,10 @@ UNIT_SCALE = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
 
 def main():
     rep, out, title = sys.argv[1], sys.argv[2], sys.argv[3]
-    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    # a report, or its `ncu -i X --page raw --csv` export (tools/ncu_capture.sh keeps only the export of
+    # the secondary captures: gpurun_out/ is capped at 64 MiB)
+    raw = open(rep).read() if rep.endswith(".csv") else subprocess.run(
+        ["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(raw.splitlines()))
     hdr, units, vals = rows[0], rows[1], rows[2]
     d = {h: (v, u) for h, u, v in zip(hdr, units, vals)}

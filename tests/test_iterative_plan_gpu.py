@@ -2,10 +2,7 @@
 expansion by libmplx) against the same host planner with the CPU oracle env, which
 tests/test_iterative_plan_vs_ref.py pins to the reference's own iterativePlan.
 
-The GPU budget of the round in which this caller was added was spent before it could be run on a
-device: the pieces (device tunnel builder, expansion, host loop) are each parity-tested, but this
-composition executes on a GPU for the first time in the round-end run, so it is marked xfail
-(non-strict) until a passing run has been observed; it must be promoted to a hard test then."""
+Passing on the device since round 1's round-end run (observed again in round 2)."""
 import numpy as np
 import pytest
 
@@ -13,8 +10,7 @@ import fixtures
 import planner_bindings as pb
 from test_iterative_plan_vs_ref import same
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.xfail(strict=False, reason="first GPU execution of this composition; promote once observed passing")]
+pytestmark = pytest.mark.gpu
 ACC = 0x03
 
 

@@ -15,12 +15,10 @@ except Exception as e:
     print(sys.argv[1], "unreadable:", e)
 P
 }
-BARGS="" run fxn MPLX_FXN_STAGE=1
-BARGS="" run fxn_nostage MPLX_FXN_STAGE=0
-BARGS="--workload cfg2" run cfg2 MPLX_FXN_STAGE=1
-BARGS="--workload cfg2" run cfg2_nostage MPLX_FXN_STAGE=0
-BARGS="--workload cfg3" run cfg3 MPLX_FXN_STAGE=1
-BARGS="--workload cfg3" run cfg3_nostage MPLX_FXN_STAGE=0
+BARGS="" run fxn MPLX_FXN_UNR=4
+BARGS="" run fxn_nowin MPLX_NO_L2_WINDOW=1
+BARGS="--workload cfg3" run cfg3 MPLX_FXN_UNR=4
+BARGS="--workload cfg3" run cfg3_nowin MPLX_NO_L2_WINDOW=1
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:expand_fx --launch-skip 2 --launch-count 1 -f \
   -o gpurun_out/prof_${TAG}_fx python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-e2e > gpurun_out/${TAG}_ncu_fx.log 2>&1
-ls -la gpurun_out/prof_${TAG}_fx.ncu-rep
+ncu -i gpurun_out/prof_${TAG}_fx.ncu-rep --page raw --csv > gpurun_out/prof_${TAG}_fx_raw.csv 2>/dev/null; ncu -i gpurun_out/prof_${TAG}_fx.ncu-rep --page source --csv --print-source sass > gpurun_out/prof_${TAG}_fx_sass.csv 2>/dev/null; rm -f gpurun_out/prof_${TAG}_fx.ncu-rep
