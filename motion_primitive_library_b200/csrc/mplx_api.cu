@@ -114,7 +114,9 @@ int mplx_destroy(mplx_ctx *c) {
   c->map.release(); c->pot.release(); c->region.release(); c->U.release(); c->stats.release();
   c->prow.release(); c->row_axis.release(); c->row_u.release();
   c->occ.release(); c->occ2.release(); c->ttab.release(); c->tcount.release(); c->tdt.release();
-  c->cb[0].release(); c->cb[1].release(); c->eb.release(); c->fxq.release();
+  for (int b = 0; b < kPackBufs; b++) c->cb[b].release();
+  if (c->d2h_stream) cudaStreamDestroy(c->d2h_stream);
+  c->eb.release(); c->fxq.release();
   c->d_nodes.release(); c->d_succ.release(); c->d_count.release(); c->d_action.release();
   c->d_lattice.release(); c->d_cost.release(); c->d_key.release();
   c->h_nodes.release(); c->h_succ.release(); c->h_count.release(); c->h_action.release();

@@ -165,7 +165,9 @@ static cudaError_t launch_deal_t(const EnvParams &P, const mplx_waypoint *d_node
   const size_t smem = (size_t)rounds * kThreads * sizeof(Ticket);
   const bool nv = YAW || (P.pot != nullptr && P.grad_w != 0.0);
   static const int unr_env = [] { const char *v = getenv("MPLX_DEAL_UNR"); return v ? atoi(v) : 0; }();  // tuning
-  const bool short_loops = unr_env ? unr_env == 2 : P.maxn <= 15;
+  // groups of 2 samples when per-sample cost terms are summed (yaw alignment, gradient): groups of 4 spill
+  // ~220 B per thread there (cfg4: 2.00 -> 1.68 ms per 262 144 nodes), and for short loops
+  const bool short_loops = unr_env ? unr_env == 2 : (P.maxn <= 15 || nv);
   const bool lat = o.lattice != nullptr;
 #define MPLX_LAUNCH_DEAL(VEL, UNR, LAT) \
   expand_deal_kernel<DIM, ORD, YAW, VEL, UNR, 4, LAT><<<grid, kThreads, smem, st>>>(P, d_nodes, n_nodes, npb, o, rounds)

@@ -95,9 +95,11 @@ struct FxQueue {
 
 // One set of per-chunk device buffers + its stream: two sets let chunk k+1 compute while
 // chunk k's results cross PCIe (mplx_expand_packed).
+constexpr int kPackBufs = 4;  // chunk buffer sets of the packed pipeline
 struct ChunkBufs {
   cudaStream_t st = nullptr;
-  cudaEvent_t ready = nullptr;
+  cudaEvent_t ready = nullptr;    // the chunk's records are packed and its record count is on the host
+  cudaEvent_t drained = nullptr;  // the chunk's device-to-host copies have left the buffers
   DevBuf<mplx_waypoint> nodes, succ;
   DevBuf<int32_t> count, action;
   DevBuf<double> cost;
@@ -116,8 +118,9 @@ struct ChunkBufs {
     kcount.release(); offset.release(); total.release(); pstate.release(); pcost.release(); paction.release();
     pkey.release(); h_total.release();
     if (ready) cudaEventDestroy(ready);
+    if (drained) cudaEventDestroy(drained);
     if (st) cudaStreamDestroy(st);
-    ready = nullptr;
+    ready = drained = nullptr;
     st = nullptr;
   }
 };
@@ -162,7 +165,8 @@ struct mplx_ctx {
   PinBuf<int32_t> h_count, h_action, h_lattice;
   PinBuf<double> h_cost;
   PinBuf<uint64_t> h_key;
-  ChunkBufs cb[2];
+  ChunkBufs cb[kPackBufs];
+  cudaStream_t d2h_stream = nullptr;  // result copies of the packed pipeline
   FxQueue fxq;
   EdgeBufs eb;
   int64_t launches = 0;

@@ -94,17 +94,26 @@ extern "C" int mplx_expand_packed(mplx_ctx *c, const mplx_waypoint *nodes, int n
   if (nU > 65535) return fail(MPLX_ERR_ARG, "action ids are uint16 in the packed stream");
   const int drop_inf = (flags & MPLX_PACK_DROP_INF) ? 1 : 0;
 
-  // successor slots per pipeline chunk (2 chunks in flight); MPLX_PACK_CHUNK_LOG2 overrides for tuning
-  int chunk_log2 = 20;
+  // Pipeline: chunks of ~2^21 successor slots cycle through kPackBufs buffer sets.  Two compute streams
+  // alternate (copy-in of chunk k+1 overlaps the kernels of chunk k), and a third stream carries every
+  // device-to-host copy, so a chunk's results cross PCIe while the next chunks are already being expanded:
+  // the copy engine — the longest stage — stays busy.  The host has to learn a chunk's record count before it
+  // can size that chunk's copies; it waits for chunk k-2's count after queueing chunk k.
+  // Chunks of 2^21 slots: 2^20 pays ~7 % more in per-copy overhead (four copies per chunk), 2^22 leaves too
+  // few chunks to overlap at the bench's batch size.  MPLX_PACK_CHUNK_LOG2 overrides for tuning.
+  int chunk_log2 = 21;
   if (const char *e = getenv("MPLX_PACK_CHUNK_LOG2")) chunk_log2 = atoi(e) < 10 ? 10 : (atoi(e) > 26 ? 26 : atoi(e));
   int chunk = (1 << chunk_log2) / nU;
   if (chunk < 1) chunk = 1;
   if (chunk > n_nodes) chunk = n_nodes;
   const size_t slots = (size_t)chunk * nU;
-  for (int b = 0; b < 2; b++) {
+  if (!c->d2h_stream) CU(cudaStreamCreateWithFlags(&c->d2h_stream, cudaStreamNonBlocking));
+  for (int b = 0; b < 2; b++)
+    if (!c->cb[b].st) CU(cudaStreamCreateWithFlags(&c->cb[b].st, cudaStreamNonBlocking));
+  for (int b = 0; b < kPackBufs; b++) {
     ChunkBufs &B = c->cb[b];
-    if (!B.st) CU(cudaStreamCreateWithFlags(&B.st, cudaStreamNonBlocking));
     if (!B.ready) CU(cudaEventCreateWithFlags(&B.ready, cudaEventDisableTiming));
+    if (!B.drained) CU(cudaEventCreateWithFlags(&B.drained, cudaEventDisableTiming));
     // successor waypoints are produced only when the caller wants state fields: a keys-only stream
     // (state == NULL: the host rebuilds coordinates of NEW states itself, graph_search.h:84-88) never
     // writes the 112-byte records to HBM
@@ -125,8 +134,9 @@ extern "C" int mplx_expand_packed(mplx_ctx *c, const mplx_waypoint *nodes, int n
   // with state records; SM stores over PCIe do not reach the copy engines' rate.  Staged copies it is.)
   std::vector<long long> bases(nchunks, 0);
   long long written = 0;
-  auto drain = [&](int k) -> int {  // results of chunk k: wait for its total, then stream them to the host
-    ChunkBufs &B = c->cb[k & 1];
+  cudaStream_t ds = c->d2h_stream;
+  auto drain = [&](int k) -> int {  // results of chunk k: wait for its count, then queue its copies on ds
+    ChunkBufs &B = c->cb[k % kPackBufs];
     const int off = k * chunk;
     const int m = n_nodes - off < chunk ? n_nodes - off : chunk;
     CU(cudaEventSynchronize(B.ready));
@@ -135,41 +145,46 @@ extern "C" int mplx_expand_packed(mplx_ctx *c, const mplx_waypoint *nodes, int n
     if (written + tot > out->capacity)
       return fail(MPLX_ERR_ARG, "packed output capacity %lld too small (need > %lld)", (long long)out->capacity,
                   written + tot);
-    CU(cudaMemcpyAsync(out->count + off, B.kcount.p, sizeof(int32_t) * m, cudaMemcpyDeviceToHost, B.st));
-    CU(cudaMemcpyAsync(out->offset + off, B.offset.p, sizeof(long long) * m, cudaMemcpyDeviceToHost, B.st));
+    CU(cudaMemcpyAsync(out->count + off, B.kcount.p, sizeof(int32_t) * m, cudaMemcpyDeviceToHost, ds));
+    CU(cudaMemcpyAsync(out->offset + off, B.offset.p, sizeof(long long) * m, cudaMemcpyDeviceToHost, ds));
     if (tot > 0) {
       if (out->state)
-        CU(cudaMemcpyAsync(out->state + written * nstate, B.pstate.p, sizeof(double) * tot * nstate, cudaMemcpyDeviceToHost, B.st));
-      if (out->cost) CU(cudaMemcpyAsync(out->cost + written, B.pcost.p, sizeof(double) * tot, cudaMemcpyDeviceToHost, B.st));
-      if (out->action) CU(cudaMemcpyAsync(out->action + written, B.paction.p, sizeof(uint16_t) * tot, cudaMemcpyDeviceToHost, B.st));
-      if (out->key) CU(cudaMemcpyAsync(out->key + written, B.pkey.p, sizeof(uint64_t) * tot, cudaMemcpyDeviceToHost, B.st));
+        CU(cudaMemcpyAsync(out->state + written * nstate, B.pstate.p, sizeof(double) * tot * nstate, cudaMemcpyDeviceToHost, ds));
+      if (out->cost) CU(cudaMemcpyAsync(out->cost + written, B.pcost.p, sizeof(double) * tot, cudaMemcpyDeviceToHost, ds));
+      if (out->action) CU(cudaMemcpyAsync(out->action + written, B.paction.p, sizeof(uint16_t) * tot, cudaMemcpyDeviceToHost, ds));
+      if (out->key) CU(cudaMemcpyAsync(out->key + written, B.pkey.p, sizeof(uint64_t) * tot, cudaMemcpyDeviceToHost, ds));
     }
+    CU(cudaEventRecord(B.drained, ds));
     written += tot;
     return MPLX_OK;
   };
 
+  const int ahead = 2;  // chunks queued before the host waits for a record count
   for (int k = 0; k < nchunks; k++) {
-    ChunkBufs &B = c->cb[k & 1];
+    ChunkBufs &B = c->cb[k % kPackBufs];
+    cudaStream_t st = c->cb[k & 1].st;
     const int off = k * chunk;
     const int m = n_nodes - off < chunk ? n_nodes - off : chunk;
-    // stream order on B.st guarantees chunk k-2's D2H copies have left these buffers
-    CU(cudaMemcpyAsync(B.nodes.p, nodes + off, sizeof(mplx_waypoint) * m, cudaMemcpyHostToDevice, B.st));
+    if (k >= kPackBufs) CU(cudaStreamWaitEvent(st, B.drained, 0));  // chunk k-kPackBufs has left these buffers
+    CU(cudaMemcpyAsync(B.nodes.p, nodes + off, sizeof(mplx_waypoint) * m, cudaMemcpyHostToDevice, st));
     mplx_succ_out d{B.count.p, out->state ? B.succ.p : nullptr, B.cost.p, B.action.p, B.key.p, nullptr};
     CU(B.fxq.reserve((size_t)m * nU));
-    CU(mplx::launch_expand(c->P, B.nodes.p, m, d, B.st, c->force_seq, &B.fxq.view));
-    CU(cudaMemsetAsync(B.total.p, 0, sizeof(long long), B.st));
-    mplx::pack_kernel<<<(m + 7) / 8, 256, 0, B.st>>>(m, nU, dim, control, drop_inf, B.count.p,
-                                                     out->state ? B.succ.p : nullptr, B.cost.p, B.action.p, B.key.p, B.total.p, B.kcount.p, B.offset.p,
-                                                     out->state ? B.pstate.p : nullptr, out->cost ? B.pcost.p : nullptr,
-                                                     out->action ? B.paction.p : nullptr, out->key ? B.pkey.p : nullptr);
+    CU(mplx::launch_expand(c->P, B.nodes.p, m, d, st, c->force_seq, &B.fxq.view));
+    CU(cudaMemsetAsync(B.total.p, 0, sizeof(long long), st));
+    mplx::pack_kernel<<<(m + 7) / 8, 256, 0, st>>>(m, nU, dim, control, drop_inf, B.count.p,
+                                                   out->state ? B.succ.p : nullptr, B.cost.p, B.action.p, B.key.p, B.total.p, B.kcount.p, B.offset.p,
+                                                   out->state ? B.pstate.p : nullptr, out->cost ? B.pcost.p : nullptr,
+                                                   out->action ? B.paction.p : nullptr, out->key ? B.pkey.p : nullptr);
     CU(cudaGetLastError());
     c->launches += 2;
-    CU(cudaMemcpyAsync(B.h_total.p, B.total.p, sizeof(long long), cudaMemcpyDeviceToHost, B.st));
-    CU(cudaEventRecord(B.ready, B.st));
-    if (k >= 1)
-      if (int r = drain(k - 1)) return r;
+    CU(cudaMemcpyAsync(B.h_total.p, B.total.p, sizeof(long long), cudaMemcpyDeviceToHost, st));
+    CU(cudaEventRecord(B.ready, st));
+    if (k >= ahead)
+      if (int r = drain(k - ahead)) return r;
   }
-  if (int r = drain(nchunks - 1)) return r;
+  for (int k = nchunks - ahead < 0 ? 0 : nchunks - ahead; k < nchunks; k++)
+    if (int r = drain(k)) return r;
+  CU(cudaStreamSynchronize(ds));
   CU(cudaStreamSynchronize(c->cb[0].st));
   CU(cudaStreamSynchronize(c->cb[1].st));
   // offsets were reserved per chunk: make them global

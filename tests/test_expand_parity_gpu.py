@@ -305,15 +305,26 @@ def _check_packed(env, sc, orc, nodes, drop_inf):
 
 def test_packed_stream_matches_oracle():
     """mplx_expand_packed: dense state/cost/action/key records, with and without +inf successors,
-    across several pipeline chunks (60k nodes > 19k-node chunks)."""
+    in one chunk and across more pipeline chunks than there are buffer sets (MPLX_PACK_CHUNK_LOG2=18:
+    60k nodes x 27 = 6.2 chunks of 2^18 slots over 4 buffer sets)."""
+    import os
+
     import scenarios as S
 
     for sc, n in ((S.scaled(S.cfg_headline(), 96), 60000), (S.scaled(S.cfg3(), 64), 9000), (S.scaled(S.cfg4(), 64), 3000)):
         nodes = sc.frontier(n, seed=21)
         orc = ob.OracleEnv.from_scenario(sc).expand(nodes, nthreads=8, lattice=False)
         env = gpu_env(sc)
-        for drop in (False, True):
-            _check_packed(env, sc, orc, nodes, drop)
+        for chunk_log2 in (None, "18"):
+            if chunk_log2 is None:
+                os.environ.pop("MPLX_PACK_CHUNK_LOG2", None)
+            else:
+                os.environ["MPLX_PACK_CHUNK_LOG2"] = chunk_log2
+            try:
+                for drop in (False, True):
+                    _check_packed(env, sc, orc, nodes, drop)
+            finally:
+                os.environ.pop("MPLX_PACK_CHUNK_LOG2", None)
     # 2-D, pageable buffers, tiny and empty batches
     c = fixtures.corridor()
     from scenarios import Scenario
