@@ -99,7 +99,7 @@ struct FxWords {
 };
 
 template <int DIM, int ORD, int UNR, bool REGION>
-__device__ __forceinline__ void fx_issue(const EnvParams &P, const unsigned *__restrict__ base, unsigned long long keep,
+__device__ __forceinline__ void fx_issue(const EnvParams &P, const unsigned *__restrict__ base,
                                          const double (&C)[DIM][ORD + 1], double dt, double &t, FxWords<UNR> &G) {
   G.uncm = 0;
 #pragma unroll
@@ -127,10 +127,10 @@ __device__ __forceinline__ void fx_issue(const EnvParams &P, const unsigned *__r
     if (REGION) {
       if (inside && !ub) {
         const unsigned wi = (unsigned)idx >> 5;
-        G.w[j] = ldg_keep(base + 2 * wi, keep) | ~ldg_keep(P.region_bits + wi, keep);
+        G.w[j] = __ldg(base + 2 * wi) | ~__ldg(P.region_bits + wi);
       }
     } else {
-      if (inside) G.w[j] = ldg_keep(base + ((((unsigned)idx >> 4) & ~1u) | ub), keep);
+      if (inside) G.w[j] = __ldg(base + ((((unsigned)idx >> 4) & ~1u) | ub));
     }
     t += dt;  // the reference's running sum (env_map.h:99)
   }
@@ -153,18 +153,17 @@ template <int DIM, int ORD, int UNR, bool REGION>
 __device__ __forceinline__ int fx_traverse(const EnvParams &P, const double (&C)[DIM][ORD + 1], double dt, int count,
                                            unsigned long long &amask, bool &full) {
   const unsigned *__restrict__ base = reinterpret_cast<const unsigned *>(P.occ2);
-  const unsigned long long keep = l2_keep_policy();
   amask = 0;
   full = false;
   double t = 0;
   int left = count, k0 = 0;
   FxWords<UNR> A, B;
-  fx_issue<DIM, ORD, UNR, REGION>(P, base, keep, C, dt, t, A);
+  fx_issue<DIM, ORD, UNR, REGION>(P, base, C, dt, t, A);
   for (;;) {
     unsigned amb;
     int st;
     // ---- group in A; group after it goes to B ----
-    if (left > UNR) fx_issue<DIM, ORD, UNR, REGION>(P, base, keep, C, dt, t, B);
+    if (left > UNR) fx_issue<DIM, ORD, UNR, REGION>(P, base, C, dt, t, B);
     st = fx_decide<UNR>(A, left, amb);
     if (st == 2) return 1;
     if (amb) {
@@ -174,7 +173,7 @@ __device__ __forceinline__ int fx_traverse(const EnvParams &P, const double (&C)
     left -= UNR;
     k0 += UNR;
     // ---- group in B; group after it goes to A ----
-    if (left > UNR) fx_issue<DIM, ORD, UNR, REGION>(P, base, keep, C, dt, t, A);
+    if (left > UNR) fx_issue<DIM, ORD, UNR, REGION>(P, base, C, dt, t, A);
     st = fx_decide<UNR>(B, left, amb);
     if (st == 2) return 1;
     if (amb) {
