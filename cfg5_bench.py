@@ -55,6 +55,13 @@ def run(sc, grid, local: int, n_queries: int = 4096, max_expand: int = 300, min_
         return a
 
     res_dtype = [("valid", "i4"), ("cost", "f8"), ("expanded", "i4"), ("n_closed", "i4"), ("n_actions", "i4")]
+    # host threads of this rank's planner: its share of the CPUs the job may use (the ranks of one box share the
+    # cgroup quota; every rank spawning a thread per CPU oversubscribed an 8-rank run 8x), within its affinity mask
+    import os
+
+    local_world = int(os.environ.get("LOCAL_WORLD_SIZE", str(world))) if on else 1
+    n_threads = max(1, min(len(os.sched_getaffinity(0)), S.effective_cpus() // max(1, local_world)))
+    os.environ["MPLH_THREADS"] = str(n_threads)
     sl = sharding.shard_slice(len(q), rank, world)
     session = planner.BatchPlanner(make(q["start"]["pos"][0], q["goal"]["pos"][0])) if sl.stop > sl.start else None
 
@@ -89,7 +96,7 @@ def run(sc, grid, local: int, n_queries: int = 4096, max_expand: int = 300, min_
         "n_gpus": world, "scaling": "strong", "value": cnt["expansions"] / secs, "unit": "expansions/s",
         "expansions": int(cnt["expansions"]), "seconds": secs, "passes": len(passes),
         "first_pass_seconds": first_seconds, "session_close_seconds": cnt["t_release_max"], "lockstep_iterations_sum": int(cnt["iterations"]),
-        "queries": n_queries, "queries_solved": int(res["valid"].sum()), "host_threads_per_rank": S.effective_cpus(),
+        "queries": n_queries, "queries_solved": int(res["valid"].sum()), "host_threads_per_rank": n_threads,
         "phase_seconds_max": {"pop": cnt["t_pop_max"], "device+pcie": cnt["t_device_max"], "relax": cnt["t_relax_max"]},
         "what": "sum of node expansions / max over ranks of MultiQueryPlanner::plan wall time (device expansion + PCIe + "
                 "host A* bookkeeping) for one pass over the query set in a session whose search states are recycled from "
