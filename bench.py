@@ -59,7 +59,8 @@ def parse():
     ap.add_argument("--no-multi-query", action="store_true", help="skip the cfg5 leg (sharded many-query planning)")
     ap.add_argument("--no-replay", action="store_true", help="skip the replay-frontier batch sweep")
     ap.add_argument("--mq-queries", type=int, default=4096)
-    ap.add_argument("--mq-max-expand", type=int, default=300)
+    ap.add_argument("--mq-max-expand", type=int, default=1000)
+    ap.add_argument("--mq-eps", type=float, default=2.0, help="cfg5: the planner's setEpsilon (weighted A*)")
     ap.add_argument("--kernel", type=int, default=0,
                     help="0 = auto, 1 = literal loop, 2 = register, 3 = flat, 4 = dealing, 5 = fixed-point")
     return ap.parse_args()
@@ -304,7 +305,7 @@ def run_cfg5_workload(args, rank, local, world):
         def one(k):
             a = planner.make_args(3, sc5.control, grid, sc5.dim_cells, sc5.origin, sc5.res, sc5.U,
                                   start=dict(pos=q["start"]["pos"][k]), goal=dict(pos=q["goal"]["pos"][k]), v_max=sc5.v_max,
-                                  a_max=sc5.a_max, T=sc5.T, w=sc5.w, max_num=args.mq_max_expand)
+                                  a_max=sc5.a_max, T=sc5.T, w=sc5.w, max_num=args.mq_max_expand, eps=args.mq_eps)
             return pb.plan_reference(a)
 
         vals = []
@@ -317,7 +318,7 @@ def run_cfg5_workload(args, rank, local, world):
         emit({"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus,
                           "steps": args.steps, "warmup": args.warmup, "ms_per_step": None, "higher_is_better": True,
                           "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                          "config": {"workload": "cfg5", "queries": args.mq_queries, "max_expand": args.mq_max_expand,
+                          "config": {"workload": "cfg5", "queries": args.mq_queries, "max_expand": args.mq_max_expand, "epsilon": args.mq_eps,
                                      "map": "512x512x512 @0.1 m int8", "control": "0x07", "primitives_per_node": 125},
                           "cpu_baseline": {"value": v, "unit": UNIT, "cores": nt, "kind": "reference",
                                            "sample": f"{n} of the {args.mq_queries} queries per step, one reference MapPlanner::plan per "
@@ -342,7 +343,7 @@ def run_cfg5_workload(args, rank, local, world):
     for it in range(args.warmup + args.steps):
         if it == args.warmup and rank == 0:
             sampler.start()
-        r = cfg5_bench.run(sc5, grid, local, n_queries=args.mq_queries, max_expand=args.mq_max_expand,
+        r = cfg5_bench.run(sc5, grid, local, n_queries=args.mq_queries, max_expand=args.mq_max_expand, eps=args.mq_eps,
                            ref_queries=32 if (world == 1 and it == 0) else 0)
         if it >= args.warmup:
             runs.append(r)
@@ -355,7 +356,7 @@ def run_cfg5_workload(args, rank, local, world):
         line = {"metric": METRIC, "value": v, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": 1e3 * secs, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
                 "data": "synthetic",
-                "config": {"workload": "cfg5", "queries": args.mq_queries, "max_expand": args.mq_max_expand,
+                "config": {"workload": "cfg5", "queries": args.mq_queries, "max_expand": args.mq_max_expand, "epsilon": args.mq_eps,
                            "map": "512x512x512 @0.1 m int8", "control": "0x07", "primitives_per_node": 125,
                            "parallelism": f"queries sharded over {world} rank(s), map broadcast once, results all-gathered"},
                 "clocks": clocks, "multi_query": runs[-1], "reference_check": (first if args.warmup else runs[0]).get("reference"),
@@ -643,7 +644,7 @@ def main():
         grid5 = sharding.broadcast_array(sc.grid() if rank == 0 else None, src=0)  # the one set-up collective
         env.close()
         torch.cuda.empty_cache()
-        multi_query = cfg5_bench.run(sc5, grid5, local, n_queries=args.mq_queries, max_expand=args.mq_max_expand,
+        multi_query = cfg5_bench.run(sc5, grid5, local, n_queries=args.mq_queries, max_expand=args.mq_max_expand, eps=args.mq_eps,
                                      ref_queries=32 if world == 1 else 0)
 
     if rank != 0:

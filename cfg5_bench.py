@@ -33,8 +33,8 @@ def make_queries(sc, n_queries: int, min_dist: float, seed: int = 5):
     return q
 
 
-def run(sc, grid, local: int, n_queries: int = 4096, max_expand: int = 300, min_dist: float = 20.0,
-        ref_queries: int = 32, repeat: int = 2):
+def run(sc, grid, local: int, n_queries: int = 4096, max_expand: int = 1000, min_dist: float = 20.0,
+        ref_queries: int = 32, repeat: int = 2, eps: float = 2.0):
     """Plan the query set sharded over the ranks of the default process group (or alone).
     Returns the result dict on every rank (counters are reduced).  `repeat` passes over the same set in one
     planner session: the first allocates the search states, the others recycle them (the fastest is reported)."""
@@ -50,7 +50,7 @@ def run(sc, grid, local: int, n_queries: int = 4096, max_expand: int = 300, min_
 
     def make(start, goal):
         a = planner.make_args(3, sc.control, grid, sc.dim_cells, sc.origin, sc.res, sc.U, start=dict(pos=start),
-                              goal=dict(pos=goal), v_max=sc.v_max, a_max=sc.a_max, T=sc.T, w=sc.w, max_num=max_expand)
+                              goal=dict(pos=goal), v_max=sc.v_max, a_max=sc.a_max, T=sc.T, w=sc.w, max_num=max_expand, eps=eps)
         a.device = local
         return a
 
@@ -91,12 +91,12 @@ def run(sc, grid, local: int, n_queries: int = 4096, max_expand: int = 300, min_
     cnt["t_release_max"] = t_rel
     secs = cnt["seconds_max"]
     out = {
-        "workload": f"cfg5: {n_queries} start/goal pairs >= {min_dist} m apart, {sc.name}, <= {max_expand} expansions/query, "
+        "workload": f"cfg5: {n_queries} start/goal pairs >= {min_dist} m apart, {sc.name}, setEpsilon({eps:g}), <= {max_expand} expansions/query, "
                     f"queries sharded over {world} rank(s)",
         "n_gpus": world, "scaling": "strong", "value": cnt["expansions"] / secs, "unit": "expansions/s",
         "expansions": int(cnt["expansions"]), "seconds": secs, "passes": len(passes),
         "first_pass_seconds": first_seconds, "session_close_seconds": cnt["t_release_max"], "lockstep_iterations_sum": int(cnt["iterations"]),
-        "queries": n_queries, "queries_solved": int(res["valid"].sum()), "host_threads_per_rank": n_threads,
+        "queries": n_queries, "queries_solved": int(res["valid"].sum()), "epsilon": eps, "max_expand": max_expand, "host_threads_per_rank": n_threads,
         "phase_seconds_max": {"pop": cnt["t_pop_max"], "device+pcie": cnt["t_device_max"], "relax": cnt["t_relax_max"]},
         "what": "sum of node expansions / max over ranks of MultiQueryPlanner::plan wall time (device expansion + PCIe + "
                 "host A* bookkeeping) for one pass over the query set in a session whose search states are recycled from "

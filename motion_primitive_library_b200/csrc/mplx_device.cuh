@@ -60,16 +60,23 @@ __device__ __forceinline__ double normalize_angle(double a) {
 
 // boost::hash_combine, 64-bit size_t, Boost 1.56-1.80 (hash_combine_impl(uint64&,uint64));
 // boost::hash<int> = sign-extending cast.  waypoint.h:98..121 call sites.
-__device__ __forceinline__ void hash_combine(uint64_t &h, int v) {
+// Split in the part that depends on the value alone (two of the three 64-bit multiplications; computed once
+// per lattice id and shared by every key the id enters) and the part that folds it into the running hash.
+__device__ __forceinline__ uint64_t hash_premix(int v) {
   uint64_t k = (uint64_t)(int64_t)v;
   const uint64_t m = 0xc6a4a7935bd1e995ULL;
   k *= m;
   k ^= k >> 47;
   k *= m;
+  return k;
+}
+__device__ __forceinline__ void hash_fold(uint64_t &h, uint64_t k) {
+  const uint64_t m = 0xc6a4a7935bd1e995ULL;
   h ^= k;
   h *= m;
   h += 0xe6546b64ULL;
 }
+__device__ __forceinline__ void hash_combine(uint64_t &h, int v) { hash_fold(h, hash_premix(v)); }
 
 // ---- exact IEEE quotients and roundings without DDIV / round() / F2I ----------------------
 // The reference computes  k = (int)std::round(RN(x / r) [- 0.5])  (waypoint.h:97-121,

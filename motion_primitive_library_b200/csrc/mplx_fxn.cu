@@ -30,6 +30,7 @@ struct FxnRow {
   double mv;          // max_vel (primitive.h:353-363)
   double J;           // Primitive1D::J (primitive.h:92-122)
   int id[4];          // lattice ids of pos, vel, acc, jrk (waypoint.h:96-110)
+  uint64_t km[ORD];   // their value-only hash parts (hash_premix), folded into a key per primitive
   unsigned char f0, f1, f2, pad[5];  // flags written by part 0 / 1 / 2
 };
 // part 0: kSame (c5 == pos, env_map.h:163), kReach (range of the fixed-point bound)
@@ -42,8 +43,11 @@ struct FxnWork {
   unsigned slot;    // output slot of the successor
 };
 
+constexpr int kMaxNpb = kThreads / 9;  // a position control set has >= 3^2 members
 struct FxnShared {
-  uint64_t hcurr[kThreads];
+  uint64_t hcurr[kMaxNpb];         // hash_value(curr) of the CTA's nodes
+  uint64_t ckm[kMaxNpb * 3 * 4];   // hash_premix of their own lattice ids, [node][axis*ORD + field]
+  double tcurr[kMaxNpb];           // curr.t
   FxnWork work[kThreads];      // primitives that need sampling, longest loops first
   unsigned char owner[kThreads];  // their phase-A threads (node, control)
   uint32_t vbits[8];
@@ -76,13 +80,25 @@ expand_fxn_kernel(const __grid_constant__ EnvParams P, const mplx_waypoint *__re
   {
     const double T = P.T;
     const int R = npb * n_rows;
-    const int total = 3 * R + npb;
-    for (int it = threadIdx.x; it < total; it += kThreads) {
-      if (it >= 3 * R) {
-        const int j = it - 3 * R;
-        if (node0 + j < n_nodes) S.hcurr[j] = curr_hash<DIM, ORD>(nodes + node0 + j);
-        continue;
+    // The warp with the fewest row items also hashes the nodes themselves; its loads go out first so that they
+    // overlap the row work (mplx_waypoint = pos[3], vel[3], acc[3], jrk[3], yaw, t: field f of axis a is double 3f+a).
+    // (a warp without row items when there is one)
+    const int tail = (3 * R) & (kThreads - 1);
+    const bool hash_warp = warp == (tail <= kThreads - 32 ? kWarps - 1 : tail >> 5);
+    double cx[2] = {0.0, 0.0}, ct = 0.0;
+    auto load_ids = [&] {
+      constexpr int F = DIM * ORD;
+#pragma unroll
+      for (int k = 0; k < 2; k++) {
+        const int q = lane + 32 * k;
+        const int j = q / F, af = q - j * F;
+        if (q < npb * F && node0 + j < n_nodes)
+          cx[k] = reinterpret_cast<const double *>(nodes + node0 + j)[(af % ORD) * 3 + af / ORD];
       }
+      if (lane < npb && node0 + lane < n_nodes) ct = nodes[node0 + lane].t;
+    };
+    if (hash_warp) load_ids();
+    for (int it = threadIdx.x; it < 3 * R; it += kThreads) {
       const int part = it >= 2 * R ? 2 : (it >= R ? 1 : 0);
       const int r = it - part * R;
       const int nl = (r * inv_rows) >> 20;  // r / n_rows
@@ -98,7 +114,9 @@ expand_fxn_kernel(const __grid_constant__ EnvParams P, const mplx_waypoint *__re
         const double pw3T = (T * T) * T, pw4T = pw3T * T;
         const double pos = ax.template p<true>(T, pw3T, pw4T);
         Rw.st[0] = pos;
-        Rw.id[0] = lattice_id(pos, 0.01, 100.0);
+        const int id = lattice_id(pos, 0.01, 100.0);
+        Rw.id[0] = id;
+        Rw.km[0] = hash_premix(id);
         unsigned char f = 0;
         if (ax.c5 == pos) f |= kSame;
         if ((fabs(ax.c5) + fabs(origin)) * P.rinv < kFxRange) f |= kReach;
@@ -108,7 +126,9 @@ expand_fxn_kernel(const __grid_constant__ EnvParams P, const mplx_waypoint *__re
         const double pw3T = (T * T) * T;
         const double vel = ax.v(T, pw3T);
         Rw.st[1] = vel;
-        Rw.id[1] = ORD >= 2 ? lattice_id(vel, 0.1, 10.0) : 0;
+        const int id = ORD >= 2 ? lattice_id(vel, 0.1, 10.0) : 0;
+        Rw.id[1] = id;
+        if (ORD >= 2) Rw.km[ORD >= 2 ? 1 : 0] = hash_premix(id);
         const double mv = ax.max_vel(T);
         Rw.mv = mv;
         // validate_xxx (primitive.h:482-496): a limit <= 0 passes
@@ -121,10 +141,40 @@ expand_fxn_kernel(const __grid_constant__ EnvParams P, const mplx_waypoint *__re
         Rw.st[3] = jrk;
         Rw.id[2] = ORD >= 3 ? lattice_id(acc, 0.1, 10.0) : 0;
         Rw.id[3] = ORD >= 4 ? lattice_id(jrk, 0.1, 10.0) : 0;
+        if (ORD >= 3) Rw.km[ORD >= 3 ? 2 : 0] = hash_premix(Rw.id[2]);
+        if (ORD >= 4) Rw.km[ORD >= 4 ? 3 : 0] = hash_premix(Rw.id[3]);
         unsigned char f = kAcc | kJrk;
         if (ORD >= 3 && P.a_max > 0 && ax.max_acc(T) > P.a_max) f &= ~kAcc;
         if (ORD >= 4 && P.j_max > 0 && ax.max_jrk(T) > P.j_max) f &= ~kJrk;
         Rw.f2 = f;
+      }
+    }
+    // hash_value(curr) of the CTA's nodes (waypoint.h:93-125): the lattice ids were loaded above; one exact
+    // quotient + premix per lane and round, then one lane per node folds them.
+    if (hash_warp) {
+      constexpr int F = DIM * ORD;
+#pragma unroll
+      for (int k = 0; k < 2; k++) {
+        const int q = lane + 32 * k;
+        if (q < npb * F) {
+          const bool is_pos = (q % F) % ORD == 0;
+          S.ckm[q] = hash_premix(lattice_id(cx[k], is_pos ? 0.01 : 0.1, is_pos ? 100.0 : 10.0));
+        }
+      }
+      for (int q = lane + 64; q < npb * F; q += 32) {
+        const int j = q / F, af = q - j * F;
+        const bool is_pos = af % ORD == 0;
+        const double x = node0 + j < n_nodes ? reinterpret_cast<const double *>(nodes + node0 + j)[(af % ORD) * 3 + af / ORD] : 0.0;
+        S.ckm[q] = hash_premix(lattice_id(x, is_pos ? 0.01 : 0.1, is_pos ? 100.0 : 10.0));
+      }
+      __syncwarp();
+      for (int j = lane; j < npb; j += 32) {
+        uint64_t h = 0;
+#pragma unroll
+        for (int af = 0; af < F; af++) hash_fold(h, S.ckm[j * F + af]);
+        S.hcurr[j] = h;
+        if (j == lane) S.tcurr[j] = ct;
+        else if (node0 + j < n_nodes) S.tcurr[j] = nodes[node0 + j].t;
       }
     }
   }
@@ -160,10 +210,8 @@ expand_fxn_kernel(const __grid_constant__ EnvParams P, const mplx_waypoint *__re
 #pragma unroll
       for (int a = 0; a < DIM; a++) {
         const FxnRow<ORD> &Rw = rows[ra[a]];
-        hash_combine(key, Rw.id[0]);
-        if (ORD >= 2) hash_combine(key, Rw.id[1]);
-        if (ORD >= 3) hash_combine(key, Rw.id[2]);
-        if (ORD >= 4) hash_combine(key, Rw.id[3]);
+#pragma unroll
+        for (int f = 0; f < ORD; f++) hash_fold(key, Rw.km[f]);
       }
     }
   }
@@ -262,7 +310,7 @@ expand_fxn_kernel(const __grid_constant__ EnvParams P, const mplx_waypoint *__re
         }
       }
       tn.yaw = 0.0;
-      tn.t = nodes[ni].t + P.T;  // env_map.h:161
+      tn.t = S.tcurr[nl] + P.T;  // env_map.h:161
       // seven 16-byte stores per record.  (Staging the CTA's records in shared memory for a fully
       // coalesced copy-out was measured: slower on every workload — the extra pass and barrier cost
       // more than the halved sector count saves.)
@@ -517,7 +565,7 @@ bool fxn_supported(const EnvParams &P, int n_nodes) {
   if (!fx_supported(P) || P.n_rows <= 0 || P.nU > kThreads) return false;
   if (P.n_rows * 2 > P.dim * P.nU) return false;
   const int npb = kThreads / P.nU;
-  if (npb * P.n_rows > 255 || npb > kThreads) return false;  // row indices are bytes
+  if (npb * P.n_rows > 255 || npb > kMaxNpb) return false;  // row indices are bytes; node tables of FxnShared
   const size_t smem = (size_t)npb * P.n_rows * 128;
   if (smem > 64 * 1024) return false;
   return (long)n_nodes * P.nU >= 64L * kThreads;
