@@ -351,6 +351,39 @@ int mplx_expand(mplx_ctx *c, const mplx_waypoint *nodes, int n_nodes, const mplx
   if (out->key && !pin_key) CU(c->h_key.reserve(slots));
   if (out->lattice && !pin_lat) CU(c->h_lattice.reserve(slots * MPLX_LATTICE_MAX));
 
+  // Small batches (the one-node get_succ of a planner without speculation, a few dozen nodes with it): the
+  // kernel reads the nodes from, and writes the successors to, pinned host memory directly — one launch and
+  // one wait instead of one copy in, up to six copies out and the wait.  (For large batches SM stores over
+  // PCIe lose against the copy engines: mplx_packed.cu.)
+  static const bool no_zero_copy = getenv("MPLX_NO_ZERO_COPY") != nullptr;  // tuning / A-B
+  if (!no_zero_copy && !c->stats_on && (size_t)n_nodes * nU <= 4096) {
+    const int m = n_nodes;
+    const size_t sm = (size_t)m * nU;
+    const mplx_waypoint *src = nodes;
+    if (!pin_nodes) {
+      memcpy(c->h_nodes.p, nodes, sizeof(mplx_waypoint) * m);
+      src = c->h_nodes.p;
+    }
+    mplx_succ_out d;
+    d.count = pin_count ? out->count : c->h_count.p;
+    d.succ = out->succ ? (pin_succ ? out->succ : c->h_succ.p) : nullptr;
+    d.cost = out->cost ? (pin_cost ? out->cost : c->h_cost.p) : nullptr;
+    d.action = out->action ? (pin_action ? out->action : c->h_action.p) : nullptr;
+    d.key = out->key ? (pin_key ? out->key : c->h_key.p) : nullptr;
+    d.lattice = out->lattice ? (pin_lat ? out->lattice : c->h_lattice.p) : nullptr;
+    CU(c->fxq.reserve(sm));
+    CU(mplx::launch_expand(c->P, src, m, d, st, c->force_seq, &c->fxq.view));
+    c->launches += mplx::fxn_supported(c->P, m) && c->force_seq == 0 ? 2 : 1;
+    CU(cudaStreamSynchronize(st));
+    if (!pin_count) memcpy(out->count, c->h_count.p, sizeof(int32_t) * m);
+    if (out->succ && !pin_succ) memcpy(out->succ, c->h_succ.p, sizeof(mplx_waypoint) * sm);
+    if (out->cost && !pin_cost) memcpy(out->cost, c->h_cost.p, sizeof(double) * sm);
+    if (out->action && !pin_action) memcpy(out->action, c->h_action.p, sizeof(int32_t) * sm);
+    if (out->key && !pin_key) memcpy(out->key, c->h_key.p, sizeof(uint64_t) * sm);
+    if (out->lattice && !pin_lat) memcpy(out->lattice, c->h_lattice.p, sizeof(int32_t) * sm * MPLX_LATTICE_MAX);
+    return MPLX_OK;
+  }
+
   unsigned long long acc_stats[2] = {0, 0};
   for (int off = 0; off < n_nodes; off += chunk) {
     const int m = n_nodes - off < chunk ? n_nodes - off : chunk;

@@ -525,6 +525,7 @@ static cudaError_t launch_fxn_t(const EnvParams &P, const mplx_waypoint *d_nodes
     av.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
     if (cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &av) != cudaSuccess) cudaGetLastError();
   }
+  static const int carve = [] { const char *v = getenv("MPLX_FXN_CARVE"); return v ? atoi(v) : -1; }();  // tuning: % of 228 KB
   static const int unr_env = [] { const char *v = getenv("MPLX_FXN_UNR"); return v ? atoi(v) : 0; }();    // tuning
   static const int minb_env = [] { const char *v = getenv("MPLX_FXN_MINB"); return v ? atoi(v) : 0; }();  // tuning
 #define MPLX_LAUNCH_FXN_S(UNR, MINB, LAT, REGION, SORT)                                                         \
@@ -532,6 +533,11 @@ static cudaError_t launch_fxn_t(const EnvParams &P, const mplx_waypoint *d_nodes
     if (smem > 32 * 1024) { /* static + dynamic may pass the 48 KB default */                                   \
       e = cudaFuncSetAttribute(expand_fxn_kernel<DIM, ORD, UNR, MINB, LAT, REGION, SORT>,                       \
                                cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                         \
+      if (e != cudaSuccess) return e;                                                                           \
+    }                                                                                                           \
+    if (carve >= 0) {                                                                                           \
+      e = cudaFuncSetAttribute(expand_fxn_kernel<DIM, ORD, UNR, MINB, LAT, REGION, SORT>,                       \
+                               cudaFuncAttributePreferredSharedMemoryCarveout, carve);                          \
       if (e != cudaSuccess) return e;                                                                           \
     }                                                                                                           \
     expand_fxn_kernel<DIM, ORD, UNR, MINB, LAT, REGION, SORT><<<grid, kThreads, smem, st>>>(                    \
@@ -544,6 +550,8 @@ static cudaError_t launch_fxn_t(const EnvParams &P, const mplx_waypoint *d_nodes
   } while (0)
   if (region) { if (lat) MPLX_LAUNCH_FXN(4, 4, true, true); else MPLX_LAUNCH_FXN(4, 4, false, true); }
   else if (lat) MPLX_LAUNCH_FXN(4, 4, true, false);
+  else if (unr_env == 8 && minb_env == 3) MPLX_LAUNCH_FXN(8, 3, false, false);
+  else if (unr_env == 4 && minb_env == 3) MPLX_LAUNCH_FXN(4, 3, false, false);
   else if (unr_env == 8) MPLX_LAUNCH_FXN(8, 4, false, false);
   else if (minb_env == 5) MPLX_LAUNCH_FXN(4, 5, false, false);
   else MPLX_LAUNCH_FXN(4, 4, false, false);
