@@ -44,6 +44,15 @@ struct DevBuf {
   }
 };
 
+// a function-local DevBuf that frees itself on every exit path
+template <typename T>
+struct ScopedDevBuf : DevBuf<T> {
+  ScopedDevBuf() = default;
+  ScopedDevBuf(const ScopedDevBuf &) = delete;
+  ScopedDevBuf &operator=(const ScopedDevBuf &) = delete;
+  ~ScopedDevBuf() { this->release(); }
+};
+
 template <typename T>
 struct PinBuf {
   T *p = nullptr;

@@ -320,12 +320,10 @@ static cudaError_t launch_t(const EnvParams &P, const mplx_waypoint *d_nodes, in
   const bool need_vel = YAW || (P.pot != nullptr && P.grad_w != 0.0);
   const int maxns = P.maxn + 1;
   const size_t smem = kWarps * L::warp_bytes(need_vel, maxns);
-  static thread_local size_t configured = 0;  // per template instantiation and host thread
-  if (smem > 48 * 1024 && smem > configured) {
+  if (smem > 48 * 1024) {  // the attribute is per device: set it on every such launch (a host-side call)
     cudaError_t e = cudaFuncSetAttribute(expand_flat_kernel<DIM, ORD, YAW>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    configured = smem;
   }
   expand_flat_kernel<DIM, ORD, YAW><<<grid, kThreads, smem, st>>>(P, d_nodes, n_nodes, npb, o, maxns,
                                                                    need_vel ? 1 : 0);

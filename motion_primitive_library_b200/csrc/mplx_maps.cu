@@ -185,9 +185,9 @@ extern "C" int mplx_update_potential_map(mplx_ctx *c, const double *radius, doub
   }
   cudaStream_t st = c->stream;
   const size_t nvox = c->nvox;
-  DevBuf<uint32_t> src;
-  DevBuf<uint8_t> rank, d_pair;
-  DevBuf<int8_t> d_htab;
+  ScopedDevBuf<uint32_t> src;
+  ScopedDevBuf<uint8_t> rank, d_pair;
+  ScopedDevBuf<int8_t> d_htab;
   int rc = MPLX_OK;
   cudaError_t e = src.reserve((nvox + 31) / 32);
   if (e == cudaSuccess) e = rank.reserve(nvox);
@@ -287,7 +287,7 @@ extern "C" int mplx_set_search_region_path(mplx_ctx *c, const double *path, int 
   cudaStream_t st = c->stream;
   const size_t nvox = c->nvox, nwords = (nvox + 31) / 32;
   const int ncell = (int)(cells.size() / 3);
-  DevBuf<int> d_cells;
+  ScopedDevBuf<int> d_cells;
   CU(c->region.reserve(nwords));
   CU(cudaMemsetAsync(c->region.p, 0, nwords * sizeof(uint32_t), st));
   if (ncell > 0) {

@@ -2011,7 +2011,9 @@ class MultiQueryPlanner {
     pool.run(Q, [&](std::size_t q) {
       if (!envs[q]) envs[q].reset(new QueryEnv(map_util_));
       QueryEnv &e = *envs[q];
-      e.w_ = gpu_->w_; e.v_max_ = gpu_->v_max_; e.dt_ = gpu_->dt_; e.t_max_ = gpu_->t_max_;
+      // every env_base parameter the goal test and the heuristic read (the expansion itself runs on gpu_)
+      e.w_ = gpu_->w_; e.wyaw_ = gpu_->wyaw_; e.v_max_ = gpu_->v_max_; e.a_max_ = gpu_->a_max_; e.j_max_ = gpu_->j_max_;
+      e.yaw_max_ = gpu_->yaw_max_; e.dt_ = gpu_->dt_; e.t_max_ = gpu_->t_max_;
       e.tol_pos_ = gpu_->tol_pos_; e.tol_vel_ = gpu_->tol_vel_; e.tol_acc_ = gpu_->tol_acc_; e.tol_yaw_ = gpu_->tol_yaw_;
       e.set_goal(goals[q]);
       if (ss[q]) ss[q]->reset(eps);
