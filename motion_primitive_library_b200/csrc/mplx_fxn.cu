@@ -61,7 +61,7 @@ template <int DIM, int ORD, int UNR, int MINB, bool LAT, bool REGION, bool SORT>
 __global__ void __launch_bounds__(kThreads, MINB)
 expand_fxn_kernel(const __grid_constant__ EnvParams P, const mplx_waypoint *__restrict__ nodes, int n_nodes, int npb,
                   int inv_nU, int inv_rows, FxAmbRec *__restrict__ amb_q, unsigned *__restrict__ amb_n,
-                  unsigned amb_cap, const __grid_constant__ OutPtrs o) {
+                  unsigned amb_cap, const __grid_constant__ OutPtrs o, int pf_ahead) {
   extern __shared__ __align__(16) unsigned char fx_dyn[];
   FxnRow<ORD> *rows = reinterpret_cast<FxnRow<ORD> *>(fx_dyn);
   __shared__ FxnShared S;
@@ -74,6 +74,14 @@ expand_fxn_kernel(const __grid_constant__ EnvParams P, const mplx_waypoint *__re
   if (SORT) {
     for (int b = threadIdx.x; b < kWarps * 33; b += kThreads) (&S.cnt[0][0])[b] = 0;
     S.work[threadIdx.x].slot = kNoWork;
+  }
+  // The nodes are read once, from DRAM, at the head of every CTA's dependency chain: ask the L2 for the block
+  // of the CTA that starts two waves from now.
+  if (pf_ahead > 0 && threadIdx.x < 16) {
+    const long long first = ((long long)blockIdx.x + pf_ahead) * npb;
+    const char *pfp = reinterpret_cast<const char *>(nodes + first) + 128 * threadIdx.x;
+    if (first < n_nodes && pfp < reinterpret_cast<const char *>(nodes + min((long long)n_nodes, first + npb)))
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(pfp));
   }
 
   // ---- phase A0: rows (three parts each) and node hashes ----
@@ -526,6 +534,7 @@ static cudaError_t launch_fxn_t(const EnvParams &P, const mplx_waypoint *d_nodes
     if (cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &av) != cudaSuccess) cudaGetLastError();
   }
   static const int carve = [] { const char *v = getenv("MPLX_FXN_CARVE"); return v ? atoi(v) : -1; }();  // tuning: % of 228 KB
+  static const int pf_ahead = [] { const char *v = getenv("MPLX_FXN_PREFETCH"); return v ? atoi(v) : 1184; }();  // CTAs ahead (0 = off)
   static const int unr_env = [] { const char *v = getenv("MPLX_FXN_UNR"); return v ? atoi(v) : 0; }();    // tuning
   static const int minb_env = [] { const char *v = getenv("MPLX_FXN_MINB"); return v ? atoi(v) : 0; }();  // tuning
 #define MPLX_LAUNCH_FXN_S(UNR, MINB, LAT, REGION, SORT)                                                         \
@@ -541,7 +550,7 @@ static cudaError_t launch_fxn_t(const EnvParams &P, const mplx_waypoint *d_nodes
       if (e != cudaSuccess) return e;                                                                           \
     }                                                                                                           \
     expand_fxn_kernel<DIM, ORD, UNR, MINB, LAT, REGION, SORT><<<grid, kThreads, smem, st>>>(                    \
-        P, d_nodes, n_nodes, npb, inv_nU, inv_rows, amb_q, amb_n, amb_cap, o);                                  \
+        P, d_nodes, n_nodes, npb, inv_nU, inv_rows, amb_q, amb_n, amb_cap, o, pf_ahead);                        \
   } while (0)
 #define MPLX_LAUNCH_FXN(UNR, MINB, LAT, REGION)                     \
   do {                                                              \

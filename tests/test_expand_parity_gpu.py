@@ -341,3 +341,26 @@ def test_packed_stream_matches_oracle():
             _check_packed(env, sc, orc, nodes, True)
         else:
             assert p["total"] == 0
+
+
+def test_small_batches_zero_copy_equal_large_batches():
+    """mplx_expand runs batches of <= 4096 successor slots zero-copy (the kernel reads and writes pinned host
+    memory, csrc/mplx_api.cu); larger ones go through the staged copies.  The same nodes must give the same
+    records either way, with pageable and with pinned caller arrays."""
+    import scenarios as S
+
+    for sc in (S.scaled(S.cfg_headline(), 64), S.scaled(S.cfg3(), 64)):
+        nodes = sc.frontier(3000, seed=3)
+        env = gpu_env(sc)
+        big = env.expand(nodes, want=WANT)  # 3000 * |U| slots: staged path
+        nU = len(sc.U)
+        for pinned in (False, True):
+            for lo, m in ((0, 1), (17, 4096 // nU), (2900, 7)):
+                g = env.expand(nodes[lo:lo + m], want=WANT, pinned=pinned)
+                np.testing.assert_array_equal(g.count, big.count[lo:lo + m])
+                for i in range(m):
+                    k = int(g.count[i])
+                    a, b = i * nU, (lo + i) * nU
+                    for name in ("succ", "cost", "action", "key"):
+                        x, y = getattr(g, name)[a:a + k], getattr(big, name)[b:b + k]
+                        assert x.tobytes() == y.tobytes(), (name, pinned, lo, m, i)
