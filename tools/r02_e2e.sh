@@ -1,14 +1,14 @@
 #!/bin/bash
+# e2e A/B: packed tests, then bench e2e legs for a list of environment variants
 mkdir -p gpurun_out
 timeout 900 python -m pytest tests/test_expand_parity_gpu.py tests/test_multi_query_gpu.py -m gpu -x -q -k "packed or multi" 2>&1 | tail -4
-for lg in 20 19 21; do
-  MPLX_PACK_CHUNK_LOG2=$lg timeout 600 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-multi-query --no-replay 2>gpurun_out/e2e_$lg.err | tail -1 > gpurun_out/e2e_$lg.json
-  python - gpurun_out/e2e_$lg.json <<'P'
+i=0
+for envs in "$@"; do
+  i=$((i+1))
+  env $envs timeout 600 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-multi-query --no-replay 2>gpurun_out/e2e_$i.err | tail -1 > gpurun_out/e2e_$i.json
+  python - gpurun_out/e2e_$i.json "$envs" <<'P'
 import json,sys
 d=json.loads(open(sys.argv[1]).read().strip().split("\n")[-1])
-print(sys.argv[1], "value", d["value"], "e2e", d["e2e"]["value"], "ms", d["e2e"]["ms_per_step"], "GB/s", d["e2e"]["d2h_gbs"], "state", d["e2e_state_records"]["value"], "full", d["e2e_full_contract"]["value"])
+print(sys.argv[2], "| value", round(d["value"]/1e8,3), "e2e", round(d["e2e"]["value"]/1e8,3), "ms", round(d["e2e"]["ms_per_step"],3), "state", round(d["e2e_state_records"]["value"]/1e7,3), "full", round(d["e2e_full_contract"]["value"]/1e7,3))
 P
 done
-for k in 2 4; do MPLX_DEAL_UNR=$k timeout 600 python bench.py --workload cfg4 --steps 10 --warmup 3 --no-e2e --no-cpu-baseline 2>/dev/null | tail -1 | python -c "
-import json,sys
-d=json.loads(sys.stdin.read().strip().split('\n')[-1]); print('cfg4 unr', $k, d['ms_per_step'])"; done
