@@ -134,7 +134,10 @@ int mplx_set_params(mplx_ctx *ctx, int control, double T, double w, double wyaw,
 
 /* Batched env_map::get_succ with HOST buffers: copies `nodes` to the device, runs the
  * expansion kernel, copies every non-NULL output back (pinned staging inside the ctx),
- * and returns when the results are in the caller's buffers. */
+ * and returns when the results are in the caller's buffers.  Batches of up to 4096 successor
+ * slots (n_nodes * nU) skip the copies: the kernel reads the nodes from and writes the outputs to
+ * pinned host memory directly — the caller's arrays when they come from mplx_host_alloc, else the
+ * ctx's staging buffers — so a single-node get_succ is one launch and one wait. */
 int mplx_expand(mplx_ctx *ctx, const mplx_waypoint *nodes, int n_nodes, const mplx_succ_out *out);
 
 /* Same, but `d_nodes` and the arrays in `out` are DEVICE pointers on the ctx's device.
