@@ -221,18 +221,6 @@ __device__ __forceinline__ void store_waypoint(mplx_waypoint *dst, const mplx_wa
     *dst = w;
   }
 }
-// L2 policy for the words that should stay: the voxel bitmaps (re-read by every CTA of every launch)
-__device__ __forceinline__ unsigned long long l2_keep_policy() {
-  unsigned long long p;
-  asm("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
-  return p;
-}
-__device__ __forceinline__ unsigned ldg_keep(const unsigned *a, unsigned long long pol) {
-  unsigned v;
-  asm volatile("ld.global.nc.L2::cache_hint.u32 %0, [%1], %2;" : "=r"(v) : "l"(a), "l"(pol));
-  return v;
-}
-
 struct OutPtrs {
   int32_t *count;
   mplx_waypoint *succ;
