@@ -56,12 +56,13 @@ struct FxnShared {
   unsigned short cnt[kWarps][33], start[kWarps][33];
 };
 constexpr unsigned kNoWork = 0xffffffffu;
+constexpr int kStageBytes = 32 * (int)sizeof(mplx_waypoint);  // one warp's successor records
 
 template <int DIM, int ORD, int UNR, int MINB, bool LAT, bool REGION, bool SORT>
 __global__ void __launch_bounds__(kThreads, MINB)
 expand_fxn_kernel(const __grid_constant__ EnvParams P, const mplx_waypoint *__restrict__ nodes, int n_nodes, int npb,
                   int inv_nU, int inv_rows, FxAmbRec *__restrict__ amb_q, unsigned *__restrict__ amb_n,
-                  unsigned amb_cap, const __grid_constant__ OutPtrs o, int pf_ahead) {
+                  unsigned amb_cap, const __grid_constant__ OutPtrs o, int pf_ahead, int stage_off) {
   extern __shared__ __align__(16) unsigned char fx_dyn[];
   FxnRow<ORD> *rows = reinterpret_cast<FxnRow<ORD> *>(fx_dyn);
   __shared__ FxnShared S;
@@ -319,10 +320,22 @@ expand_fxn_kernel(const __grid_constant__ EnvParams P, const mplx_waypoint *__re
       }
       tn.yaw = 0.0;
       tn.t = S.tcurr[nl] + P.T;  // env_map.h:161
-      // seven 16-byte stores per record.  (Staging the CTA's records in shared memory for a fully
-      // coalesced copy-out was measured: slower on every workload — the extra pass and barrier cost
-      // more than the halved sector count saves.)
-      store_waypoint(o.succ + (size_t)ni * nU + rank, tn);
+      if (stage_off >= 0) {
+        // the warp's records, compacted in lane order (= slot order), wait in shared memory for the bulk copies below
+        double2 *sp = reinterpret_cast<double2 *>(fx_dyn + stage_off + warp * kStageBytes +
+                                                  __popc(bal & ((1u << lane) - 1u)) * (int)sizeof(mplx_waypoint));
+        sp[0] = make_double2(tn.pos[0], tn.pos[1]);
+        sp[1] = make_double2(tn.pos[2], tn.vel[0]);
+        sp[2] = make_double2(tn.vel[1], tn.vel[2]);
+        sp[3] = make_double2(tn.acc[0], tn.acc[1]);
+        sp[4] = make_double2(tn.acc[2], tn.jrk[0]);
+        sp[5] = make_double2(tn.jrk[1], tn.jrk[2]);
+        sp[6] = make_double2(tn.yaw, tn.t);
+      } else {
+        // 256-bit stores (store_waypoint).  (Staging the CTA's records in shared memory for a coalesced copy-out
+        // by the threads themselves was measured: slower — the extra pass and barrier cost more than it saves.)
+        store_waypoint(o.succ + (size_t)ni * nU + rank, tn);
+      }
     }
     if (emit) {
       slot = (size_t)ni * nU + rank;
@@ -343,6 +356,26 @@ expand_fxn_kernel(const __grid_constant__ EnvParams P, const mplx_waypoint *__re
 #pragma unroll
       for (int a = 1; a < DIM; a++) J += rows[ra[a]].J;
       intrinsic = J + P.w * P.T;
+    }
+  }
+
+  // The records leave through the bulk-copy engine (cp.async.bulk, shared -> global): the emitting lanes of one
+  // node hold consecutive slots, so each node's part of the warp is ONE contiguous copy issued by its first
+  // lane, and the 112-byte records never pass the L1's tag stage (as per-lane stores they cost it as many
+  // look-ups as all voxel loads of the kernel).
+  bool bulk_issued = false;
+  if (stage_off >= 0 && o.succ) {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // my generic-proxy writes, before the async reads
+    __syncwarp();
+    const unsigned peers = __match_any_sync(0xffffffffu, nl) & bal;  // emitting lanes of my node in this warp
+    if (emit && lane == __ffs(peers) - 1) {
+      const unsigned bytes = (unsigned)__popc(peers) * (unsigned)sizeof(mplx_waypoint);
+      const unsigned src = (unsigned)__cvta_generic_to_shared(
+          fx_dyn + stage_off + warp * kStageBytes + __popc(bal & ((1u << lane) - 1u)) * (int)sizeof(mplx_waypoint));
+      asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(o.succ + slot), "r"(src), "r"(bytes)
+                   : "memory");
+      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      bulk_issued = true;
     }
   }
 
@@ -452,6 +485,8 @@ expand_fxn_kernel(const __grid_constant__ EnvParams P, const mplx_waypoint *__re
     verdict = isinf(traverse_loop<DIM, ORD, false>(P, cf, false, mv, ns)) ? 1 : 0;
   }
   if ((verdict == 0 || verdict == 1) && o.cost) __stcs(o.cost + wslot, verdict == 1 ? (double)INFINITY : 0.0 + wintr);
+  // the staging buffer must outlive the copies that read it
+  if (bulk_issued) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
 }
 
 // Exact re-evaluation of the queued primitives: a thread rebuilds the exact quotients from (node,
@@ -515,9 +550,16 @@ static cudaError_t launch_fxn_t(const EnvParams &P, const mplx_waypoint *d_nodes
   const int inv_nU = ((1 << 20) + P.nU - 1) / P.nU;
   const int inv_rows = ((1 << 20) + P.n_rows - 1) / P.n_rows;
   const int rows_bytes = (int)(((size_t)npb * P.n_rows * sizeof(FxnRow<ORD>) + 15) & ~(size_t)15);
-  const size_t smem = (size_t)rows_bytes;
   static const int sort_env = [] { const char *v = getenv("MPLX_FXN_SORT"); return v ? atoi(v) : -1; }();  // tuning
   const bool sort = sort_env >= 0 ? sort_env != 0 : ORD >= 3;
+  // staging of the successor records for the bulk copies (expand_fxn_kernel): destination 16-byte aligned
+  // Measured: 0.518 -> 0.503-0.511 ms on the headline workload, 0.352 -> 0.330 ms on cfg2; with the CTA sort
+  // (JRK-125) 1.84 -> 1.94 ms, so the sorted path keeps the per-lane 256-bit stores.
+  static const int bulk_env = [] { const char *v = getenv("MPLX_FXN_BULK"); return v ? atoi(v) : -1; }();  // tuning / A-B
+  const bool bulk = (bulk_env >= 0 ? bulk_env != 0 : !sort) && o.succ != nullptr &&
+                    (reinterpret_cast<uintptr_t>(o.succ) & 15u) == 0;
+  const int stage_off = bulk ? rows_bytes : -1;
+  const size_t smem = (size_t)rows_bytes + (bulk ? (size_t)kWarps * kStageBytes : 0);
   cudaError_t e = cudaMemsetAsync(amb_n, 0, sizeof(unsigned) * kFxSegments, st);
   if (e != cudaSuccess) return e;
   // Keep the voxel bitmaps in the L2's persisting carve-out: every CTA of every launch re-reads them while
@@ -550,7 +592,7 @@ static cudaError_t launch_fxn_t(const EnvParams &P, const mplx_waypoint *d_nodes
       if (e != cudaSuccess) return e;                                                                           \
     }                                                                                                           \
     expand_fxn_kernel<DIM, ORD, UNR, MINB, LAT, REGION, SORT><<<grid, kThreads, smem, st>>>(                    \
-        P, d_nodes, n_nodes, npb, inv_nU, inv_rows, amb_q, amb_n, amb_cap, o, pf_ahead);                        \
+        P, d_nodes, n_nodes, npb, inv_nU, inv_rows, amb_q, amb_n, amb_cap, o, pf_ahead, stage_off);                        \
   } while (0)
 #define MPLX_LAUNCH_FXN(UNR, MINB, LAT, REGION)                     \
   do {                                                              \
